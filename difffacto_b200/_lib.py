@@ -1,0 +1,112 @@
+"""ctypes binding of the C ABI in include/difffacto_b200.h.
+
+The product path fails loudly if the CUDA library is missing: there is no eager / CPU fallback.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libdifffacto_b200.so")
+
+c_int, c_float, c_void_p, c_size_t, c_u64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64
+
+
+class DenoiserCfg(ctypes.Structure):
+    """struct dfb200_denoiser_cfg"""
+    _fields_ = [("in_channels", c_int), ("out_channels", c_int), ("n_heads", c_int), ("d_head", c_int),
+                ("depth", c_int), ("context_dim", c_int), ("n_class", c_int), ("flags", c_int)]
+
+
+NET_CLASS_COND, NET_CAT_PARAMS_TO_X, NET_CAT_CLASS_TO_X, NET_MASK_UNREFERENCED, NET_INCLUDE_STD = 1, 2, 4, 8, 16
+MODE_FP32, MODE_BF16 = 0, 1
+SCHED_ROWS = 8
+P = c_void_p
+_CFG = ctypes.POINTER(DenoiserCfg)
+
+# name -> (restype, argtypes); must list every symbol declared in include/difffacto_b200.h
+SIGNATURES = {
+    "dfb200_abi_version": (c_int, []),
+    "dfb200_last_error": (ctypes.c_char_p, []),
+    "dfb200_launch_count": (ctypes.c_ulonglong, []),
+    "dfb200_gather_points": (c_int, [c_int] * 4 + [P, P, P, P]),
+    "dfb200_gather_points_grad": (c_int, [c_int] * 4 + [P, P, P, P]),
+    "dfb200_furthest_point_sampling": (c_int, [c_int] * 3 + [P, P, P, P]),
+    "dfb200_query_ball_point": (c_int, [c_int] * 3 + [c_float, c_int, P, P, P, P]),
+    "dfb200_group_points": (c_int, [c_int] * 5 + [P, P, P, P]),
+    "dfb200_group_points_grad": (c_int, [c_int] * 5 + [P, P, P, P]),
+    "dfb200_three_nn": (c_int, [c_int] * 3 + [P, P, P, P, P]),
+    "dfb200_three_interpolate": (c_int, [c_int] * 4 + [P, P, P, P, P]),
+    "dfb200_three_interpolate_grad": (c_int, [c_int] * 4 + [P, P, P, P, P]),
+    "dfb200_chamfer_forward": (c_int, [c_int, c_int, P, c_int, P, P, P, P, P, P]),
+    "dfb200_chamfer_backward": (c_int, [c_int, c_int, P, c_int, P, P, P, P, P, P, P, P]),
+    "dfb200_emd_forward": (c_int, [c_int, c_int] + [P] * 14 + [c_float, c_int, P]),
+    "dfb200_emd_backward": (c_int, [c_int, c_int, P, P, P, P, P, P]),
+    "dfb200_denoiser_num_params": (c_int, [_CFG]),
+    "dfb200_denoiser_packed_bytes": (c_size_t, [_CFG]),
+    "dfb200_denoiser_pack": (c_int, [_CFG, ctypes.POINTER(P), c_int, P, P]),
+    "dfb200_denoiser_workspace_bytes": (c_size_t, [_CFG, c_int, c_int, c_int]),
+    "dfb200_denoiser_forward": (c_int, [_CFG, P, c_int, c_int, c_int] + [P] * 8 + [P, c_size_t, P]),
+    "dfb200_ddpm_step": (c_int, [c_int] * 3 + [P] * 10),
+    "dfb200_q_sample": (c_int, [c_int] * 3 + [P] * 8),
+    "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),
+    "dfb200_ddpm_sample_loop_workspace_bytes": (c_size_t, [_CFG, c_int, c_int, c_int, c_int]),
+    "dfb200_ddpm_sample_loop": (c_int, [_CFG, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_u64, P,
+                                         c_int, P, c_size_t, P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and type every entry point (no CUDA call is made here)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m difffacto_b200.build` "
+                              "(difffacto_b200 has no CPU or eager-PyTorch fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class DFB200Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().dfb200_last_error().decode(errors="replace")
+        raise DFB200Error(f"difffacto_b200 status {rc}: {msg}")
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    # same contract as the reference's CHECK_CUDA / "CPU not supported" (ball_query.cpp:28)
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("CPU not supported: difffacto_b200 ops take CUDA tensors")
+
+
+def require(t, dtype, name):
+    # reference: CHECK_CONTIGUOUS / CHECK_IS_FLOAT / CHECK_IS_INT (include/utils.h:5-25)
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be a {'float' if dtype == torch.float32 else 'int'} tensor")
+
+
+def launch_count():
+    return int(load().dfb200_launch_count())

@@ -1,0 +1,68 @@
+// Packed weight image + workspace layout of the cross-diffusion denoiser, shared by the fp32
+// (CUDA-core) path, the bf16 (tcgen05) path and the sampling loop.
+#pragma once
+#include "common.cuh"
+
+namespace dfb200 {
+
+constexpr int D_MODEL = 128;   // inner_dim = n_heads * d_head
+constexpr int D_FF = 512;      // GEGLU inner dim (mult=4): proj 128 -> 2*512, out 512 -> 128
+constexpr int D_TEMB = 256;    // timestep embedding width (attention.py:357, 393)
+constexpr int D_TEMB_H = 1024; // time_embed GEGLU inner dim
+constexpr int MAX_TOKENS = 4;  // n_class part tokens
+constexpr float LN_EPS = 1e-5f;
+
+// Parameter indices of dfb200_denoiser_pack (see include/difffacto_b200.h)
+enum GlobalParam { P_PRE_W, P_PRE_B, P_POST_W, P_POST_B, P_IN_W, P_IN_B, P_TE0_W, P_TE0_B, P_TE2_W, P_TE2_B,
+                   P_OUT_W, P_OUT_B, N_GLOBAL_PARAMS };
+enum BlockParam { B_N2_W, B_N2_B, B_N3_W, B_N3_B, B_WQ, B_WK, B_WV, B_WO, B_BO, B_W1, B_B1, B_W2, B_B2,
+                  N_BLOCK_PARAMS };
+constexpr int MAX_DEPTH = 16;
+
+struct NetDims {
+  int c_in;    // channels of the concatenated point features (13)
+  int c_out;   // 3
+  int c_ctx;   // key/value input width (522 = context_dim + n_class + 256)
+  int c_ctx_static;  // context_dim + n_class one-hot (266): the part that does not depend on t
+  int depth, n_tok, n_heads, d_head, flags;
+};
+
+// Offsets (in floats) of every fp32 parameter inside the packed image, and (in bytes from the image
+// start) of the bf16 UMMA operand stream consumed by the tcgen05 kernel.
+struct PackLayout {
+  NetDims d;
+  size_t g[N_GLOBAL_PARAMS];
+  size_t blk[MAX_DEPTH][N_BLOCK_PARAMS];
+  size_t freqs;          // 128 sinusoid frequencies (appended by pack, see denoiser_pack)
+  size_t fp32_floats;    // end of the fp32 region
+  size_t tc_stream_off;  // byte offset of the bf16 packet stream (16 B aligned)
+  size_t tc_stream_bytes;
+  size_t total_bytes;
+};
+
+int make_net_dims(const dfb200_denoiser_cfg* cfg, NetDims* d);          // validates cfg
+int make_pack_layout(const dfb200_denoiser_cfg* cfg, PackLayout* L);    // host-side, deterministic
+size_t param_numel(const NetDims& d, bool global, int which);
+
+// ---- workspace ------------------------------------------------------------------------------
+struct Workspace {
+  float* temb_h;  // [B, 1024]
+  float* temb;    // [B, 256]
+  float* kv;      // [B, depth, 2, n_tok, 128]
+  float* x;       // [M, 128]   residual stream (fp32 path)
+  float* q;       // [M, 128]   q, then attention output in place (fp32 path)
+  float* u;       // [M, 512]   GEGLU output (fp32 path)
+  size_t bytes;
+};
+Workspace carve_workspace(const NetDims& d, int mode, int B, int N, void* base);
+
+// ---- launches shared between the paths (denoiser_ctx.cu) --------------------------------------
+// K/V of every block for every sample: kv[b,l,{k,v},j,:] = W{k,v}_l . [ctx[b,:,j] | onehot(j) | temb(t[b])]
+int launch_context_kv(const PackLayout& L, const float* packed, int B, const float* t, const float* ctx,
+                      Workspace& ws, cudaStream_t st);
+
+int denoiser_forward_fp32(const PackLayout& L, const float* packed, int B, int N, const float* x,
+                          const float* anchors, const float* variances, const int* assign,
+                          const float* valid_id, float* eps_out, Workspace& ws, cudaStream_t st);
+
+}  // namespace dfb200

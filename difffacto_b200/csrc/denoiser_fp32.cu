@@ -1,0 +1,407 @@
+// fp32 (CUDA-core FFMA) path of the cross-diffusion denoiser: DFB200_MODE_FP32.
+// This is the numerically faithful mode (fp32 operands and accumulation everywhere, like the
+// reference's fp32 cuBLAS path); the throughput mode is the tcgen05 kernel in denoiser_tc.cu.
+//
+// Reference: python/difffacto/models/diffusions/nets/attention.py
+//   :400-407  point features  [x | anchors | variances | onehot(part)]  (13 channels)
+//   :411-440  proj_in -> pre_norm -> depth x block -> post_norm -> proj_out
+//   :296-306  block (single_attn): x += attn2(norm2(x), ctx, mask);  x += ff(norm3(x))
+//   :179-204  cross attention over the 4 part tokens, masked softmax
+//   :50-57,77-94  GEGLU feed-forward
+// Kernels per forward: embed, then per block {LN+Q GEMM, attention, out-proj+residual GEMM,
+// LN+GEGLU GEMM, FF-out+residual GEMM}, then post_norm+proj_out.  LayerNorm, bias, GEGLU and the
+// residual add are fused into the GEMM prologue/epilogue; the only materialised intermediates are
+// q/o (512 B/token) and the gated FF activation (2 KB/token instead of the reference's 4+2 KB).
+#include <float.h>
+#include <math.h>
+
+#include "denoiser.cuh"
+
+namespace dfb200 {
+
+__device__ __forceinline__ float gelu_erf32(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// embed: 13-channel point features -> proj_in (13 -> 128) -> pre_norm
+// ---------------------------------------------------------------------------------------------
+constexpr int EMB_TOK = 32;  // tokens per CTA
+__global__ void __launch_bounds__(256)
+embed_kernel(int N, long long M, int flags, const float* __restrict__ x, const float* __restrict__ anchors,
+             const float* __restrict__ variances, const int* __restrict__ assign,
+             const float* __restrict__ w_in, const float* __restrict__ b_in,
+             const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out) {
+  __shared__ float feat[EMB_TOK][16];
+  __shared__ float ws[D_MODEL * 13];
+  const long long tok0 = (long long)blockIdx.x * EMB_TOK;
+  for (int i = threadIdx.x; i < D_MODEL * 13; i += blockDim.x) ws[i] = __ldg(w_in + i);
+  // feature f of token p: coalesced along p
+  for (int i = threadIdx.x; i < EMB_TOK * 13; i += blockDim.x) {
+    const int f = i / EMB_TOK, tl = i - f * EMB_TOK;
+    const long long tok = tok0 + tl;
+    float v = 0.f;
+    if (tok < M) {
+      const long long b = tok / N;
+      const int p = (int)(tok - b * N);
+      if (f < 3) v = __ldg(x + (b * 3 + f) * N + p);
+      else if (f < 6) v = __ldg(anchors + (b * 3 + (f - 3)) * N + p);
+      else if (f < 9) {
+        v = __ldg(variances + (b * 3 + (f - 6)) * N + p);
+        if (flags & DFB200_NET_INCLUDE_STD) v = sqrtf(v);
+      } else v = (__ldg(assign + tok) == f - 9) ? 1.f : 0.f;  // F.one_hot(anchor_assignment)
+    }
+    feat[tl][f] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 bi = __ldg(reinterpret_cast<const float4*>(b_in) + lane);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w) + lane);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(ln_b) + lane);
+  for (int tl = warp; tl < EMB_TOK; tl += 8) {
+    const long long tok = tok0 + tl;
+    if (tok >= M) break;
+    float v[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float* w = ws + (lane * 4 + c) * 13;
+      float s = 0.f;
+#pragma unroll
+      for (int f = 0; f < 13; ++f) s = fmaf(feat[tl][f], w[f], s);
+      v[c] += s;
+    }
+    float mean = v[0] + v[1] + v[2] + v[3];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mean += __shfl_xor_sync(0xFFFFFFFFu, mean, d);
+    mean *= (1.f / D_MODEL);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { const float dlt = v[c] - mean; var = fmaf(dlt, dlt, var); }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xFFFFFFFFu, var, d);
+    const float rstd = rsqrtf(var * (1.f / D_MODEL) + LN_EPS);
+    float4 o;
+    o.x = (v[0] - mean) * rstd * g.x + be.x;
+    o.y = (v[1] - mean) * rstd * g.y + be.y;
+    o.z = (v[2] - mean) * rstd * g.z + be.z;
+    o.w = (v[3] - mean) * rstd * g.w + be.w;
+    reinterpret_cast<float4*>(out + tok * D_MODEL)[lane] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 64x64x128 SIMT GEMM tile: C[64 tok][64 out] = A[64][128] . W[64][128]^T, 256 threads x (4x4)
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 64;    // tile edge (tokens and outputs)
+constexpr int GK = 128;   // k extent held in smem
+constexpr int GLD = 68;   // smem row stride (floats): keeps float4 alignment, 2-way store conflicts
+constexpr size_t GEMM_SMEM = sizeof(float) * 2 * GK * GLD;
+
+// Load 64 rows x 128 k of a row-major matrix into smem transposed ([k][row]); 4 threads per row,
+// thread `part` takes the float4 at k = 16*it + 4*part.  Optional fused LayerNorm over the 128 k.
+template <bool LN>
+__device__ __forceinline__ void load_tile_T(float* __restrict__ S, const float* __restrict__ src, long long row0,
+                                            long long rows_total, int ld, int koff,
+                                            const float* __restrict__ ln_w, const float* __restrict__ ln_b) {
+  const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const long long row = row0 + r;
+  const bool in = row < rows_total;
+  const float* p = src + row * ld + koff;
+  float4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it)
+    v[it] = in ? __ldg(reinterpret_cast<const float4*>(p + 16 * it + 4 * part)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (LN) {
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) s += v[it].x + v[it].y + v[it].z + v[it].w;
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
+    const float mean = s * (1.f / GK);
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      float d;
+      d = v[it].x - mean; q = fmaf(d, d, q);
+      d = v[it].y - mean; q = fmaf(d, d, q);
+      d = v[it].z - mean; q = fmaf(d, d, q);
+      d = v[it].w - mean; q = fmaf(d, d, q);
+    }
+    q += __shfl_xor_sync(0xFFFFFFFFu, q, 1);
+    q += __shfl_xor_sync(0xFFFFFFFFu, q, 2);
+    const float rstd = rsqrtf(q * (1.f / GK) + LN_EPS);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int k = 16 * it + 4 * part;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w + k));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b + k));
+      v[it].x = (v[it].x - mean) * rstd * g.x + b.x;
+      v[it].y = (v[it].y - mean) * rstd * g.y + b.y;
+      v[it].z = (v[it].z - mean) * rstd * g.z + b.z;
+      v[it].w = (v[it].w - mean) * rstd * g.w + b.w;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int k = 16 * it + 4 * part;
+    S[(k + 0) * GLD + r] = v[it].x;
+    S[(k + 1) * GLD + r] = v[it].y;
+    S[(k + 2) * GLD + r] = v[it].z;
+    S[(k + 3) * GLD + r] = v[it].w;
+  }
+}
+
+// W tile whose 64 smem columns map to arbitrary global rows (used for the GEGLU value/gate interleave)
+__device__ __forceinline__ void load_w_tile_T(float* __restrict__ S, const float* __restrict__ W, int ld, int koff,
+                                              int global_row) {
+  const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const float* p = W + (size_t)global_row * ld + koff;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int k = 16 * it + 4 * part;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + k));
+    S[(k + 0) * GLD + r] = v.x;
+    S[(k + 1) * GLD + r] = v.y;
+    S[(k + 2) * GLD + r] = v.z;
+    S[(k + 3) * GLD + r] = v.w;
+  }
+}
+
+__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Ws, float (&acc)[4][4]) {
+  const int tm = threadIdx.x >> 4, tn = threadIdx.x & 15;
+#pragma unroll 8
+  for (int k = 0; k < GK; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(As + k * GLD + tm * 4);
+    const float4 w = *reinterpret_cast<const float4*>(Ws + k * GLD + tn * 4);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+  }
+}
+
+// q = LN(x) . Wq^T   (to_q has no bias).  grid (M/64, 2)
+__global__ void __launch_bounds__(256)
+ln_q_kernel(long long M, const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+            const float* __restrict__ wq, float* __restrict__ q) {
+  extern __shared__ float gsm[];
+  float* As = gsm;
+  float* Ws = gsm + GK * GLD;
+  const long long row0 = (long long)blockIdx.x * GT;
+  const int n0 = blockIdx.y * GT;
+  load_tile_T<true>(As, x, row0, M, D_MODEL, 0, ln_w, ln_b);
+  load_w_tile_T(Ws, wq, D_MODEL, 0, n0 + (threadIdx.x >> 2));
+  __syncthreads();
+  float acc[4][4] = {};
+  tile_mma(As, Ws, acc);
+  const int tm = threadIdx.x >> 4, tn = threadIdx.x & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long row = row0 + tm * 4 + i;
+    if (row < M) *reinterpret_cast<float4*>(q + row * D_MODEL + n0 + tn * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+}
+
+// u = (LN(x) . W1a^T + b1a) * gelu(LN(x) . W1g^T + b1g).  grid (M/64, 512/32): smem W columns
+// alternate value/gate rows so each thread owns complete (value, gate) pairs.
+__global__ void __launch_bounds__(256)
+ln_geglu_kernel(long long M, const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ u) {
+  extern __shared__ float gsm[];
+  float* As = gsm;
+  float* Ws = gsm + GK * GLD;
+  const long long row0 = (long long)blockIdx.x * GT;
+  const int i0 = blockIdx.y * (GT / 2);
+  load_tile_T<true>(As, x, row0, M, D_MODEL, 0, ln_w, ln_b);
+  {
+    const int c = threadIdx.x >> 2;
+    load_w_tile_T(Ws, w1, D_MODEL, 0, (c & 1) ? (D_FF + i0 + (c >> 1)) : (i0 + (c >> 1)));
+  }
+  __syncthreads();
+  float acc[4][4] = {};
+  tile_mma(As, Ws, acc);
+  const int tm = threadIdx.x >> 4, tn = threadIdx.x & 15;
+  const int i = i0 + tn * 2;
+  const float ba0 = __ldg(b1 + i), ba1 = __ldg(b1 + i + 1);
+  const float bg0 = __ldg(b1 + D_FF + i), bg1 = __ldg(b1 + D_FF + i + 1);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long row = row0 + tm * 4 + r;
+    if (row < M) {
+      float2 o;
+      o.x = (acc[r][0] + ba0) * gelu_erf32(acc[r][1] + bg0);
+      o.y = (acc[r][2] + ba1) * gelu_erf32(acc[r][3] + bg1);
+      *reinterpret_cast<float2*>(u + row * D_FF + i) = o;
+    }
+  }
+}
+
+// x += A . W^T + bias,  A (M, K) row-major, W (128, K).  grid (M/64, 2)
+template <int K>
+__global__ void __launch_bounds__(256)
+gemm_residual_kernel(long long M, const float* __restrict__ A, const float* __restrict__ W,
+                     const float* __restrict__ bias, float* __restrict__ x) {
+  extern __shared__ float gsm[];
+  float* As = gsm;
+  float* Ws = gsm + GK * GLD;
+  const long long row0 = (long long)blockIdx.x * GT;
+  const int n0 = blockIdx.y * GT;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    if (k0) __syncthreads();
+    load_tile_T<false>(As, A, row0, M, K, k0, nullptr, nullptr);
+    load_w_tile_T(Ws, W, K, k0, n0 + (threadIdx.x >> 2));
+    __syncthreads();
+    tile_mma(As, Ws, acc);
+  }
+  const int tm = threadIdx.x >> 4, tn = threadIdx.x & 15;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + tn * 4));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long row = row0 + tm * 4 + i;
+    if (row < M) {
+      float4* p = reinterpret_cast<float4*>(x + row * D_MODEL + n0 + tn * 4);
+      float4 v = *p;
+      v.x += acc[i][0] + b.x;
+      v.y += acc[i][1] + b.y;
+      v.z += acc[i][2] + b.z;
+      v.w += acc[i][3] + b.w;
+      *p = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention core: one thread per (token, head); q is replaced by the head's output in place.
+// sim = q.k * d_head^-0.5, masked_fill(~valid, -FLT_MAX), softmax over the 4 keys, out = P.V
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attention_kernel(int N, long long M, int depth, int l, const float* __restrict__ kv,
+                 const float* __restrict__ valid_id, float* __restrict__ q) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tok = g >> 3;
+  const int h = (int)(g & 7);
+  if (tok >= M) return;
+  const long long b = tok / N;
+  float4* qp = reinterpret_cast<float4*>(q + tok * D_MODEL + h * 16);
+  float qv[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = qp[i];
+    qv[4 * i] = t.x; qv[4 * i + 1] = t.y; qv[4 * i + 2] = t.z; qv[4 * i + 3] = t.w;
+  }
+  const float* kb = kv + ((b * depth + l) * 2 + 0) * MAX_TOKENS * D_MODEL + h * 16;
+  const float* vb = kb + MAX_TOKENS * D_MODEL;
+  float sim[MAX_TOKENS];
+#pragma unroll
+  for (int j = 0; j < MAX_TOKENS; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 k4 = __ldg(reinterpret_cast<const float4*>(kb + j * D_MODEL) + i);
+      s = fmaf(qv[4 * i], k4.x, s); s = fmaf(qv[4 * i + 1], k4.y, s);
+      s = fmaf(qv[4 * i + 2], k4.z, s); s = fmaf(qv[4 * i + 3], k4.w, s);
+    }
+    s *= 0.25f;  // dim_head ** -0.5
+    if (valid_id != nullptr && __ldg(valid_id + b * MAX_TOKENS + j) == 0.f) s = -FLT_MAX;
+    sim[j] = s;
+  }
+  const float mx = fmaxf(fmaxf(sim[0], sim[1]), fmaxf(sim[2], sim[3]));
+  float p[MAX_TOKENS], den = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_TOKENS; ++j) { p[j] = expf(sim[j] - mx); den += p[j]; }
+  const float inv = 1.f / den;
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_TOKENS; ++j) {
+    const float pj = p[j] * inv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(vb + j * D_MODEL) + i);
+      o[4 * i] = fmaf(pj, v4.x, o[4 * i]); o[4 * i + 1] = fmaf(pj, v4.y, o[4 * i + 1]);
+      o[4 * i + 2] = fmaf(pj, v4.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(pj, v4.w, o[4 * i + 3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) qp[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// post_norm + proj_out (128 -> 3), written channel-major (B,3,N).  One warp per token.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_kernel(int N, long long M, const float* __restrict__ x, const float* __restrict__ ln_w,
+            const float* __restrict__ ln_b, const float* __restrict__ w_out, const float* __restrict__ b_out,
+            float* __restrict__ eps) {
+  const int lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= M) return;
+  const float4 v = reinterpret_cast<const float4*>(x + tok * D_MODEL)[lane];
+  float mean = v.x + v.y + v.z + v.w;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) mean += __shfl_xor_sync(0xFFFFFFFFu, mean, d);
+  mean *= (1.f / D_MODEL);
+  const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+  float var = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xFFFFFFFFu, var, d);
+  const float rstd = rsqrtf(var * (1.f / D_MODEL) + LN_EPS);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w) + lane);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(ln_b) + lane);
+  const float y0 = d0 * rstd * g.x + be.x, y1 = d1 * rstd * g.y + be.y;
+  const float y2 = d2 * rstd * g.z + be.z, y3 = d3 * rstd * g.w + be.w;
+  float o[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w_out + c * D_MODEL) + lane);
+    float s = y0 * w.x + y1 * w.y + y2 * w.z + y3 * w.w;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    o[c] = s + __ldg(b_out + c);
+  }
+  if (lane < 3) {
+    const long long b = tok / N;
+    const int p = (int)(tok - b * N);
+    eps[(b * 3 + lane) * N + p] = lane == 0 ? o[0] : lane == 1 ? o[1] : o[2];
+  }
+}
+
+int denoiser_forward_fp32(const PackLayout& L, const float* P, int B, int N, const float* x,
+                          const float* anchors, const float* variances, const int* assign,
+                          const float* valid_id, float* eps_out, Workspace& ws, cudaStream_t st) {
+  const long long M = (long long)B * N;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFB_CUDA(cudaFuncSetAttribute(ln_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    DFB_CUDA(cudaFuncSetAttribute(ln_geglu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    DFB_CUDA(cudaFuncSetAttribute(gemm_residual_kernel<D_MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    DFB_CUDA(cudaFuncSetAttribute(gemm_residual_kernel<D_FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    attr_set = true;
+  }
+  const int mt = cdiv(M, GT);
+  embed_kernel<<<cdiv(M, EMB_TOK), 256, 0, st>>>(N, M, L.d.flags, x, anchors, variances, assign, P + L.g[P_IN_W],
+                                                 P + L.g[P_IN_B], P + L.g[P_PRE_W], P + L.g[P_PRE_B], ws.x);
+  DFB_LAUNCH_CHECK();
+  for (int l = 0; l < L.d.depth; ++l) {
+    const size_t* o = L.blk[l];
+    ln_q_kernel<<<dim3(mt, 2), 256, GEMM_SMEM, st>>>(M, ws.x, P + o[B_N2_W], P + o[B_N2_B], P + o[B_WQ], ws.q);
+    DFB_LAUNCH_CHECK();
+    attention_kernel<<<cdiv(M * 8, 256), 256, 0, st>>>(N, M, L.d.depth, l, ws.kv, valid_id, ws.q);
+    DFB_LAUNCH_CHECK();
+    gemm_residual_kernel<D_MODEL><<<dim3(mt, 2), 256, GEMM_SMEM, st>>>(M, ws.q, P + o[B_WO], P + o[B_BO], ws.x);
+    DFB_LAUNCH_CHECK();
+    ln_geglu_kernel<<<dim3(mt, D_FF / (GT / 2)), 256, GEMM_SMEM, st>>>(M, ws.x, P + o[B_N3_W], P + o[B_N3_B], P + o[B_W1], P + o[B_B1], ws.u);
+    DFB_LAUNCH_CHECK();
+    gemm_residual_kernel<D_FF><<<dim3(mt, 2), 256, GEMM_SMEM, st>>>(M, ws.u, P + o[B_W2], P + o[B_B2], ws.x);
+    DFB_LAUNCH_CHECK();
+  }
+  head_kernel<<<cdiv(M, 8), 256, 0, st>>>(N, M, ws.x, P + L.g[P_POST_W], P + L.g[P_POST_B], P + L.g[P_OUT_W], P + L.g[P_OUT_B], eps_out);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+}  // namespace dfb200

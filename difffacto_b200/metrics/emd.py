@@ -1,0 +1,68 @@
+"""Approximate EMD (auction algorithm) on B200 behind the reference's API
+(python/difffacto/metrics/emd/emd_module.py:32-87: emdFunction, EMD registered in METRICS).
+One persistent kernel per call instead of 7 launches per auction round."""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .. import _lib
+from .._lib import check, ptr, require_cuda, stream
+from ..utils.registry import METRICS
+
+
+class emdFunction(Function):
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, eps, iters):
+        batchsize, n, _ = xyz1.size()
+        _, m, _ = xyz2.size()
+        assert n == m
+        assert xyz1.size()[0] == xyz2.size()[0]
+        assert n % 1024 == 0
+        assert batchsize <= 512
+        require_cuda(xyz1, xyz2)
+        xyz1 = xyz1.contiguous().float()
+        xyz2 = xyz2.contiguous().float()
+        dev = xyz1.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        dist = torch.empty(batchsize, n, device=dev)
+        assignment = torch.empty(batchsize, n, **i32)
+        assignment_inv = torch.empty(batchsize, m, **i32)
+        price = torch.empty(batchsize, m, device=dev)
+        bid = torch.empty(batchsize, n, **i32)
+        bid_increments = torch.empty(batchsize, n, device=dev)
+        max_increments = torch.empty(batchsize, m, device=dev)
+        unass_idx = torch.empty(batchsize * n, **i32)
+        max_idx = torch.empty(batchsize * m, **i32)
+        unass_cnt = torch.zeros(512, **i32)
+        with torch.cuda.device(dev):
+            check(_lib.load().dfb200_emd_forward(batchsize, n, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(assignment), ptr(price),
+                                                 ptr(assignment_inv), ptr(bid), ptr(bid_increments), ptr(max_increments),
+                                                 ptr(unass_idx), ptr(unass_cnt), None, None, ptr(max_idx), float(eps),
+                                                 int(iters), stream()))
+        ctx.save_for_backward(xyz1, xyz2, assignment)
+        return dist, assignment
+
+    @staticmethod
+    def backward(ctx, graddist, gradidx):
+        xyz1, xyz2, assignment = ctx.saved_tensors
+        graddist = graddist.contiguous()
+        gradxyz1 = torch.empty_like(xyz1)
+        gradxyz2 = torch.zeros_like(xyz2)
+        B, n, _ = xyz1.shape
+        with torch.cuda.device(xyz1.device):
+            check(_lib.load().dfb200_emd_backward(B, n, ptr(xyz1), ptr(xyz2), ptr(gradxyz1), ptr(graddist), ptr(assignment), stream()))
+        return gradxyz1, gradxyz2, None, None
+
+
+@METRICS.register_module()
+class EMD(nn.Module):
+    def __init__(self, eps, iters, dist_only=False):
+        super().__init__()
+        self.eps = eps
+        self.iters = iters
+        self.dist_only = dist_only
+
+    def forward(self, input1, input2):
+        if self.dist_only:
+            return torch.sqrt(emdFunction.apply(input1, input2, self.eps, self.iters)[0]).mean(1)
+        return emdFunction.apply(input1, input2, self.eps, self.iters)

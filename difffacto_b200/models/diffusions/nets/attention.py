@@ -1,0 +1,196 @@
+"""NETS['TransformerNet']: the cross-diffusion denoiser, host side.
+
+Mirror of the reference class (python/difffacto/models/diffusions/nets/attention.py:308-440): same
+constructor keywords, same parameter names/shapes (state_dicts interchange with the reference and
+its pretrained checkpoints), same `forward(x, t, ctx, anchors=, variances=, valid_id=,
+anchor_assignment=)` contract.  The modules below only HOLD parameters; the forward pass is the
+hand-written CUDA of difffacto_b200/csrc/denoiser_*.cu reached through the C ABI
+(dfb200_denoiser_forward).  There is no PyTorch fallback: CPU tensors raise.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from .... import _lib
+from ...._lib import DenoiserCfg, check, ptr, stream
+from ....utils.registry import NETS
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class _FeedForward(nn.Module):  # reference attention.py:77-94 (glu=True): net = [GEGLU, Dropout, Linear]
+    def __init__(self, dim, mult=4, dropout=0.0):
+        super().__init__()
+        inner = int(dim * mult)
+        self.net = nn.Sequential(_GEGLU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim))
+
+
+class _CrossAttention(nn.Module):  # reference attention.py:161-177
+    def __init__(self, query_dim, context_dim, heads, dim_head, dropout=0.0):
+        super().__init__()
+        inner = heads * dim_head
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(context_dim, inner, bias=False)
+        self.to_v = nn.Linear(context_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(dropout))
+
+
+class _Block(nn.Module):  # reference attention.py:259-294 with single_attn=True
+    def __init__(self, dim, n_heads, d_head, dropout, context_dim):
+        super().__init__()
+        self.ff = _FeedForward(dim, dropout=dropout)
+        self.attn2 = _CrossAttention(dim, context_dim, n_heads, d_head, dropout)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+
+_GLOBAL_ORDER = ["pre_norm.weight", "pre_norm.bias", "post_norm.weight", "post_norm.bias", "proj_in.weight", "proj_in.bias",
+                 "time_embed.net.0.proj.weight", "time_embed.net.0.proj.bias", "time_embed.net.2.weight",
+                 "time_embed.net.2.bias", "proj_out.weight", "proj_out.bias"]
+_BLOCK_ORDER = ["norm2.weight", "norm2.bias", "norm3.weight", "norm3.bias", "attn2.to_q.weight", "attn2.to_k.weight",
+                "attn2.to_v.weight", "attn2.to_out.0.weight", "attn2.to_out.0.bias", "ff.net.0.proj.weight",
+                "ff.net.0.proj.bias", "ff.net.2.weight", "ff.net.2.bias"]
+
+
+def pack_order(depth):
+    """Parameter names in the order dfb200_denoiser_pack expects (include/difffacto_b200.h)."""
+    return _GLOBAL_ORDER + [f"transformer_blocks.{i}.{n}" for i in range(depth) for n in _BLOCK_ORDER]
+
+
+@NETS.register_module()
+class TransformerNet(nn.Module):
+    def __init__(self, in_channels, n_heads, d_head, out_channels, depth=1, dropout=0., context_dim=None,
+                 use_linear=False, use_checkpoint=False, single_attn=False, class_cond=False, n_class=4,
+                 cat_params_to_x=False, mask_out_unreferenced_code=True, cat_class_to_x=False, use_sine_proj_in=False,
+                 add_t_to_x=False, res=False, add_class_cond=False, context_proj=False, include_std=False,
+                 precision=None):
+        super().__init__()
+        unsupported = dict(use_linear=not use_linear, single_attn=not single_attn, class_cond=not class_cond,
+                           cat_params_to_x=not cat_params_to_x, cat_class_to_x=not cat_class_to_x,
+                           use_sine_proj_in=use_sine_proj_in, add_t_to_x=add_t_to_x, res=res,
+                           add_class_cond=add_class_cond, context_proj=context_proj)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad or n_heads * d_head != 128:
+            raise NotImplementedError(
+                "difffacto_b200.TransformerNet implements the configuration of the shipped configs "
+                f"(configs/gen_*.py, train_*.py); unsupported setting(s): {bad or 'inner_dim != 128'}")
+        self.raw_in_channels = in_channels
+        self.in_channels = in_channels + 6 + n_class
+        self.out_channels = out_channels
+        self.n_heads, self.d_head, self.depth = n_heads, d_head, depth
+        self.n_class = n_class
+        self.raw_context_dim = context_dim
+        self.context_dim = context_dim + 256 + n_class
+        self.inner_dim = n_heads * d_head
+        self.mask_out_unreferenced_code = mask_out_unreferenced_code
+        self.include_std = include_std
+        self.class_cond, self.add_class_cond = class_cond, add_class_cond
+        self.cat_params_to_x, self.cat_class_to_x = cat_params_to_x, cat_class_to_x
+        self.add_t_to_x, self.res, self.context_proj, self.use_linear = add_t_to_x, res, context_proj, use_linear
+        self.dropout = dropout
+
+        self.pre_norm = nn.LayerNorm(self.inner_dim)
+        self.post_norm = nn.LayerNorm(self.inner_dim)
+        self.proj_in = nn.Linear(self.in_channels, self.inner_dim)
+        self.time_embed = _FeedForward(256, dropout=dropout)
+        self.transformer_blocks = nn.ModuleList(
+            [_Block(self.inner_dim, n_heads, d_head, dropout, self.context_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(self.inner_dim, out_channels)
+
+        # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulation); "fp32": CUDA-core path
+        self.precision = precision or os.environ.get("DFB200_PRECISION", "bf16")
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+
+    # ---- C-ABI plumbing -------------------------------------------------------------------
+    def c_cfg(self):
+        flags = _lib.NET_CLASS_COND | _lib.NET_CAT_PARAMS_TO_X | _lib.NET_CAT_CLASS_TO_X
+        if self.mask_out_unreferenced_code:
+            flags |= _lib.NET_MASK_UNREFERENCED
+        if self.include_std:
+            flags |= _lib.NET_INCLUDE_STD
+        return DenoiserCfg(self.raw_in_channels, self.out_channels, self.n_heads, self.d_head, self.depth,
+                           self.raw_context_dim, self.n_class, flags)
+
+    def mode(self):
+        if self.precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
+        return _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
+
+    def packed_weights(self):
+        """Device weight image for the kernels; rebuilt whenever a parameter was modified."""
+        sd = dict(self.named_parameters())
+        params = [sd[n] for n in pack_order(self.depth)]
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("CPU not supported: move the TransformerNet to a CUDA device")
+        key = (dev,) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed_key != key:
+            lib = _lib.load()
+            cfg = self.c_cfg()
+            nbytes = lib.dfb200_denoiser_packed_bytes(cfg)
+            if nbytes == 0:
+                check(2)
+            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            off = (-buf.data_ptr()) % 1024
+            packed = buf[off:off + nbytes]
+            tensors = [p.detach().to(torch.float32).contiguous() for p in params]
+            # sinusoid frequencies exactly as the reference builds them (on the CPU, nets/utils.py:17-19)
+            freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=128, dtype=torch.float32) / 128).to(dev)
+            tensors.append(freqs)
+            arr = (_lib.P * len(tensors))(*[t.data_ptr() for t in tensors])
+            with torch.cuda.device(dev):
+                check(lib.dfb200_denoiser_pack(cfg, arr, len(tensors), ptr(packed), stream()))
+                torch.cuda.current_stream().synchronize()
+            self._packed, self._packed_key, self._packed_buf = packed, key, buf
+        return self._packed
+
+    def workspace(self, nbytes, dev):
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != dev:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return self._workspace
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward(self, x, t, ctx, anchors=None, variances=None, valid_id=None, anchor_assignment=None, **kwargs):
+        """x (B,3,N); t (B,); ctx list of (B,C,4) or a (B,262,4) tensor; anchors/variances (B,N,3)
+        (the reference passes `.transpose(1,2)` views of (B,3,N) tensors); valid_id (B,4);
+        anchor_assignment (B,N) int32.  Returns eps (B,3,N).  Reference attention.py:385-440."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("difffacto_b200.TransformerNet: backward kernels are not part of this build; "
+                                      "call under torch.no_grad() / eval()")
+        if isinstance(ctx, (list, tuple)):
+            ctx = torch.cat(list(ctx), dim=1)
+        _lib.require_cuda(x, ctx, anchors, variances, anchor_assignment, valid_id)
+        B, C, N = x.shape
+        assert C == self.raw_in_channels
+        assert ctx.shape[1] + 256 + self.n_class == self.context_dim and ctx.shape[2] == self.n_class
+        dev = x.device
+        f32 = torch.float32
+        x = x.to(f32).contiguous()
+        ctx = ctx.to(f32).contiguous()
+        anchors_cm = anchors.transpose(1, 2).to(f32).contiguous()      # back to (B,3,N) channel-major
+        variances_cm = variances.transpose(1, 2).to(f32).contiguous()
+        assign = anchor_assignment.to(torch.int32).contiguous()
+        valid = None
+        if self.mask_out_unreferenced_code and valid_id is not None:
+            assert valid_id.shape == (B, self.n_class)
+            valid = valid_id.to(f32).contiguous()
+        tf = t.to(f32).contiguous()
+        assert tf.shape == (B,)
+        eps = torch.empty(B, self.out_channels, N, dtype=f32, device=dev)
+        lib = _lib.load()
+        cfg, mode = self.c_cfg(), self.mode()
+        packed = self.packed_weights()
+        nws = lib.dfb200_denoiser_workspace_bytes(cfg, mode, B, N)
+        ws = self.workspace(nws, dev)
+        with torch.cuda.device(dev):
+            check(lib.dfb200_denoiser_forward(cfg, ptr(packed), mode, B, N, ptr(x), ptr(tf), ptr(ctx), ptr(anchors_cm),
+                                              ptr(variances_cm), ptr(assign), ptr(valid), ptr(eps), ptr(ws), nws, stream()))
+        return eps

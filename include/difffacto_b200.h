@@ -1,0 +1,232 @@
+/*
+ * difffacto_b200 -- C ABI of the B200-native DiffFacto sampling hot path.
+ *
+ * One shared library (difffacto_b200/lib/libdifffacto_b200.so), plain C linkage, raw device
+ * pointers + sizes + a CUDA stream; no torch types anywhere.  Every entry point returns an
+ * int status (DFB200_OK == 0) instead of the reference's `exit(-1)` on launch failure
+ * (reference: pointnet2_ops_lib/pointnet2_ops/_ext-src/include/cuda_utils.h:30-39).
+ * Ownership follows the reference: the CALLER owns and allocates every buffer (inputs, outputs,
+ * scratch); the library never allocates device memory.  Initialisation the semantics rely on
+ * (idx zeros for ball_query, temp = 1e10 for FPS, zeroed grads) is done INSIDE the library, so
+ * output buffers may be uninitialised on entry.
+ *
+ * Each declaration cites the reference interface (file:line under /root/reference) it replaces.
+ * All tensors are contiguous, row-major, fp32 / int32, resident on the current device.
+ * `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ */
+#ifndef DIFFFACTO_B200_H_
+#define DIFFFACTO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB200_OK 0
+#define DFB200_ERR_INVALID_ARG 1
+#define DFB200_ERR_UNSUPPORTED 2
+#define DFB200_ERR_CUDA 3
+#define DFB200_ERR_WORKSPACE 4
+
+typedef void* dfb200_stream_t;
+
+/* ABI version of this header (bumped on any signature change). */
+int dfb200_abi_version(void);
+/* Human-readable message for the last non-OK status returned on this thread. */
+const char* dfb200_last_error(void);
+/* Number of kernels this library has launched on this process so far (bench.py's gpu_launches). */
+unsigned long long dfb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * pointnet2_ops  (reference: pointnet2_ops_lib/pointnet2_ops/_ext-src/src/bindings.cpp:6-19)
+ * ------------------------------------------------------------------------------------------ */
+
+/* out[b,c,j] = points[b,c,idx[b,j]].  points (b,c,n), idx (b,npoints) -> out (b,c,npoints).
+ * Replaces gather_points_kernel_wrapper, sampling.cpp:4-6 / sampling_gpu.cu:22-30. */
+int dfb200_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx,
+                         float* out, dfb200_stream_t stream);
+/* grad_points[b,c,idx[b,j]] += grad_out[b,c,j]; grad_points (b,c,n) is zeroed by the callee.
+ * Replaces gather_points_grad_kernel_wrapper, sampling.cpp:7-9 / sampling_gpu.cu:49-57. */
+int dfb200_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out,
+                              const int* idx, float* grad_points, dfb200_stream_t stream);
+/* Iterative furthest point sampling.  dataset (b,n,3) -> idxs (b,m) int32, idxs[:,0] = 0.
+ * `temp` (b,n) is optional scratch kept for signature compatibility: if non-NULL it receives the
+ * final per-point min squared distances (1e10 for never-updated points) exactly as the
+ * reference leaves them.  Bit-exact with the reference kernel incl. the |p|^2 <= 1e-3 skip and
+ * its tree-reduction tie rule.
+ * Replaces furthest_point_sampling_kernel_wrapper, sampling.cpp:11-13 / sampling_gpu.cu:175-229. */
+int dfb200_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp,
+                                   int* idxs, dfb200_stream_t stream);
+/* idx[b,j,:] = first `nsample` indices k (ascending) with |new_xyz[b,j]-xyz[b,k]|^2 < radius^2,
+ * padded with the first hit; all zeros if the ball is empty.  new_xyz (b,m,3), xyz (b,n,3).
+ * Replaces query_ball_point_kernel_wrapper, ball_query.cpp:4-6 / ball_query_gpu.cu:46-54. */
+int dfb200_query_ball_point(int b, int n, int m, float radius, int nsample, const float* new_xyz,
+                            const float* xyz, int* idx, dfb200_stream_t stream);
+/* out[b,c,j,k] = points[b,c,idx[b,j,k]].  points (b,c,n), idx (b,npoints,nsample).
+ * Replaces group_points_kernel_wrapper, group_points.cpp:4-6 / group_points_gpu.cu:30-39. */
+int dfb200_group_points(int b, int c, int n, int npoints, int nsample, const float* points,
+                        const int* idx, float* out, dfb200_stream_t stream);
+/* Scatter-add of grad_out (b,c,npoints,nsample) into grad_points (b,c,n) (zeroed by callee).
+ * Replaces group_points_grad_kernel_wrapper, group_points.cpp:8-10 / group_points_gpu.cu:66-75. */
+int dfb200_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out,
+                             const int* idx, float* grad_points, dfb200_stream_t stream);
+/* Three nearest `known` points of each `unknown` point: SQUARED distances ascending + indices.
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3), idx (b,n,3).
+ * Replaces three_nn_kernel_wrapper, interpolate.cpp:4-5 / interpolate_gpu.cu:61-68. */
+int dfb200_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2,
+                    int* idx, dfb200_stream_t stream);
+/* out[b,c,j] = sum_q weight[b,j,q] * points[b,c,idx[b,j,q]].  points (b,c,m) -> out (b,c,n).
+ * Replaces three_interpolate_kernel_wrapper, interpolate.cpp:6-8 / interpolate_gpu.cu:103-111. */
+int dfb200_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx,
+                             const float* weight, float* out, dfb200_stream_t stream);
+/* grad_points (b,c,m), zeroed by callee.
+ * Replaces three_interpolate_grad_kernel_wrapper, interpolate.cpp:9-12 / interpolate_gpu.cu:145-154. */
+int dfb200_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
+                                  const float* weight, float* grad_points, dfb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* Chamfer distance, both directions.  xyz1 (b,n,3), xyz2 (b,m,3) -> dist1 (b,n), idx1 (b,n),
+ * dist2 (b,m), idx2 (b,m): squared distance to / index of the nearest point of the other cloud
+ * (earliest index wins ties).  Runs on `stream` (the reference uses the legacy default stream).
+ * Replaces chamfer_cuda_forward, python/difffacto/metrics/chamfer_dist/chamfer.cu:147-171. */
+int dfb200_chamfer_forward(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1,
+                           float* dist2, int* idx1, int* idx2, dfb200_stream_t stream);
+/* grad_xyz1 (b,n,3), grad_xyz2 (b,m,3), zeroed by callee.
+ * Replaces chamfer_cuda_backward, chamfer.cu:203-229. */
+int dfb200_chamfer_backward(int b, int n, const float* xyz1, int m, const float* xyz2,
+                            const int* idx1, const int* idx2, const float* grad_dist1,
+                            const float* grad_dist2, float* grad_xyz1, float* grad_xyz2,
+                            dfb200_stream_t stream);
+
+/* Approximate earth mover's distance by the auction algorithm (n == m, n % 1024 == 0, b <= 512,
+ * coordinates in [0,1]).  All scratch is caller-allocated with the reference's shapes
+ * (python/difffacto/metrics/emd/emd_module.py:46-57); assignment/assignment_inv/price/... are
+ * (re)initialised by the callee.  dist (b,n) squared distances of the final assignment (b,n).
+ * One persistent kernel runs all `iters` auction rounds (the reference launches 7 kernels per
+ * round).  Replaces emd_cuda_forward, python/difffacto/metrics/emd/emd_cuda.cu:228-282. */
+int dfb200_emd_forward(int b, int n, const float* xyz1, const float* xyz2, float* dist,
+                       int* assignment, float* price, int* assignment_inv, int* bid,
+                       float* bid_increments, float* max_increments, int* unass_idx,
+                       int* unass_cnt, int* unass_cnt_sum, int* cnt_tmp, int* max_idx, float eps,
+                       int iters, dfb200_stream_t stream);
+/* grad_xyz1 (b,n,3), zeroed by callee.  Replaces emd_cuda_backward, emd_cuda.cu:302-317. */
+int dfb200_emd_backward(int b, int n, const float* xyz1, const float* xyz2, float* grad_xyz,
+                        const float* grad_dist, const int* assignment, dfb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-diffusion denoiser (TransformerNet) and anchored DDPM
+ * ------------------------------------------------------------------------------------------ */
+
+/* Static architecture of NETS['TransformerNet'] as resolved from the config
+ * (python/difffacto/models/diffusions/nets/attention.py:318-383; configs/gen_chair.py:50-66). */
+typedef struct dfb200_denoiser_cfg {
+  int in_channels;  /* 3: channels of x before the concatenations                        */
+  int out_channels; /* 3                                                                  */
+  int n_heads;      /* 8                                                                  */
+  int d_head;       /* 16  (inner_dim = n_heads*d_head must be 128)                       */
+  int depth;        /* 5 transformer blocks (single_attn=True: cross-attn + GEGLU FF)     */
+  int context_dim;  /* 262: channels of the concatenated ctx list before +n_class +256    */
+  int n_class;      /* 4 part tokens (keys/values)                                        */
+  int flags;        /* DFB200_NET_* below                                                 */
+} dfb200_denoiser_cfg;
+
+#define DFB200_NET_CLASS_COND 1        /* class_cond and not add_class_cond: one-hot in ctx */
+#define DFB200_NET_CAT_PARAMS_TO_X 2   /* cat anchors+variances to x (attention.py:400-404) */
+#define DFB200_NET_CAT_CLASS_TO_X 4    /* cat one-hot(assignment) to x (attention.py:405-407) */
+#define DFB200_NET_MASK_UNREFERENCED 8 /* mask_out_unreferenced_code (attention.py:409)     */
+#define DFB200_NET_INCLUDE_STD 16      /* include_std: sqrt(variance) instead of variance   */
+
+/* Precision mode of the denoiser GEMMs. */
+#define DFB200_MODE_FP32 0 /* CUDA-core FFMA, fp32 everywhere (reference numerics)          */
+#define DFB200_MODE_BF16 1 /* tcgen05 tensor cores: bf16 operands, fp32 accumulate in TMEM  */
+
+/* Number of fp32 parameter tensors dfb200_denoiser_pack expects: 12 + 13*depth, in this order
+ * (names as in the reference state_dict under `diffusion.model.`):
+ *   pre_norm.weight, pre_norm.bias, post_norm.weight, post_norm.bias, proj_in.weight,
+ *   proj_in.bias, time_embed.net.0.proj.weight, time_embed.net.0.proj.bias,
+ *   time_embed.net.2.weight, time_embed.net.2.bias, proj_out.weight, proj_out.bias,
+ *   then for each block i: norm2.weight, norm2.bias, norm3.weight, norm3.bias, attn2.to_q.weight,
+ *   attn2.to_k.weight, attn2.to_v.weight, attn2.to_out.0.weight, attn2.to_out.0.bias,
+ *   ff.net.0.proj.weight, ff.net.0.proj.bias, ff.net.2.weight, ff.net.2.bias. */
+int dfb200_denoiser_num_params(const dfb200_denoiser_cfg* cfg);
+/* Bytes of the packed device weight image (fp32 copies + bf16 UMMA operand images). */
+size_t dfb200_denoiser_packed_bytes(const dfb200_denoiser_cfg* cfg);
+/* Build the packed image in caller-owned device memory from device fp32 parameter tensors. */
+int dfb200_denoiser_pack(const dfb200_denoiser_cfg* cfg, const float* const* params, int n_params,
+                         void* packed, dfb200_stream_t stream);
+/* Scratch bytes for one forward at (B,N) in `mode`. */
+size_t dfb200_denoiser_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B, int N);
+
+/* eps = TransformerNet(x, t, ctx, anchors, variances, valid_id, anchor_assignment).
+ *   x, anchors, variances, eps_out : (B,3,N) channel-major (the memory the reference's
+ *                                    `anchors.transpose(1,2)` views alias)
+ *   t          : (B) fp32, the value the reference feeds to timestep_embedding
+ *   ctx        : (B, context_dim, n_class) = torch.cat(ctx_list, dim=1)
+ *   anchor_assignment : (B,N) int32 part id of each point;  valid_id : (B,n_class) or NULL
+ * Replaces TransformerNet.forward/_forward_attn, attention.py:385-440 (+ blocks :161-306). */
+int dfb200_denoiser_forward(const dfb200_denoiser_cfg* cfg, const void* packed, int mode, int B,
+                            int N, const float* x, const float* t, const float* ctx,
+                            const float* anchors, const float* variances,
+                            const int* anchor_assignment, const float* valid_id, float* eps_out,
+                            void* workspace, size_t workspace_bytes, dfb200_stream_t stream);
+
+/* Schedule table: device fp32 array [DFB200_SCHED_ROWS][T], each row float32(np.float64 table)
+ * exactly as python/difffacto/models/diffusions/anchored_diffusion.py:62-112 builds them. */
+#define DFB200_SCHED_SQRT_ALPHAS_CUMPROD 0
+#define DFB200_SCHED_SQRT_ONE_MINUS_ALPHAS_CUMPROD 1
+#define DFB200_SCHED_SQRT_RECIP_ALPHAS_CUMPROD 2
+#define DFB200_SCHED_SQRT_RECIPM1_ALPHAS_CUMPROD 3
+#define DFB200_SCHED_POSTERIOR_VARIANCE 4
+#define DFB200_SCHED_POSTERIOR_MEAN_COEF1 5
+#define DFB200_SCHED_POSTERIOR_MEAN_COEF2 6
+#define DFB200_SCHED_POSTERIOR_MEAN_COEF3 7
+#define DFB200_SCHED_ROWS 8
+
+/* One reverse step given eps (epsilon / fixed_small / learn_variance / learn_anchor path):
+ *   x0   = sqrt_recip[t]*(x_t-a)+a - sqrt_recipm1[t]*sqrt(var)*eps   (anchored_diffusion.py:401-409)
+ *   mean = c1[t]*x0 + c2[t]*x_t + c3[t]*a                            (:184-188)
+ *   x'   = mean + [t!=0]*sqrt(post_var[t]*var)*noise                 (:313, :476-483)
+ * t (B) int32; noise may be NULL only if every t == 0; pred_xstart may be NULL.
+ * Replaces AnchoredDiffusion.p_mean_variance/p_sample arithmetic, anchored_diffusion.py:227-484. */
+int dfb200_ddpm_step(int B, int N, int T, const float* sched, const int* t, const float* x_t,
+                     const float* eps, const float* anchors, const float* variance,
+                     const float* noise, float* x_prev, float* pred_xstart,
+                     dfb200_stream_t stream);
+/* x_t = sqrt_ac[t]*(x0-a)+a + sqrt_1mac[t]*sqrt(var)*noise.  Replaces q_sample, :148-173. */
+int dfb200_q_sample(int B, int N, int T, const float* sched, const int* t, const float* x_start,
+                    const float* anchors, const float* variance, const float* noise, float* x_t,
+                    dfb200_stream_t stream);
+/* Fill `out` (count floats) with N(0,1) samples from the library's counter-based Philox4x32-10
+ * stream (seed, offset); the same generator the sampling loop uses when `noise == NULL`. */
+int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uint64_t offset,
+                         dfb200_stream_t stream);
+
+/* Scratch bytes for dfb200_ddpm_sample_loop. */
+size_t dfb200_ddpm_sample_loop_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B,
+                                               int N, int T);
+/* Full reverse process x_T -> x_0 for a batch: T x (denoiser + fused eps->x_{t-1} update).
+ *   x          : (B,3,N) in: x_T if x_T_from_noise == 0; N(0,1) noise z that is turned into
+ *                sqrt(var)*z + anchors (anchored_diffusion.py:564) if == 1; ignored if == 2 (z is
+ *                Philox(seed) draw number T); out: x_0.
+ *   noise      : (T,B,3,N) per-step N(0,1) noise, index [T-1-i] for step i counting down from
+ *                T-1 (step order of the loop), or NULL to use Philox(seed).
+ *   traj       : optional (n_traj,B,3,N) buffer; x after step t is stored for every t>0 with
+ *                t % traj_interval == 0 at slot t/traj_interval - 1 (AnchorDiffAE.decode's
+ *                ret_traj/ret_interval, python/difffacto/models/networks/anchor_gen.py:160-167).
+ * Replaces AnchoredDiffusion.p_sample_loop_progressive, anchored_diffusion.py:528-588. */
+int dfb200_ddpm_sample_loop(const dfb200_denoiser_cfg* cfg, const void* packed, int mode, int B,
+                            int N, int T, const float* sched, float* x, int x_T_from_noise,
+                            const float* ctx, const float* anchors, const float* variance,
+                            const int* anchor_assignment, const float* valid_id,
+                            const float* noise, uint64_t seed, float* traj, int traj_interval,
+                            void* workspace, size_t workspace_bytes, dfb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFFACTO_B200_H_ */

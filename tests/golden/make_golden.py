@@ -1,0 +1,134 @@
+"""Generate tests/golden/denoiser_golden.npz from the REAL reference implementation.
+
+Run in the build container only (needs /root/reference; it does not exist on the GPU box):
+    python tests/golden/make_golden.py
+The reference's Python hot path is imported with namespace shims (no package __init__ runs, so the
+compiled `emd`/`chamfer`/`pointnet2_ops` extensions and tensorboardX/plyfile are not needed), the
+`AnchoredDiffusion` + `TransformerNet` of configs/gen_chair.py are built through the reference's
+own registry, their weights are overwritten with oracle.denoiser_ref.synthetic_state_dict(seed) and
+they are run on oracle.denoiser_ref.synthetic_inputs(seed, ...).  Only outputs are stored: inputs
+and weights are regenerated from the seeds by the tests.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/python/difffacto"
+
+
+def import_reference():
+    def ns(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+
+    for name, sub in [("difffacto", ""), ("difffacto.utils", "/utils"), ("difffacto.models", "/models"),
+                      ("difffacto.models.diffusions", "/models/diffusions"),
+                      ("difffacto.models.diffusions.nets", "/models/diffusions/nets")]:
+        ns(name, REF + sub)
+    p2 = types.ModuleType("pointnet2_ops")
+    p2u = types.ModuleType("pointnet2_ops.pointnet2_utils")
+    p2u.gather_operation = lambda f, idx: torch.gather(f, 2, idx.long().unsqueeze(1).expand(-1, f.shape[1], -1))
+    p2u.furthest_point_sample = None
+    p2.pointnet2_utils = p2u
+    sys.modules["pointnet2_ops"] = p2
+    sys.modules["pointnet2_ops.pointnet2_utils"] = p2u
+    importlib.import_module("difffacto.models.diffusions.nets.attention")
+    importlib.import_module("difffacto.models.diffusions.anchored_diffusion")
+    from difffacto.utils.registry import DIFFUSIONS, build_from_cfg
+    return DIFFUSIONS, build_from_cfg
+
+
+def gen_chair_diffusion_cfg():
+    # the `diffusion=dict(...)` block of /root/reference/configs/gen_chair.py:48-85, read from the file
+    sys.path.insert(0, "/root/reference/configs")
+    mod = importlib.import_module("gen_chair")
+    sys.path.pop(0)
+    return dict(mod.model["diffusion"])
+
+
+class FixedNoise:
+    """Replace torch.randn_like / torch.randn inside the reference by a queue of given tensors."""
+    def __init__(self, tensors):
+        self.q = list(tensors)
+
+    def __enter__(self):
+        self._rl, self._r = torch.randn_like, torch.randn
+        torch.randn_like = lambda x, *a, **k: self.q.pop(0).to(x)
+        torch.randn = lambda *a, **k: self.q.pop(0)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn_like, torch.randn = self._rl, self._r
+
+
+def main():
+    from oracle import denoiser_ref as R
+    DIFFUSIONS, build_from_cfg = import_reference()
+    torch.set_num_threads(4)
+    out = {}
+    T = 100
+    diff = build_from_cfg(gen_chair_diffusion_cfg(), DIFFUSIONS, num_timesteps=T).eval()
+    sd = R.synthetic_state_dict(seed=1234)
+    missing = diff.model.load_state_dict(sd, strict=True)
+    out["state_dict_keys"] = np.array(sorted(diff.model.state_dict().keys()))
+    out["n_params"] = np.array(sum(p.numel() for p in diff.model.parameters()))
+    # schedule tables as float32(np.float64 table)
+    out["sched"] = np.stack([getattr(diff, k).astype(np.float32) for k in R.SCHED_ROWS])
+
+    for tag, (seed, B, N, all_valid) in {"a": (11, 3, 64, False), "b": (12, 2, 128, True)}.items():
+        inp = R.synthetic_inputs(seed, B, N, all_valid)
+        ctx = [inp["code"], inp["params"]]
+        with torch.no_grad():
+            eps = diff.model(inp["x"], inp["t"], ctx, anchors=inp["anchors"].transpose(1, 2), anchor_assignment=inp["assign"],
+                             variances=inp["variance"].transpose(1, 2), valid_id=inp["valid"])
+            with FixedNoise([inp["noise"]]):
+                ps = diff.p_sample(inp["x"], inp["t"], inp["anchors"], ctx=ctx, variance=inp["variance"],
+                                   anchor_assignment=inp["assign"], valid_id=inp["valid"])
+            # t == 0 row: no noise
+            t0 = torch.zeros_like(inp["t"])
+            with FixedNoise([inp["noise"]]):
+                ps0 = diff.p_sample(inp["x"], t0, inp["anchors"], ctx=ctx, variance=inp["variance"],
+                                    anchor_assignment=inp["assign"], valid_id=inp["valid"])
+            xq = diff.q_sample(inp["x"], inp["t"], inp["anchors"], noise=inp["noise"], variance=inp["variance"])
+            flags = torch.ones(B, 1, N)
+            loss = diff.training_losses(inp["x"], inp["t"], anchors=inp["anchors"], variance=inp["variance"], ctx=ctx,
+                                        anchor_assignment=inp["assign"], valid_id=inp["valid"], flags=flags,
+                                        noise=inp["noise"])["mse_loss"]
+        out[f"{tag}_eps"] = eps.numpy()
+        out[f"{tag}_sample"] = ps["sample"].numpy()
+        out[f"{tag}_pred_xstart"] = ps["pred_xstart"].numpy()
+        out[f"{tag}_sample_t0"] = ps0["sample"].numpy()
+        out[f"{tag}_q_sample"] = xq.numpy()
+        out[f"{tag}_mse_loss"] = loss.numpy()
+
+    # short full loop: T=6, B=2, N=64, noise supplied (x_T draw first, then one per step)
+    Ts = 6
+    diff6 = build_from_cfg(gen_chair_diffusion_cfg(), DIFFUSIONS, num_timesteps=Ts).eval()
+    diff6.model.load_state_dict(sd, strict=True)
+    inp = R.synthetic_inputs(21, 2, 64, False)
+    rng = np.random.default_rng(99)
+    noises = [torch.from_numpy(rng.standard_normal((2, 3, 64)).astype(np.float32)) for _ in range(Ts + 1)]
+    import contextlib, io
+    with FixedNoise(list(noises)), contextlib.redirect_stdout(io.StringIO()):
+        traj = [(t, {k: v.clone() for k, v in o.items()}) for t, o in diff6.p_sample_loop_progressive(
+            [2, 3, 64], anchors=inp["anchors"], ctx=[inp["code"], inp["params"]], variance=inp["variance"],
+            anchor_assignment=inp["assign"], valid_id=inp["valid"], device="cpu")]
+    out["loop_ts"] = np.array([t for t, _ in traj])
+    out["loop_samples"] = np.stack([o["sample"].numpy() for _, o in traj])
+    out["loop_noises"] = np.stack([n.numpy() for n in noises])
+    out["loop_sched"] = np.stack([getattr(diff6, k).astype(np.float32) for k in R.SCHED_ROWS])
+    path = os.path.join(HERE, "denoiser_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
