@@ -1,11 +1,678 @@
-// placeholder -- replaced by the tcgen05 path
+// DFB200_MODE_BF16: the whole cross-diffusion denoiser as ONE fused tcgen05 kernel.
+//
+// Reference computation: python/difffacto/models/diffusions/nets/attention.py:385-440 (+ blocks
+// :161-306).  The reference materialises every activation in HBM (512 B/token per tensor, 4 KB/token
+// for the GEGLU intermediate, ~180 kernels per step); here a CTA owns two 128-token tiles for the whole
+// network and HBM sees only the 13 input features and the 3 output channels per token:
+//   * residual stream x (fp32) lives in TENSOR MEMORY: 128 lanes x 128 columns per tile; the out-proj and
+//     FF-out GEMMs accumulate straight into it (tcgen05.mma D += A.B), so the residual add is free;
+//   * LayerNorm / attention-over-4-part-tokens / GEGLU run on CUDA cores out of TMEM (one thread = one
+//     token row) and write the next bf16 A operand into shared memory in the canonical UMMA K-major
+//     layout; LN gains/biases and all Linear biases are folded into the packed weights (bias = one
+//     extra K=16 MMA against a constant "ones" tile, bf16 hi+lo split so it is fp32-accurate);
+//   * weights stream L2 -> smem as pre-packed bf16 UMMA tiles through a 6-slot cp.async.bulk ring fed by
+//     a producer warp; both tiles consume each packet, halving L2 traffic per token;
+//   * one warp issues all MMAs; the two tiles ping-pong so the epilogue of one overlaps the MMAs of the
+//     other; within a tile the FF hidden chunks are double-buffered in TMEM.
+// TMEM map (512 columns): X0 [0,128) X1 [128,256) ACC0 [256,384) ACC1 [384,512).
+#include <float.h>
+
 #include "denoiser.cuh"
+#include "tc_common.cuh"
+
 namespace dfb200 {
-size_t tc_stream_bytes_for(const NetDims&) { return 0; }
-int tc_pack_stream(const PackLayout&, void*, cudaStream_t) { return DFB200_OK; }
-int denoiser_forward_tc(const PackLayout&, const void*, int, int, const float*, const float*, const float*, const int*,
-                        const float*, float*, Workspace&, cudaStream_t) {
-  set_error("bf16 tcgen05 path not built");
-  return DFB200_ERR_UNSUPPORTED;
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------------
+// packed bf16 stream: per layer 36 packets, each at a fixed 18 KB stride, in MMA consumption order
+//   0: Wq' k[0,64)  + bias slab bq' (2 KB @16384)     1: Wq' k[64,128)
+//   2: Wo  k[0,64)  + bias slab bo                    3: Wo  k[64,128)
+//   4: W1' chunk 0 (+1 KB bias slab)   5: W1' chunk 1
+//   6+2c: W2 chunk c, 7+2c: W1' chunk c+2   (c = 0..13);   34: W2 chunk 14;   35: W2 chunk 15 + b2 slab (2 KB @8192)
+// Wq' = Wq.diag(norm2.w), bq' = Wq.norm2.b;  W1' = W1.diag(norm3.w), b1' = b1 + W1.norm3.b
+// W1' chunk c: rows [0,32) = value units 32c.., rows [32,64) = gate units 512+32c..  (64 x 128)
+// W2 chunk c: 128 rows x k[32c, 32c+32)
+// ---------------------------------------------------------------------------------------------
+constexpr int SLOT_BYTES = 18432;
+constexpr int NSLOT = 6;
+constexpr int PKT_PER_LAYER = 36;
+constexpr int FF_CHUNKS = 16;
+constexpr int BIAS_OFF_W128 = 16384;  // q0 / o0 / W1 packets: bias slab after 16 KB of weights
+constexpr int BIAS_OFF_W2 = 8192;
+
+__host__ __device__ inline int pkt_bytes(int p) {
+  if (p == 0 || p == 2) return 16384 + 2048;
+  if (p == 1 || p == 3) return 16384;
+  if (p == 35) return 8192 + 2048;
+  if (p == 34) return 8192;
+  if (p == 4 || p == 5) return 16384 + 1024;
+  return ((p - 6) & 1) ? 16384 + 1024 : 8192;
 }
+__host__ __device__ inline int pkt_w2(int c) { return c <= 13 ? 6 + 2 * c : 20 + c; }
+__host__ __device__ inline int pkt_w1(int c) { return c < 2 ? 4 + c : 7 + 2 * (c - 2); }
+
+size_t tc_stream_bytes_for(const NetDims& d) {
+  // stream + folded head (3x128 weights + 4 biases, fp32)
+  return (size_t)d.depth * PKT_PER_LAYER * SLOT_BYTES + sizeof(float) * (3 * D_MODEL + 4);
+}
+
+// ---- pack kernels (run once per weight update) -----------------------------------------------------
+// dst: UMMA tile of R rows x KC k-values; element (r,k) = src[rowmap(r)*ld + k0 + k] * (gamma ? gamma[k0+k] : 1)
+__global__ void pack_tile_kernel(uint8_t* __restrict__ dst, int R, int KC, const float* __restrict__ src, int ld, int k0,
+                                 const float* __restrict__ gamma, int geglu_chunk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * KC) return;
+  const int r = i / KC, k = i - r * KC;
+  int row = r;
+  if (geglu_chunk >= 0) row = r < 32 ? 32 * geglu_chunk + r : D_FF + 32 * geglu_chunk + (r - 32);
+  float v = __ldg(src + (size_t)row * ld + k0 + k);
+  if (gamma != nullptr) v *= __ldg(gamma + k0 + k);
+  *reinterpret_cast<__nv_bfloat16*>(dst + tile_off(R, r, k)) = __float2bfloat16_rn(v);
+}
+// bias slab: R rows x 8 k-values (16 B per row); k=0: bf16 hi, k=1: bf16 lo of  bias[row] + W[row,:].beta
+__global__ void pack_bias_kernel(uint8_t* __restrict__ dst, int R, const float* __restrict__ bias,
+                                 const float* __restrict__ W, int ld, const float* __restrict__ beta, int geglu_chunk) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int row = r;
+  if (geglu_chunk >= 0) row = r < 32 ? 32 * geglu_chunk + r : D_FF + 32 * geglu_chunk + (r - 32);
+  float v = bias != nullptr ? __ldg(bias + row) : 0.f;
+  if (beta != nullptr)
+    for (int k = 0; k < ld; ++k) v = fmaf(__ldg(W + (size_t)row * ld + k), __ldg(beta + k), v);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dst + r * 16);
+  o[0] = hi;
+  o[1] = lo;
+#pragma unroll
+  for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
+}
+// folded head: w_out' = w_out.diag(post_norm.w), b_out' = b_out + w_out.post_norm.b   (fp32)
+__global__ void pack_head_kernel(float* __restrict__ dst, const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                 const float* __restrict__ g, const float* __restrict__ be) {
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < D_MODEL; k += 32) {
+    const float w = __ldg(w_out + c * D_MODEL + k);
+    dst[c * D_MODEL + k] = w * __ldg(g + k);
+    acc = fmaf(w, __ldg(be + k), acc);
+  }
+  for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+  if (threadIdx.x == 0) dst[3 * D_MODEL + c] = acc + __ldg(b_out + c);
+}
+
+int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
+  const float* P = reinterpret_cast<const float*>(packed);
+  uint8_t* S = reinterpret_cast<uint8_t*>(packed) + L.tc_stream_off;
+  auto tile = [&](uint8_t* dst, int R, int KC, const float* src, int ld, int k0, const float* gamma, int chunk) {
+    pack_tile_kernel<<<cdiv(R * KC, 256), 256, 0, st>>>(dst, R, KC, src, ld, k0, gamma, chunk);
+    count_launch();
+  };
+  auto bias = [&](uint8_t* dst, int R, const float* b, const float* W, int ld, const float* beta, int chunk) {
+    pack_bias_kernel<<<cdiv(R, 128), 128, 0, st>>>(dst, R, b, W, ld, beta, chunk);
+    count_launch();
+  };
+  for (int l = 0; l < L.d.depth; ++l) {
+    const size_t* o = L.blk[l];
+    uint8_t* base = S + (size_t)l * PKT_PER_LAYER * SLOT_BYTES;
+    auto pk = [&](int p) { return base + (size_t)p * SLOT_BYTES; };
+    tile(pk(0), 128, 64, P + o[B_WQ], D_MODEL, 0, P + o[B_N2_W], -1);
+    bias(pk(0) + BIAS_OFF_W128, 128, nullptr, P + o[B_WQ], D_MODEL, P + o[B_N2_B], -1);
+    tile(pk(1), 128, 64, P + o[B_WQ], D_MODEL, 64, P + o[B_N2_W], -1);
+    tile(pk(2), 128, 64, P + o[B_WO], D_MODEL, 0, nullptr, -1);
+    bias(pk(2) + BIAS_OFF_W128, 128, P + o[B_BO], nullptr, 0, nullptr, -1);
+    tile(pk(3), 128, 64, P + o[B_WO], D_MODEL, 64, nullptr, -1);
+    for (int c = 0; c < FF_CHUNKS; ++c) {
+      tile(pk(pkt_w1(c)), 64, 128, P + o[B_W1], D_MODEL, 0, P + o[B_N3_W], c);
+      bias(pk(pkt_w1(c)) + BIAS_OFF_W128, 64, P + o[B_B1], P + o[B_W1], D_MODEL, P + o[B_N3_B], c);
+      tile(pk(pkt_w2(c)), 128, 32, P + o[B_W2], D_FF, 32 * c, nullptr, -1);
+    }
+    bias(pk(35) + BIAS_OFF_W2, 128, P + o[B_B2], nullptr, 0, nullptr, -1);
+  }
+  float* head = reinterpret_cast<float*>(S + (size_t)L.d.depth * PKT_PER_LAYER * SLOT_BYTES);
+  pack_head_kernel<<<3, 32, 0, st>>>(head, P + L.g[P_OUT_W], P + L.g[P_OUT_B], P + L.g[P_POST_W], P + L.g[P_POST_B]);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 320;  // warps 0-3: tile 0 epilogue, 4-7: tile 1 epilogue, 8: MMA issuer, 9: weight producer
+constexpr uint32_t SM_A = 0;               // 2 x 32768  A operand tiles (128 x 128 bf16)
+constexpr uint32_t SM_U = 65536;           // [2][2] x 8192  gated FF activations (128 x 32 bf16)
+constexpr uint32_t SM_ONES = 98304;        // 4096  ones tile (128 x 16 bf16: k=0,1 -> 1)
+constexpr uint32_t SM_RING = 102400;       // 6 x 18432
+constexpr uint32_t SM_KV = 212992;         // [2][2][4][128] fp32
+constexpr uint32_t SM_BAR = 221184;        // mbarriers
+constexpr uint32_t SM_TMEM = SM_BAR + 256;
+constexpr uint32_t TC_SMEM_BYTES = SM_TMEM + 64;
+
+enum Bar { BAR_A = 0 /*[2]*/, BAR_ACC = 2 /*[2][2]*/, BAR_UREADY = 6 /*[2][2]*/, BAR_UFREE = 10 /*[2][2]*/, BAR_X = 14 /*[2]*/,
+           BAR_WFULL = 16 /*[6]*/, BAR_WEMPTY = 22 /*[6]*/, BAR_COUNT = 28 };
+
+struct TcParams {
+  const uint8_t* stream;
+  const float* head;  // folded proj_out: [3][128] weights, then 3 biases
+  const float* w_in; const float* b_in; const float* pre_w; const float* pre_b;
+  const float* kv;    // [B][depth][2][4][128]
+  const float* x; const float* anchors; const float* variances; const int* assign; const float* valid;
+  float* eps_out;
+  int N, depth, flags;
+  long long M;
+};
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// one thread = one token row: mean / rstd of the 128-wide fp32 row held in TMEM columns [col, col+128)
+__device__ __forceinline__ void row_stats(uint32_t taddr, float& mean, float& rstd) {
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    float h[32];
+    tmem_ld32(taddr + cb * 32, h);
+    tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { s += h[k]; q = fmaf(h[k], h[k], q); }
+  }
+  mean = s * (1.f / D_MODEL);
+  const float var = fmaxf(q * (1.f / D_MODEL) - mean * mean, 0.f);
+  rstd = rsqrtf(var + LN_EPS);
+}
+
+// normalise the TMEM row (gain/bias are folded into the next weights) and write it as the bf16 A operand row
+__device__ __forceinline__ void row_normalize_to_tile(uint32_t taddr, float mean, float rstd, uint8_t* tile, int r) {
+  const float nm = -mean * rstd;
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    float h[32];
+    tmem_ld32(taddr + cb * 32, h);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 v;
+      v.x = pack_bf16(fmaf(h[8 * j + 0], rstd, nm), fmaf(h[8 * j + 1], rstd, nm));
+      v.y = pack_bf16(fmaf(h[8 * j + 2], rstd, nm), fmaf(h[8 * j + 3], rstd, nm));
+      v.z = pack_bf16(fmaf(h[8 * j + 4], rstd, nm), fmaf(h[8 * j + 5], rstd, nm));
+      v.w = pack_bf16(fmaf(h[8 * j + 6], rstd, nm), fmaf(h[8 * j + 7], rstd, nm));
+      *reinterpret_cast<uint4*>(tile + (cb * 4 + j) * 2048 + r * 16) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup ----
+  if (warp == 8 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[BAR_A + i], 128); mbar_init(&bars[BAR_X + i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars[BAR_ACC + i], 1); mbar_init(&bars[BAR_UREADY + i], 128); mbar_init(&bars[BAR_UFREE + i], 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bars[BAR_WFULL + i], 1); mbar_init(&bars[BAR_WEMPTY + i], 1); }
+    fence_barrier_init();
+  }
+  if (tid < 256) {  // ones tile: slab 0 (k 0..7) = {1,1,0,...}, slab 1 (k 8..15) = 0
+    uint4 v = make_uint4(tid < 128 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(smem + SM_ONES + tid * 16) = v;
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    // =========================== epilogue warps: one thread per token row ===========================
+    const int T = warp >> 2, r = tid & 127;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t X = lane_base + T * 128, ACC = lane_base + 256 + T * 128;
+    uint8_t* a_tile = smem + SM_A + T * 32768;
+    float* kvs = reinterpret_cast<float*>(smem + SM_KV) + T * 1024;
+    const long long tile_tok0 = ((long long)blockIdx.x * 2 + T) * 128;
+    const bool tile_ok = tile_tok0 < P.M;
+    const long long tok = tile_ok ? tile_tok0 + r : (P.M - 128 + r);  // an out-of-range tile recomputes the last one
+    const long long b = tok / P.N;
+    const int p = (int)(tok - b * P.N);
+    uint32_t ph_acc[2] = {0, 0}, ph_x = 0;
+    float vm[MAX_TOKENS];
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) vm[j] = P.valid != nullptr ? __ldg(P.valid + b * MAX_TOKENS + j) : 1.f;
+
+    // ---- proj_in (13 -> 128) + pre_norm, result (the residual stream) into TMEM ----
+    {
+      float f[13];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        f[c] = __ldg(P.x + (b * 3 + c) * P.N + p);
+        f[3 + c] = __ldg(P.anchors + (b * 3 + c) * P.N + p);
+        const float v = __ldg(P.variances + (b * 3 + c) * P.N + p);
+        f[6 + c] = (P.flags & DFB200_NET_INCLUDE_STD) ? sqrtf(v) : v;
+      }
+      const int part = __ldg(P.assign + tok);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) f[9 + c] = part == c ? 1.f : 0.f;
+      float s = 0.f, q = 0.f;
+      for (int cb = 0; cb < 4; ++cb) {
+        float h[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float* w = P.w_in + (cb * 32 + k) * 13;
+          float acc = __ldg(P.b_in + cb * 32 + k);
+#pragma unroll
+          for (int c = 0; c < 13; ++c) acc = fmaf(f[c], __ldg(w + c), acc);
+          h[k] = acc;
+          s += acc;
+          q = fmaf(acc, acc, q);
+        }
+        tmem_st32(X + cb * 32, h);
+      }
+      tmem_wait_st();
+      const float mean = s * (1.f / D_MODEL);
+      const float rstd = rsqrtf(fmaxf(q * (1.f / D_MODEL) - mean * mean, 0.f) + LN_EPS);
+      for (int cb = 0; cb < 4; ++cb) {
+        float h[32];
+        tmem_ld32(X + cb * 32, h);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          h[k] = fmaf((h[k] - mean) * rstd, __ldg(P.pre_w + cb * 32 + k), __ldg(P.pre_b + cb * 32 + k));
+        tmem_st32(X + cb * 32, h);
+      }
+      tmem_wait_st();
+    }
+
+    for (int l = 0; l < P.depth; ++l) {
+      // K/V of this sample and block -> smem (every row of the tile belongs to the same sample)
+      {
+        const float4* src = reinterpret_cast<const float4*>(P.kv + ((size_t)b * P.depth + l) * 1024);
+        float4* dst = reinterpret_cast<float4*>(kvs);
+        dst[r * 2] = __ldg(src + r * 2);
+        dst[r * 2 + 1] = __ldg(src + r * 2 + 1);
+      }
+      // ---- LN2 -> A ----
+      float mean, rstd;
+      row_stats(X, mean, rstd);
+      row_normalize_to_tile(X, mean, rstd, a_tile, r);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_A + T]);
+      named_bar_sync(1 + T, 128);  // kvs visible to the tile's 128 threads
+
+      // ---- attention over the 4 part tokens, head by head, out of the Q accumulator ----
+      mbar_wait(&bars[BAR_ACC + T * 2 + 0], ph_acc[0]);
+      ph_acc[0] ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 8; ++h) {
+        float qv[16];
+        tmem_ld16(ACC + h * 16, qv);
+        tmem_wait_ld();
+        float sim[MAX_TOKENS];
+#pragma unroll
+        for (int j = 0; j < MAX_TOKENS; ++j) {
+          const float4* kp = reinterpret_cast<const float4*>(kvs + j * D_MODEL + h * 16);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 k4 = kp[i];
+            s = fmaf(qv[4 * i], k4.x, s); s = fmaf(qv[4 * i + 1], k4.y, s);
+            s = fmaf(qv[4 * i + 2], k4.z, s); s = fmaf(qv[4 * i + 3], k4.w, s);
+          }
+          sim[j] = vm[j] == 0.f ? -FLT_MAX : s * 0.25f;  // masked_fill(~mask, -finfo.max)
+        }
+        const float mx = fmaxf(fmaxf(sim[0], sim[1]), fmaxf(sim[2], sim[3]));
+        float pj[MAX_TOKENS], den = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_TOKENS; ++j) { pj[j] = __expf(sim[j] - mx); den += pj[j]; }
+        const float inv = __fdividef(1.f, den);
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_TOKENS; ++j) {
+          const float w = pj[j] * inv;
+          const float4* vp = reinterpret_cast<const float4*>(kvs + 512 + j * D_MODEL + h * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v4 = vp[i];
+            o[4 * i] = fmaf(w, v4.x, o[4 * i]); o[4 * i + 1] = fmaf(w, v4.y, o[4 * i + 1]);
+            o[4 * i + 2] = fmaf(w, v4.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(w, v4.w, o[4 * i + 3]);
+          }
+        }
+        uint4 v0, v1;
+        v0.x = pack_bf16(o[0], o[1]); v0.y = pack_bf16(o[2], o[3]); v0.z = pack_bf16(o[4], o[5]); v0.w = pack_bf16(o[6], o[7]);
+        v1.x = pack_bf16(o[8], o[9]); v1.y = pack_bf16(o[10], o[11]); v1.z = pack_bf16(o[12], o[13]); v1.w = pack_bf16(o[14], o[15]);
+        *reinterpret_cast<uint4*>(a_tile + (2 * h) * 2048 + r * 16) = v0;
+        *reinterpret_cast<uint4*>(a_tile + (2 * h + 1) * 2048 + r * 16) = v1;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_A + T]);
+
+      // ---- x += attn @ Wo^T + bo (accumulated in TMEM by the MMA warp);  LN3 -> A ----
+      mbar_wait(&bars[BAR_X + T], ph_x);
+      ph_x ^= 1;
+      tc_fence_after();
+      row_stats(X, mean, rstd);
+      row_normalize_to_tile(X, mean, rstd, a_tile, r);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_A + T]);
+
+      // ---- GEGLU feed-forward, 16 chunks of 32 value + 32 gate columns ----
+#pragma unroll 1
+      for (int c = 0; c < FF_CHUNKS; ++c) {
+        const int hb = c & 1;
+        const int g = l * FF_CHUNKS + c;  // global chunk counter: U[T][hb] is reused every 2 chunks
+        mbar_wait(&bars[BAR_ACC + T * 2 + hb], ph_acc[hb]);
+        ph_acc[hb] ^= 1;
+        tc_fence_after();
+        float a[32], gt[32];
+        tmem_ld32(ACC + hb * 64, a);
+        tmem_ld32(ACC + hb * 64 + 32, gt);
+        tmem_wait_ld();
+        uint32_t u[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) u[k] = pack_bf16(a[2 * k] * gelu_exact(gt[2 * k]), a[2 * k + 1] * gelu_exact(gt[2 * k + 1]));
+        // the FF-out MMAs of chunk g-2 must have finished reading this U buffer
+        mbar_wait(&bars[BAR_UFREE + T * 2 + hb], (((uint32_t)g >> 1) & 1u) ^ 1u);
+        uint8_t* ut = smem + SM_U + (T * 2 + hb) * 8192;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(ut + j * 2048 + r * 16) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bars[BAR_UREADY + T * 2 + hb]);
+      }
+      mbar_wait(&bars[BAR_X + T], ph_x);
+      ph_x ^= 1;
+      tc_fence_after();
+    }
+
+    // ---- post_norm (folded) + proj_out (128 -> 3) ----
+    {
+      float mean, rstd;
+      row_stats(X, mean, rstd);
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+      for (int cb = 0; cb < 4; ++cb) {
+        float h[32];
+        tmem_ld32(X + cb * 32, h);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float y = (h[k] - mean) * rstd;
+          o0 = fmaf(y, __ldg(P.head + cb * 32 + k), o0);
+          o1 = fmaf(y, __ldg(P.head + D_MODEL + cb * 32 + k), o1);
+          o2 = fmaf(y, __ldg(P.head + 2 * D_MODEL + cb * 32 + k), o2);
+        }
+      }
+      if (tile_ok) {
+        P.eps_out[(b * 3 + 0) * P.N + p] = o0 + __ldg(P.head + 3 * D_MODEL + 0);
+        P.eps_out[(b * 3 + 1) * P.N + p] = o1 + __ldg(P.head + 3 * D_MODEL + 1);
+        P.eps_out[(b * 3 + 2) * P.N + p] = o2 + __ldg(P.head + 3 * D_MODEL + 2);
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // =========================== MMA issuer (lane 0 issues, the warp stays converged) ===========================
+    const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64);
+    const uint32_t ring = smem_u32(smem + SM_RING), a_base = smem_u32(smem + SM_A), u_base = smem_u32(smem + SM_U);
+    const uint64_t ones_desc = make_smem_desc(smem_u32(smem + SM_ONES), 2048, TILE_SBO);
+    uint32_t ph_a[2] = {0, 0}, ph_u[4] = {0, 0, 0, 0};
+    auto pkt_addr = [&](int G) -> uint32_t {  // wait until packet G has landed; its smem address
+      mbar_wait(&bars[BAR_WFULL + G % NSLOT], (uint32_t)(G / NSLOT) & 1u);
+      return ring + (uint32_t)(G % NSLOT) * SLOT_BYTES;
+    };
+    auto release = [&](int G) {
+      if (lane == 0) umma_commit(&bars[BAR_WEMPTY + G % NSLOT]);
+      __syncwarp();
+    };
+    // D[128 x NW] (+)= A[128 x 16*ksteps] . B^T, A rows are 128 (slab 2048 B), B rows are NB (slab NB*16 B)
+    auto gemm = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int NB, int ksteps, uint32_t idesc, uint32_t acc_first) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ad = make_smem_desc(a_addr + ks * 4096, 2048, TILE_SBO);
+        const uint64_t bd = make_smem_desc(b_addr + ks * (NB * 32), NB * 16, TILE_SBO);
+        umma_bf16(d_tmem, ad, bd, idesc, (ks > 0) ? 1u : acc_first);
+      }
+    };
+    auto bias_mma = [&](uint32_t d_tmem, uint32_t slab_addr, uint32_t idesc) {
+      // B = one slab (k 0..7); LBO = 0 aliases it as k 8..15 too, where the ones tile is zero
+      umma_bf16(d_tmem, ones_desc, make_smem_desc(slab_addr, 0, TILE_SBO), idesc, 1u);
+    };
+    for (int l = 0; l < P.depth; ++l) {
+      const int G0 = l * PKT_PER_LAYER;
+      // ---- Q = LN2(x) Wq'^T + bq' ----
+      for (int T = 0; T < 2; ++T) {
+        mbar_wait(&bars[BAR_A + T], ph_a[T]); ph_a[T] ^= 1;
+        const uint32_t p0 = pkt_addr(G0 + 0), p1 = pkt_addr(G0 + 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t d = tmem + 256 + T * 128;
+          gemm(d, a_base + T * 32768, p0, 128, 4, idesc128, 0u);
+          gemm(d, a_base + T * 32768 + 4 * 4096, p1, 128, 4, idesc128, 1u);
+          bias_mma(d, p0 + BIAS_OFF_W128, idesc128);
+          umma_commit(&bars[BAR_ACC + T * 2 + 0]);
+        }
+        __syncwarp();
+      }
+      release(G0 + 0); release(G0 + 1);
+      // ---- x += O Wo^T + bo ----
+      for (int T = 0; T < 2; ++T) {
+        mbar_wait(&bars[BAR_A + T], ph_a[T]); ph_a[T] ^= 1;
+        const uint32_t p2 = pkt_addr(G0 + 2), p3 = pkt_addr(G0 + 3);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t d = tmem + T * 128;
+          gemm(d, a_base + T * 32768, p2, 128, 4, idesc128, 1u);
+          gemm(d, a_base + T * 32768 + 4 * 4096, p3, 128, 4, idesc128, 1u);
+          bias_mma(d, p2 + BIAS_OFF_W128, idesc128);
+          umma_commit(&bars[BAR_X + T]);
+        }
+        __syncwarp();
+      }
+      release(G0 + 2); release(G0 + 3);
+      // ---- feed-forward ----
+      auto ff_in = [&](int T, int c) {  // H_c = LN3(x) W1'_c^T + b1'_c -> ACC_T half (c & 1)
+        const uint32_t pw = pkt_addr(G0 + pkt_w1(c));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t d = tmem + 256 + T * 128 + (c & 1) * 64;
+          gemm(d, a_base + T * 32768, pw, 64, 8, idesc64, 0u);
+          bias_mma(d, pw + BIAS_OFF_W128, idesc64);
+          umma_commit(&bars[BAR_ACC + T * 2 + (c & 1)]);
+        }
+        __syncwarp();
+      };
+      for (int T = 0; T < 2; ++T) { mbar_wait(&bars[BAR_A + T], ph_a[T]); ph_a[T] ^= 1; }
+      ff_in(0, 0); ff_in(1, 0); ff_in(0, 1); ff_in(1, 1);
+      release(G0 + 4); release(G0 + 5);
+      for (int c = 0; c < FF_CHUNKS; ++c) {
+        const int hb = c & 1;
+        for (int T = 0; T < 2; ++T) {
+          mbar_wait(&bars[BAR_UREADY + T * 2 + hb], ph_u[T * 2 + hb]); ph_u[T * 2 + hb] ^= 1;
+          const uint32_t pw = pkt_addr(G0 + pkt_w2(c));
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t d = tmem + T * 128;
+            gemm(d, u_base + (T * 2 + hb) * 8192, pw, 128, 2, idesc128, 1u);
+            if (c == FF_CHUNKS - 1) bias_mma(d, pw + BIAS_OFF_W2, idesc128);
+            umma_commit(&bars[BAR_UFREE + T * 2 + hb]);
+            if (c == FF_CHUNKS - 1) umma_commit(&bars[BAR_X + T]);
+          }
+          __syncwarp();
+          if (c + 2 < FF_CHUNKS) ff_in(T, c + 2);
+        }
+        release(G0 + pkt_w2(c));
+        if (c + 2 < FF_CHUNKS) release(G0 + pkt_w1(c + 2));
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================== weight producer ===========================
+    const int total = P.depth * PKT_PER_LAYER;
+    for (int G = 0; G < total; ++G) {
+      const int slot = G % NSLOT;
+      mbar_wait(&bars[BAR_WEMPTY + slot], ((uint32_t)(G / NSLOT) & 1u) ^ 1u);
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)pkt_bytes(G % PKT_PER_LAYER);
+        mbar_arrive_expect_tx(&bars[BAR_WFULL + slot], bytes);
+        bulk_g2s(smem + SM_RING + slot * SLOT_BYTES, P.stream + (size_t)G * SLOT_BYTES, bytes, &bars[BAR_WFULL + slot]);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
+                        const float* variances, const int* assign, const float* valid_id, float* eps_out, Workspace& ws,
+                        cudaStream_t st) {
+  DFB_REQUIRE(N % 128 == 0, DFB200_ERR_UNSUPPORTED, "denoiser (bf16 mode): N must be a multiple of 128 (got %d); use fp32 mode", N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFB_CUDA(cudaFuncSetAttribute(denoiser_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const float* Pf = reinterpret_cast<const float*>(packed);
+  const uint8_t* S = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
+  TcParams p{};
+  p.stream = S;
+  p.head = reinterpret_cast<const float*>(S + (size_t)L.d.depth * PKT_PER_LAYER * SLOT_BYTES);
+  p.w_in = Pf + L.g[P_IN_W]; p.b_in = Pf + L.g[P_IN_B]; p.pre_w = Pf + L.g[P_PRE_W]; p.pre_b = Pf + L.g[P_PRE_B];
+  p.kv = ws.kv;
+  p.x = x; p.anchors = anchors; p.variances = variances; p.assign = assign; p.valid = valid_id;
+  p.eps_out = eps_out;
+  p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
+  p.M = (long long)B * N;
+  const int grid = cdiv(p.M, 256);
+  denoiser_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// UMMA self-test: D[128 x N] = (Cin) + A[128 x K] . W[N x K]^T (+ bias), bf16 operands, one CTA.
+// Exercises exactly the building blocks of the fused kernel: canonical no-swizzle K-major tiles written
+// by threads, bulk-copied B tile, TMEM alloc / st / ld, accumulate onto pre-stored TMEM, bias-by-ones-MMA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, const float* __restrict__ W,
+                     const float* __restrict__ bias, const float* __restrict__ Cin, float* __restrict__ D,
+                     uint8_t* __restrict__ scratch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_tile = smem;                 // 128 x 128 bf16 max = 32768
+  uint8_t* b_tile = smem + 32768;         // 128 x 128 bf16 max = 32768
+  uint8_t* ones = smem + 65536;           // 4096
+  uint8_t* bslab = smem + 69632;          // 2 slabs x 2048
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 73728);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 73728 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool swap_lbo_sbo = variant & 1, bias_two_slabs = variant & 2, use_bulk = variant & 4;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+  // A: row tid
+  for (int k = 0; k < K; k += 2)
+    *reinterpret_cast<uint32_t*>(a_tile + tile_off(128, tid, k)) = pack_bf16(A[tid * K + k], A[tid * K + k + 1]);
+  uint8_t* bdst = use_bulk ? scratch : b_tile;
+  for (int i = tid; i < N * K / 2; i += 128) {
+    const int n = i / (K / 2), k = (i - n * (K / 2)) * 2;
+    *reinterpret_cast<uint32_t*>(bdst + tile_off(N, n, k)) = pack_bf16(W[n * K + k], W[n * K + k + 1]);
+  }
+  {
+    *reinterpret_cast<uint4*>(ones + tid * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(ones + 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < N) {
+      const float v = bias != nullptr ? bias[tid] : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      uint32_t w0 = (uint32_t)(*reinterpret_cast<const uint16_t*>(&hi)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&lo)) << 16);
+      *reinterpret_cast<uint4*>(bslab + tid * 16) = make_uint4(w0, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(bslab + N * 16 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  fence_proxy_async();
+  __threadfence();
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t row_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  if (use_bulk && tid == 0) {
+    mbar_arrive_expect_tx(&bars[1], (uint32_t)(N * K * 2));
+    bulk_g2s(b_tile, scratch, (uint32_t)(N * K * 2), &bars[1]);
+  }
+  if (Cin != nullptr) {
+    for (int cb = 0; cb < N / 32; ++cb) {
+      float h[32];
+      for (int k = 0; k < 32; ++k) h[k] = Cin[tid * N + cb * 32 + k];
+      tmem_st32(row_addr + cb * 32, h);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    if (use_bulk) mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, N);
+      const uint32_t a_lbo = swap_lbo_sbo ? TILE_SBO : 2048u, a_sbo = swap_lbo_sbo ? 2048u : TILE_SBO;
+      const uint32_t b_lbo = swap_lbo_sbo ? TILE_SBO : (uint32_t)(N * 16), b_sbo = swap_lbo_sbo ? (uint32_t)(N * 16) : TILE_SBO;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ad = make_smem_desc(smem_u32(a_tile) + ks * 4096, a_lbo, a_sbo);
+        const uint64_t bd = make_smem_desc(smem_u32(b_tile) + ks * (N * 32), b_lbo, b_sbo);
+        umma_bf16(tmem, ad, bd, idesc, (ks > 0 || Cin != nullptr) ? 1u : 0u);
+      }
+      if (bias != nullptr) {
+        const uint64_t od = make_smem_desc(smem_u32(ones), a_lbo, a_sbo);
+        const uint64_t bd = bias_two_slabs ? make_smem_desc(smem_u32(bslab), b_lbo, b_sbo)
+                                           : (swap_lbo_sbo ? make_smem_desc(smem_u32(bslab), TILE_SBO, 0u)
+                                                           : make_smem_desc(smem_u32(bslab), 0u, TILE_SBO));
+        umma_bf16(tmem, od, bd, idesc, 1u);
+      }
+      umma_commit(&bars[0]);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bars[0], 0);
+  tc_fence_after();
+  for (int cb = 0; cb < N / 32; ++cb) {
+    float h[32];
+    tmem_ld32(row_addr + cb * 32, h);
+    tmem_wait_ld();
+    for (int k = 0; k < 32; ++k) D[tid * N + cb * 32 + k] = h[k];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
 }  // namespace dfb200
+
+using namespace dfb200;
+
+extern "C" int dfb200_selftest_umma(int variant, int N, int K, const float* A, const float* W, const float* bias,
+                                    const float* Cin, float* D, void* scratch, dfb200_stream_t stream) {
+  DFB_REQUIRE((N == 32 || N == 64 || N == 128) && K >= 16 && K <= 128 && K % 16 == 0, DFB200_ERR_INVALID_ARG,
+              "selftest_umma: N in {32,64,128}, K multiple of 16 in [16,128]");
+  DFB_REQUIRE(!(variant & 4) || scratch != nullptr, DFB200_ERR_INVALID_ARG, "selftest_umma: bulk variant needs scratch");
+  const int smem = 73728 + 128;
+  DFB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(variant, N, K, A, W, bias, Cin, D, reinterpret_cast<uint8_t*>(scratch));
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}

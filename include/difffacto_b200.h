@@ -206,6 +206,15 @@ int dfb200_q_sample(int B, int N, int T, const float* sched, const int* t, const
 int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uint64_t offset,
                          dfb200_stream_t stream);
 
+/* Library self-test of the tcgen05 building blocks the bf16 denoiser is made of (canonical K-major
+ * UMMA shared-memory tiles, cp.async.bulk staging, TMEM alloc/store/load, accumulate onto pre-stored
+ * TMEM, bias as an extra MMA against a ones tile): D[128,N] = Cin + A[128,K].W[N,K]^T + bias with bf16
+ * operands and fp32 accumulation.  N in {32,64,128}, K a multiple of 16 <= 128; bias/Cin may be NULL;
+ * variant: bit0 swap LBO/SBO roles, bit1 two-slab bias tile, bit2 stage W through `scratch`
+ * (>= N*K*2 bytes) with cp.async.bulk.  All pointers are device pointers. */
+int dfb200_selftest_umma(int variant, int N, int K, const float* A, const float* W, const float* bias,
+                         const float* Cin, float* D, void* scratch, dfb200_stream_t stream);
+
 /* Scratch bytes for dfb200_ddpm_sample_loop. */
 size_t dfb200_ddpm_sample_loop_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B,
                                                int N, int T);

@@ -93,8 +93,9 @@ def synthetic_inputs(seed, B, N, all_valid=False):
     t = rng.integers(0, 100, size=(B,)).astype(np.int64)
     noise = rng.standard_normal((B, 3, N)).astype(np.float32)
     T = torch.from_numpy
-    return dict(x=T(x), t=T(t), code=T(code), params=T(params), anchors=T(anchors.astype(np.float32)),
-                variance=T(variance.astype(np.float32)), assign=T(assign), valid=T(valid), noise=T(noise))
+    C = lambda a: T(np.ascontiguousarray(a, dtype=np.float32))  # noqa: E731  (take_along_axis output is not C-contiguous)
+    return dict(x=T(x), t=T(t), code=T(code), params=T(params), anchors=C(anchors), variance=C(variance),
+                assign=T(assign), valid=T(valid), noise=T(noise))
 
 
 # ---------------------------------------------------------------------------------------------

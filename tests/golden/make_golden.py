@@ -109,17 +109,17 @@ def main():
         out[f"{tag}_q_sample"] = xq.numpy()
         out[f"{tag}_mse_loss"] = loss.numpy()
 
-    # short full loop: T=6, B=2, N=64, noise supplied (x_T draw first, then one per step)
+    # short full loop: T=6, B=2, N=128, noise supplied (x_T draw first, then one per step)
     Ts = 6
     diff6 = build_from_cfg(gen_chair_diffusion_cfg(), DIFFUSIONS, num_timesteps=Ts).eval()
     diff6.model.load_state_dict(sd, strict=True)
-    inp = R.synthetic_inputs(21, 2, 64, False)
+    inp = R.synthetic_inputs(21, 2, 128, False)
     rng = np.random.default_rng(99)
-    noises = [torch.from_numpy(rng.standard_normal((2, 3, 64)).astype(np.float32)) for _ in range(Ts + 1)]
+    noises = [torch.from_numpy(rng.standard_normal((2, 3, 128)).astype(np.float32)) for _ in range(Ts + 1)]
     import contextlib, io
     with FixedNoise(list(noises)), contextlib.redirect_stdout(io.StringIO()):
         traj = [(t, {k: v.clone() for k, v in o.items()}) for t, o in diff6.p_sample_loop_progressive(
-            [2, 3, 64], anchors=inp["anchors"], ctx=[inp["code"], inp["params"]], variance=inp["variance"],
+            [2, 3, 128], anchors=inp["anchors"], ctx=[inp["code"], inp["params"]], variance=inp["variance"],
             anchor_assignment=inp["assign"], valid_id=inp["valid"], device="cpu")]
     out["loop_ts"] = np.array([t for t, _ in traj])
     out["loop_samples"] = np.stack([o["sample"].numpy() for _, o in traj])

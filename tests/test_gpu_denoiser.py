@@ -1,0 +1,203 @@
+"""-m gpu: the CUDA denoiser + anchored-DDPM kernels, through the registry classes / C ABI, against
+the golden vectors minted from the real reference (tests/golden) and the oracle port.
+
+Stated tolerances (abs, on eps ~ O(0.5)):
+  fp32 mode (CUDA-core FFMA):  1e-4   (fp32 accumulation order only)
+  bf16 mode (tcgen05, bf16 operands, fp32 accumulate): 3e-2 per step
+DDPM update arithmetic: bit-exact given eps and noise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser_ref as R
+
+pytestmark = pytest.mark.gpu
+CASES = {"a": (11, 3, 64, False), "b": (12, 2, 128, True)}
+TOL = {"fp32": 1e-4, "bf16": 3e-2}
+NET_CFG = dict(type="TransformerNet", in_channels=3, out_channels=3, n_heads=8, d_head=16, depth=5, dropout=0.2,
+               context_dim=262, n_class=4, class_cond=True, use_linear=True, cat_params_to_x=True, use_checkpoint=False,
+               single_attn=True, cat_class_to_x=True)
+DIFF_CFG = dict(type="AnchoredDiffusion", net=NET_CFG, beta_1=1e-4, beta_T=.02, k=1.0, res=False, mode="linear",
+                use_beta=False, rescale_timesteps=False, model_mean_type="epsilon", learn_variance=True, loss_type="mse",
+                include_anchors=False, classifier_weight=1., guidance=False, ddim_sampling=False, ddim_nsteps=25,
+                ddim_discretize="quad", ddim_eta=1.)
+
+
+def build(T, precision):
+    import difffacto_b200 as D
+    diff = D.build_from_cfg(DIFF_CFG, D.DIFFUSIONS, num_timesteps=T)
+    diff.model.load_state_dict(R.synthetic_state_dict(1234), strict=True)
+    diff.model.precision = precision
+    return diff.cuda().eval()
+
+
+def dev(inp):
+    return {k: v.cuda() for k, v in inp.items()}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_denoiser_forward_matches_reference(golden, tag, precision):
+    seed, B, N, av = CASES[tag]
+    if precision == "bf16" and N % 128:
+        pytest.skip("bf16 (tcgen05) mode tiles 128 tokens of one shape: N must be a multiple of 128")
+    d = build(100, precision)
+    i = dev(R.synthetic_inputs(seed, B, N, av))
+    with torch.no_grad():
+        eps = d.model(i["x"], i["t"], [i["code"], i["params"]], anchors=i["anchors"].transpose(1, 2),
+                      anchor_assignment=i["assign"], variances=i["variance"].transpose(1, 2), valid_id=i["valid"])
+    err = np.abs(eps.cpu().numpy() - golden[tag + "_eps"]).max()
+    assert err < TOL[precision], err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_denoiser_forward_full_size_vs_oracle_port(precision):
+    """B=4, N=2048 (the BASELINE point count), random masks incl. an all-absent row (uniform 0.25 attention)."""
+    d = build(100, precision)
+    inp = R.synthetic_inputs(5, 4, 2048, False)
+    inp["valid"][3] = 0.0
+    sd = R.synthetic_state_dict(1234)
+    with torch.no_grad():
+        exp = R.denoiser_forward(sd, inp["x"], inp["t"], [inp["code"], inp["params"]], inp["anchors"], inp["variance"],
+                                 inp["valid"], inp["assign"])
+        i = dev(inp)
+        got = d.model(i["x"], i["t"], [i["code"], i["params"]], anchors=i["anchors"].transpose(1, 2),
+                      anchor_assignment=i["assign"], variances=i["variance"].transpose(1, 2), valid_id=i["valid"])
+    err = (got.cpu() - exp).abs().max().item()
+    assert err < TOL[precision], err
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_ddpm_step_and_q_sample_bit_exact(golden, tag):
+    from difffacto_b200 import _lib
+    seed, B, N, av = CASES[tag]
+    d = build(100, "fp32")
+    i = dev(R.synthetic_inputs(seed, B, N, av))
+    eps = torch.from_numpy(golden[tag + "_eps"]).cuda()
+    out, x0 = torch.empty_like(eps), torch.empty_like(eps)
+    ti = i["t"].to(torch.int32)
+    _lib.check(_lib.load().dfb200_ddpm_step(B, N, 100, _lib.ptr(d._sched(eps.device)), _lib.ptr(ti), _lib.ptr(i["x"]),
+                                            _lib.ptr(eps), _lib.ptr(i["anchors"]), _lib.ptr(i["variance"]),
+                                            _lib.ptr(i["noise"]), _lib.ptr(out), _lib.ptr(x0), _lib.stream()))
+    assert np.array_equal(out.cpu().numpy(), golden[tag + "_sample"])
+    assert np.array_equal(x0.cpu().numpy(), golden[tag + "_pred_xstart"])
+    xq = d.q_sample(i["x"], i["t"], i["anchors"], noise=i["noise"], variance=i["variance"])
+    assert np.array_equal(xq.cpu().numpy(), golden[tag + "_q_sample"])
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_p_sample_and_loss_match_reference(golden, tag):
+    seed, B, N, av = CASES[tag]
+    d = build(100, "fp32")
+    i = dev(R.synthetic_inputs(seed, B, N, av))
+    ctx = [i["code"], i["params"]]
+    with torch.no_grad():
+        out = d.p_sample(i["x"], i["t"], i["anchors"], ctx=ctx, variance=i["variance"], anchor_assignment=i["assign"],
+                         valid_id=i["valid"], noise=i["noise"])
+        out0 = d.p_sample(i["x"], torch.zeros_like(i["t"]), i["anchors"], ctx=ctx, variance=i["variance"],
+                          anchor_assignment=i["assign"], valid_id=i["valid"], noise=i["noise"])
+        loss = d.training_losses(i["x"], i["t"], anchors=i["anchors"], variance=i["variance"], ctx=ctx,
+                                 anchor_assignment=i["assign"], valid_id=i["valid"], flags=torch.ones(B, 1, N, device="cuda"),
+                                 noise=i["noise"])["mse_loss"]
+    assert set(out) == {"sample", "pred_xstart"}
+    assert np.abs(out["sample"].cpu().numpy() - golden[tag + "_sample"]).max() < 1e-4
+    assert np.abs(out["pred_xstart"].cpu().numpy() - golden[tag + "_pred_xstart"]).max() < 1e-3
+    assert np.abs(out0["sample"].cpu().numpy() - golden[tag + "_sample_t0"]).max() < 1e-4
+    assert abs(loss.item() - float(golden[tag + "_mse_loss"])) < 1e-4 * max(1.0, float(golden[tag + "_mse_loss"]))
+
+
+def test_generator_protocol_and_loop_vs_reference(golden):
+    """p_sample_loop_progressive: yields (T,{'sample'}) then (i,{'sample','pred_xstart'}); with the
+    reference's noise the whole trajectory matches the reference's (fp32 mode)."""
+    d = build(6, "fp32")
+    i = dev(R.synthetic_inputs(21, 2, 128, False))
+    noises = [torch.from_numpy(n).cuda() for n in golden["loop_noises"]]
+    ctx = [i["code"], i["params"]]
+    x = torch.sqrt(i["variance"]) * noises[0] + i["anchors"]
+    gen = d.p_sample_loop_progressive([2, 3, 128], anchors=i["anchors"], ctx=ctx, variance=i["variance"],
+                                      anchor_assignment=i["assign"], valid_id=i["valid"], noise=x)
+    t, o = next(gen)
+    assert t == 6 and set(o) == {"sample"}
+    # drive the remaining steps with the reference's per-step noise through p_sample
+    kept = [o["sample"]]
+    for k, step in enumerate(range(5, -1, -1)):
+        tt = torch.full((2,), step, dtype=torch.long, device="cuda")
+        o = d.p_sample(kept[-1], tt, i["anchors"], ctx=ctx, variance=i["variance"], anchor_assignment=i["assign"],
+                       valid_id=i["valid"], noise=noises[k + 1])
+        kept.append(o["sample"])
+        assert np.abs(o["sample"].cpu().numpy() - golden["loop_samples"][k + 1]).max() < 2e-4
+    # generator itself: protocol + retained tensors are not clobbered by later steps
+    torch.manual_seed(0)
+    outs = list(d.p_sample_loop_progressive([2, 3, 128], anchors=i["anchors"], ctx=ctx, variance=i["variance"],
+                                            anchor_assignment=i["assign"], valid_id=i["valid"]))
+    assert [t for t, _ in outs] == [6, 5, 4, 3, 2, 1, 0]
+    assert all(set(o) == {"sample", "pred_xstart"} for _, o in outs[1:])
+    snap = [o["sample"].clone() for _, o in outs]
+    torch.manual_seed(0)
+    again = list(d.p_sample_loop_progressive([2, 3, 128], anchors=i["anchors"], ctx=ctx, variance=i["variance"],
+                                             anchor_assignment=i["assign"], valid_id=i["valid"]))
+    for (_, a), s, (_, b) in zip(outs, snap, again):
+        assert torch.equal(a["sample"], s) and torch.equal(a["sample"], b["sample"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_sample_loop_matches_stepwise_and_reference(golden, precision):
+    d = build(6, precision)
+    i = dev(R.synthetic_inputs(21, 2, 128, False))
+    noises = torch.from_numpy(golden["loop_noises"]).cuda()
+    ctx = [i["code"], i["params"]]
+    from difffacto_b200 import _lib
+    lib = _lib.load()
+    x = noises[0].clone()
+    cfg, mode = d.model.c_cfg(), d.model.mode()
+    nws = lib.dfb200_ddpm_sample_loop_workspace_bytes(cfg, mode, 2, 128, 6)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    traj = torch.empty(2, 2, 3, 128, device="cuda")
+    cc = torch.cat(ctx, 1).contiguous()
+    step_noise = noises[1:].contiguous()
+    _lib.check(lib.dfb200_ddpm_sample_loop(cfg, _lib.ptr(d.model.packed_weights()), mode, 2, 128, 6, _lib.ptr(d._sched(x.device)),
+                                           _lib.ptr(x), 1, _lib.ptr(cc), _lib.ptr(i["anchors"]), _lib.ptr(i["variance"]),
+                                           _lib.ptr(i["assign"]), _lib.ptr(i["valid"]), _lib.ptr(step_noise), 0,
+                                           _lib.ptr(traj), 2, _lib.ptr(ws), nws, _lib.stream()))
+    tol = 5e-4 if precision == "fp32" else 5e-2
+    assert np.abs(x.cpu().numpy() - golden["loop_samples"][-1]).max() < tol
+    # traj slots: t=2 -> slot 0, t=4 -> slot 1 (x after step t)
+    assert np.abs(traj[0].cpu().numpy() - golden["loop_samples"][6 - 2]).max() < tol
+    assert np.abs(traj[1].cpu().numpy() - golden["loop_samples"][6 - 4]).max() < tol
+
+
+def test_philox_loop_equals_explicit_noise_loop():
+    """rng='philox' must equal a run fed with dfb200_philox_normal draws (draw T = x_T, draw i = step i)."""
+    from difffacto_b200 import _lib
+    lib = _lib.load()
+    T, B, N = 5, 2, 128
+    d = build(T, "fp32")
+    i = dev(R.synthetic_inputs(33, B, N, False))
+    ctx = [i["code"], i["params"]]
+    seed = 1234567
+    a = d.p_sample_loop([B, 3, N], i["anchors"], ctx=ctx, variance=i["variance"], anchor_assignment=i["assign"],
+                        valid_id=i["valid"], rng="philox", seed=seed)
+    draws = torch.empty(T + 1, B, 3, N, device="cuda")
+    for k in range(T + 1):
+        _lib.check(lib.dfb200_philox_normal(_lib.ptr(draws[k]), B * 3 * N, seed, k, _lib.stream()))
+    x = torch.sqrt(i["variance"]) * draws[T] + i["anchors"]
+    for step in range(T - 1, -1, -1):
+        tt = torch.full((B,), step, dtype=torch.long, device="cuda")
+        x = d.p_sample(x, tt, i["anchors"], ctx=ctx, variance=i["variance"], anchor_assignment=i["assign"],
+                       valid_id=i["valid"], noise=draws[step])["sample"]
+    assert (a - x).abs().max().item() < 1e-5
+    z = draws.flatten().cpu().numpy()
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05 and np.abs(z).max() < 7
+
+
+def test_seeded_torch_rng_reproducibility():
+    d = build(4, "fp32")
+    i = dev(R.synthetic_inputs(3, 2, 64, True))
+    kw = dict(ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"], valid_id=i["valid"])
+    torch.manual_seed(7)
+    a = d.p_sample_loop([2, 3, 128], i["anchors"], **kw)
+    torch.manual_seed(7)
+    final = None
+    for t, o in d.p_sample_loop_progressive([2, 3, 128], i["anchors"], **kw):
+        final = o["sample"]
+    assert (a - final).abs().max().item() < 1e-5  # same torch generator consumption order in both paths

@@ -1,0 +1,23 @@
+"""-m gpu: the tcgen05 building blocks (dfb200_selftest_umma) against a bf16-operand fp32-accumulate reference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("variant", [0, 2, 4, 6])
+@pytest.mark.parametrize("N,K", [(128, 128), (64, 128), (128, 32), (32, 16)])
+def test_umma_selftest(variant, N, K):
+    from tools.diag_umma import ref
+    from difffacto_b200 import _lib
+    torch.manual_seed(N + K + variant)
+    A = torch.randn(128, K, device="cuda")
+    W = torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    Cin = torch.randn(128, N, device="cuda")
+    D = torch.empty(128, N, device="cuda")
+    scratch = torch.zeros(N * K * 2 + 256, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.load().dfb200_selftest_umma(variant, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(Cin),
+                                                _lib.ptr(D), _lib.ptr(scratch), _lib.stream()))
+    torch.cuda.synchronize()
+    assert (D - ref(A, W, bias, Cin)).abs().max().item() < 2e-4 * K ** 0.5 + 1e-4
