@@ -67,6 +67,7 @@ __global__ void pack_tile_kernel(uint8_t* __restrict__ dst, int R, int KC, const
   if (geglu_chunk >= 0) row = r < 32 ? 32 * geglu_chunk + r : D_FF + 32 * geglu_chunk + (r - 32);
   float v = __ldg(src + (size_t)row * ld + k0 + k);
   if (gamma != nullptr) v *= __ldg(gamma + k0 + k);
+  if (geglu_chunk >= 0 && r < 32) v *= 0.5f;  // value rows carry gelu's 0.5:  a*gelu(g) = (a/2)*g*(1+tanh(..))
   *reinterpret_cast<__nv_bfloat16*>(dst + tile_off(R, r, k)) = __float2bfloat16_rn(v);
 }
 // bias slab: R rows x 8 k-values (16 B per row); k=0: bf16 hi, k=1: bf16 lo of  bias[row] + W[row,:].beta
@@ -79,6 +80,7 @@ __global__ void pack_bias_kernel(uint8_t* __restrict__ dst, int R, const float* 
   float v = bias != nullptr ? __ldg(bias + row) : 0.f;
   if (beta != nullptr)
     for (int k = 0; k < ld; ++k) v = fmaf(__ldg(W + (size_t)row * ld + k), __ldg(beta + k), v);
+  if (geglu_chunk >= 0 && r < 32) v *= 0.5f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dst + r * 16);
@@ -162,7 +164,25 @@ struct TcParams {
   long long M;
 };
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// Packed fp32x2 math (FFMA2 on sm_100): the CUDA-core epilogues are the bottleneck of this kernel (the
+// tensor pipe waits on them), so every elementwise chain below processes two columns per instruction.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GEGLU for two columns: (a/2 arrives from the MMA) * g * (1 + tanh(g*(c0 + c1 g^2))).
+// tanh-form GELU with (c0, c1) refit against the exact erf GELU (max abs error 2.7e-4 over R, below the bf16
+// rounding of the result); 5 packed FMA-pipe instructions + 2 MUFU.TANH per column pair (erff costs ~45/column).
+__device__ __forceinline__ float2 geglu2(float2 a_half, float2 g) {
+  const float2 g2 = __fmul2_rn(g, g);
+  const float2 in = __fmul2_rn(g, __ffma2_rn(g2, f2s(0.034700932528f), f2s(0.800156991001f)));
+  const float2 t = f2(tanh_approx(in.x), tanh_approx(in.y));
+  const float2 ag = __fmul2_rn(a_half, g);
+  return __ffma2_rn(ag, t, ag);
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -170,15 +190,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // one thread = one token row: mean / rstd of the 128-wide fp32 row held in TMEM columns [col, col+128)
 __device__ __forceinline__ void row_stats(uint32_t taddr, float& mean, float& rstd) {
-  float s = 0.f, q = 0.f;
+  float2 s2 = f2s(0.f), q2 = f2s(0.f);
 #pragma unroll
   for (int cb = 0; cb < 4; ++cb) {
     float h[32];
     tmem_ld32(taddr + cb * 32, h);
     tmem_wait_ld();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { s += h[k]; q = fmaf(h[k], h[k], q); }
+    for (int k = 0; k < 16; ++k) {
+      const float2 v = f2(h[2 * k], h[2 * k + 1]);
+      s2 = __fadd2_rn(s2, v);
+      q2 = __ffma2_rn(v, v, q2);
+    }
   }
+  const float s = s2.x + s2.y, q = q2.x + q2.y;
   mean = s * (1.f / D_MODEL);
   const float var = fmaxf(q * (1.f / D_MODEL) - mean * mean, 0.f);
   rstd = rsqrtf(var + LN_EPS);
@@ -186,7 +211,7 @@ __device__ __forceinline__ void row_stats(uint32_t taddr, float& mean, float& rs
 
 // normalise the TMEM row (gain/bias are folded into the next weights) and write it as the bf16 A operand row
 __device__ __forceinline__ void row_normalize_to_tile(uint32_t taddr, float mean, float rstd, uint8_t* tile, int r) {
-  const float nm = -mean * rstd;
+  const float2 nm = f2s(-mean * rstd), rs = f2s(rstd);
 #pragma unroll
   for (int cb = 0; cb < 4; ++cb) {
     float h[32];
@@ -194,21 +219,33 @@ __device__ __forceinline__ void row_normalize_to_tile(uint32_t taddr, float mean
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint4 v;
-      v.x = pack_bf16(fmaf(h[8 * j + 0], rstd, nm), fmaf(h[8 * j + 1], rstd, nm));
-      v.y = pack_bf16(fmaf(h[8 * j + 2], rstd, nm), fmaf(h[8 * j + 3], rstd, nm));
-      v.z = pack_bf16(fmaf(h[8 * j + 4], rstd, nm), fmaf(h[8 * j + 5], rstd, nm));
-      v.w = pack_bf16(fmaf(h[8 * j + 6], rstd, nm), fmaf(h[8 * j + 7], rstd, nm));
-      *reinterpret_cast<uint4*>(tile + (cb * 4 + j) * 2048 + r * 16) = v;
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 y = __ffma2_rn(f2(h[8 * j + 2 * i], h[8 * j + 2 * i + 1]), rs, nm);
+        w[i] = pack_bf16(y.x, y.y);
+      }
+      *reinterpret_cast<uint4*>(tile + (cb * 4 + j) * 2048 + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+}
+
+// D[128 x NB] (+)= A[128 x 16*KSTEPS] . B[NB x 16*KSTEPS]^T.  A tiles have 128 rows (k-slab = 2048 B), B tiles NB rows
+// (k-slab = NB*16 B).  Fully unrolled so that descriptors are (uniform base + immediate).
+template <int NB, int KSTEPS>
+__device__ __forceinline__ void umma_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    umma_bf16(d_tmem, make_smem_desc(a_addr + ks * 4096, 2048, TILE_SBO), make_smem_desc(b_addr + ks * (NB * 32), NB * 16, TILE_SBO),
+              idesc, ks > 0 ? 1u : acc_first);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // warp-uniform by construction (helps uniform-datapath codegen)
 
   // ---- one-time setup ----
   if (warp == 8 && lane == 0) {
@@ -227,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tmem != 0u) __trap();  // a 512-column allocation owns the whole TMEM: base = lane 0, column 0 (the MMA path relies on it)
 
   if (warp < 8) {
     // =========================== epilogue warps: one thread per token row ===========================
@@ -318,37 +356,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
 #pragma unroll
         for (int j = 0; j < MAX_TOKENS; ++j) {
           const float4* kp = reinterpret_cast<const float4*>(kvs + j * D_MODEL + h * 16);
-          float s = 0.f;
+          float2 s2 = f2s(0.f);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 k4 = kp[i];
-            s = fmaf(qv[4 * i], k4.x, s); s = fmaf(qv[4 * i + 1], k4.y, s);
-            s = fmaf(qv[4 * i + 2], k4.z, s); s = fmaf(qv[4 * i + 3], k4.w, s);
+            s2 = __ffma2_rn(f2(qv[4 * i], qv[4 * i + 1]), f2(k4.x, k4.y), s2);
+            s2 = __ffma2_rn(f2(qv[4 * i + 2], qv[4 * i + 3]), f2(k4.z, k4.w), s2);
           }
-          sim[j] = vm[j] == 0.f ? -FLT_MAX : s * 0.25f;  // masked_fill(~mask, -finfo.max)
+          sim[j] = vm[j] == 0.f ? -FLT_MAX : (s2.x + s2.y) * 0.25f;  // masked_fill(~mask, -finfo.max)
         }
         const float mx = fmaxf(fmaxf(sim[0], sim[1]), fmaxf(sim[2], sim[3]));
         float pj[MAX_TOKENS], den = 0.f;
 #pragma unroll
         for (int j = 0; j < MAX_TOKENS; ++j) { pj[j] = __expf(sim[j] - mx); den += pj[j]; }
         const float inv = __fdividef(1.f, den);
-        float o[16];
+        float2 o[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = 0.f;
+        for (int i = 0; i < 8; ++i) o[i] = f2s(0.f);
 #pragma unroll
         for (int j = 0; j < MAX_TOKENS; ++j) {
-          const float w = pj[j] * inv;
+          const float2 w = f2s(pj[j] * inv);
           const float4* vp = reinterpret_cast<const float4*>(kvs + 512 + j * D_MODEL + h * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v4 = vp[i];
-            o[4 * i] = fmaf(w, v4.x, o[4 * i]); o[4 * i + 1] = fmaf(w, v4.y, o[4 * i + 1]);
-            o[4 * i + 2] = fmaf(w, v4.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(w, v4.w, o[4 * i + 3]);
+            o[2 * i] = __ffma2_rn(w, f2(v4.x, v4.y), o[2 * i]);
+            o[2 * i + 1] = __ffma2_rn(w, f2(v4.z, v4.w), o[2 * i + 1]);
           }
         }
         uint4 v0, v1;
-        v0.x = pack_bf16(o[0], o[1]); v0.y = pack_bf16(o[2], o[3]); v0.z = pack_bf16(o[4], o[5]); v0.w = pack_bf16(o[6], o[7]);
-        v1.x = pack_bf16(o[8], o[9]); v1.y = pack_bf16(o[10], o[11]); v1.z = pack_bf16(o[12], o[13]); v1.w = pack_bf16(o[14], o[15]);
+        v0.x = pack_bf16(o[0].x, o[0].y); v0.y = pack_bf16(o[1].x, o[1].y); v0.z = pack_bf16(o[2].x, o[2].y); v0.w = pack_bf16(o[3].x, o[3].y);
+        v1.x = pack_bf16(o[4].x, o[4].y); v1.y = pack_bf16(o[5].x, o[5].y); v1.z = pack_bf16(o[6].x, o[6].y); v1.w = pack_bf16(o[7].x, o[7].y);
         *reinterpret_cast<uint4*>(a_tile + (2 * h) * 2048 + r * 16) = v0;
         *reinterpret_cast<uint4*>(a_tile + (2 * h + 1) * 2048 + r * 16) = v1;
       }
@@ -380,7 +418,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         tmem_wait_ld();
         uint32_t u[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) u[k] = pack_bf16(a[2 * k] * gelu_exact(gt[2 * k]), a[2 * k + 1] * gelu_exact(gt[2 * k + 1]));
+        for (int k = 0; k < 16; ++k) {
+          const float2 y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]));
+          u[k] = pack_bf16(y.x, y.y);
+        }
         // the FF-out MMAs of chunk g-2 must have finished reading this U buffer
         mbar_wait(&bars[BAR_UFREE + T * 2 + hb], (((uint32_t)g >> 1) & 1u) ^ 1u);
         uint8_t* ut = smem + SM_U + (T * 2 + hb) * 8192;
@@ -421,96 +462,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     }
     tc_fence_before();
   } else if (warp == 8) {
-    // =========================== MMA issuer (lane 0 issues, the warp stays converged) ===========================
-    const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64);
-    const uint32_t ring = smem_u32(smem + SM_RING), a_base = smem_u32(smem + SM_A), u_base = smem_u32(smem + SM_U);
-    const uint64_t ones_desc = make_smem_desc(smem_u32(smem + SM_ONES), 2048, TILE_SBO);
-    uint32_t ph_a[2] = {0, 0}, ph_u[4] = {0, 0, 0, 0};
+    // =========================== MMA issuer ===========================
+    // The whole warp runs this control flow (waits included); one elected lane issues tcgen05.mma / commit.
+    // Everything that feeds a descriptor is warp-uniform by construction (constants, loop counters, the TMEM
+    // base which is 0 for a 512-column allocation), so the issue sequence stays on the uniform datapath.
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t ring = sbase + SM_RING, a_base = sbase + SM_A, u_base = sbase + SM_U;
+    const uint64_t ones_desc = make_smem_desc(sbase + SM_ONES, 2048, TILE_SBO);
+    uint32_t ph_a0 = 0, ph_a1 = 0, ph_u = 0;  // ph_u: bit (T*2+hb)
     auto pkt_addr = [&](int G) -> uint32_t {  // wait until packet G has landed; its smem address
       mbar_wait(&bars[BAR_WFULL + G % NSLOT], (uint32_t)(G / NSLOT) & 1u);
       return ring + (uint32_t)(G % NSLOT) * SLOT_BYTES;
     };
-    auto release = [&](int G) {
-      if (lane == 0) umma_commit(&bars[BAR_WEMPTY + G % NSLOT]);
-      __syncwarp();
-    };
-    // D[128 x NW] (+)= A[128 x 16*ksteps] . B^T, A rows are 128 (slab 2048 B), B rows are NB (slab NB*16 B)
-    auto gemm = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int NB, int ksteps, uint32_t idesc, uint32_t acc_first) {
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + ks * 4096, 2048, TILE_SBO);
-        const uint64_t bd = make_smem_desc(b_addr + ks * (NB * 32), NB * 16, TILE_SBO);
-        umma_bf16(d_tmem, ad, bd, idesc, (ks > 0) ? 1u : acc_first);
-      }
-    };
-    auto bias_mma = [&](uint32_t d_tmem, uint32_t slab_addr, uint32_t idesc) {
-      // B = one slab (k 0..7); LBO = 0 aliases it as k 8..15 too, where the ones tile is zero
-      umma_bf16(d_tmem, ones_desc, make_smem_desc(slab_addr, 0, TILE_SBO), idesc, 1u);
+    auto wait_a = [&](int T) {
+      if (T == 0) { mbar_wait(&bars[BAR_A + 0], ph_a0); ph_a0 ^= 1; }
+      else { mbar_wait(&bars[BAR_A + 1], ph_a1); ph_a1 ^= 1; }
     };
     for (int l = 0; l < P.depth; ++l) {
       const int G0 = l * PKT_PER_LAYER;
       // ---- Q = LN2(x) Wq'^T + bq' ----
+#pragma unroll
       for (int T = 0; T < 2; ++T) {
-        mbar_wait(&bars[BAR_A + T], ph_a[T]); ph_a[T] ^= 1;
+        wait_a(T);
         const uint32_t p0 = pkt_addr(G0 + 0), p1 = pkt_addr(G0 + 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tmem + 256 + T * 128;
-          gemm(d, a_base + T * 32768, p0, 128, 4, idesc128, 0u);
-          gemm(d, a_base + T * 32768 + 4 * 4096, p1, 128, 4, idesc128, 1u);
-          bias_mma(d, p0 + BIAS_OFF_W128, idesc128);
+        if (elect_one()) {
+          const uint32_t d = 256 + T * 128;
+          umma_gemm<128, 4>(d, a_base + T * 32768, p0, idesc128, 0u);
+          umma_gemm<128, 4>(d, a_base + T * 32768 + 4 * 4096, p1, idesc128, 1u);
+          umma_bf16(d, ones_desc, make_smem_desc(p0 + BIAS_OFF_W128, 0, TILE_SBO), idesc128, 1u);
           umma_commit(&bars[BAR_ACC + T * 2 + 0]);
         }
         __syncwarp();
       }
-      release(G0 + 0); release(G0 + 1);
+      if (elect_one()) { umma_commit(&bars[BAR_WEMPTY + (G0 + 0) % NSLOT]); umma_commit(&bars[BAR_WEMPTY + (G0 + 1) % NSLOT]); }
+      __syncwarp();
       // ---- x += O Wo^T + bo ----
+#pragma unroll
       for (int T = 0; T < 2; ++T) {
-        mbar_wait(&bars[BAR_A + T], ph_a[T]); ph_a[T] ^= 1;
+        wait_a(T);
         const uint32_t p2 = pkt_addr(G0 + 2), p3 = pkt_addr(G0 + 3);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tmem + T * 128;
-          gemm(d, a_base + T * 32768, p2, 128, 4, idesc128, 1u);
-          gemm(d, a_base + T * 32768 + 4 * 4096, p3, 128, 4, idesc128, 1u);
-          bias_mma(d, p2 + BIAS_OFF_W128, idesc128);
+        if (elect_one()) {
+          const uint32_t d = T * 128;
+          umma_gemm<128, 4>(d, a_base + T * 32768, p2, idesc128, 1u);
+          umma_gemm<128, 4>(d, a_base + T * 32768 + 4 * 4096, p3, idesc128, 1u);
+          umma_bf16(d, ones_desc, make_smem_desc(p2 + BIAS_OFF_W128, 0, TILE_SBO), idesc128, 1u);
           umma_commit(&bars[BAR_X + T]);
         }
         __syncwarp();
       }
-      release(G0 + 2); release(G0 + 3);
+      if (elect_one()) { umma_commit(&bars[BAR_WEMPTY + (G0 + 2) % NSLOT]); umma_commit(&bars[BAR_WEMPTY + (G0 + 3) % NSLOT]); }
+      __syncwarp();
       // ---- feed-forward ----
       auto ff_in = [&](int T, int c) {  // H_c = LN3(x) W1'_c^T + b1'_c -> ACC_T half (c & 1)
         const uint32_t pw = pkt_addr(G0 + pkt_w1(c));
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tmem + 256 + T * 128 + (c & 1) * 64;
-          gemm(d, a_base + T * 32768, pw, 64, 8, idesc64, 0u);
-          bias_mma(d, pw + BIAS_OFF_W128, idesc64);
+        if (elect_one()) {
+          const uint32_t d = 256 + T * 128 + (c & 1) * 64;
+          umma_gemm<64, 8>(d, a_base + T * 32768, pw, idesc64, 0u);
+          umma_bf16(d, ones_desc, make_smem_desc(pw + BIAS_OFF_W128, 0, TILE_SBO), idesc64, 1u);
           umma_commit(&bars[BAR_ACC + T * 2 + (c & 1)]);
         }
         __syncwarp();
       };
-      for (int T = 0; T < 2; ++T) { mbar_wait(&bars[BAR_A + T], ph_a[T]); ph_a[T] ^= 1; }
+      wait_a(0); wait_a(1);
       ff_in(0, 0); ff_in(1, 0); ff_in(0, 1); ff_in(1, 1);
-      release(G0 + 4); release(G0 + 5);
+      if (elect_one()) { umma_commit(&bars[BAR_WEMPTY + (G0 + 4) % NSLOT]); umma_commit(&bars[BAR_WEMPTY + (G0 + 5) % NSLOT]); }
+      __syncwarp();
+#pragma unroll 1
       for (int c = 0; c < FF_CHUNKS; ++c) {
         const int hb = c & 1;
+#pragma unroll
         for (int T = 0; T < 2; ++T) {
-          mbar_wait(&bars[BAR_UREADY + T * 2 + hb], ph_u[T * 2 + hb]); ph_u[T * 2 + hb] ^= 1;
+          const int ub = T * 2 + hb;
+          mbar_wait(&bars[BAR_UREADY + ub], (ph_u >> ub) & 1u);
+          ph_u ^= 1u << ub;
           const uint32_t pw = pkt_addr(G0 + pkt_w2(c));
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t d = tmem + T * 128;
-            gemm(d, u_base + (T * 2 + hb) * 8192, pw, 128, 2, idesc128, 1u);
-            if (c == FF_CHUNKS - 1) bias_mma(d, pw + BIAS_OFF_W2, idesc128);
-            umma_commit(&bars[BAR_UFREE + T * 2 + hb]);
+          if (elect_one()) {
+            const uint32_t d = T * 128;
+            umma_gemm<128, 2>(d, u_base + ub * 8192, pw, idesc128, 1u);
+            if (c == FF_CHUNKS - 1) umma_bf16(d, ones_desc, make_smem_desc(pw + BIAS_OFF_W2, 0, TILE_SBO), idesc128, 1u);
+            umma_commit(&bars[BAR_UFREE + ub]);
             if (c == FF_CHUNKS - 1) umma_commit(&bars[BAR_X + T]);
           }
           __syncwarp();
           if (c + 2 < FF_CHUNKS) ff_in(T, c + 2);
         }
-        release(G0 + pkt_w2(c));
-        if (c + 2 < FF_CHUNKS) release(G0 + pkt_w1(c + 2));
+        if (elect_one()) {
+          umma_commit(&bars[BAR_WEMPTY + (G0 + pkt_w2(c)) % NSLOT]);
+          if (c + 2 < FF_CHUNKS) umma_commit(&bars[BAR_WEMPTY + (G0 + pkt_w1(c + 2)) % NSLOT]);
+        }
+        __syncwarp();
       }
     }
     tc_fence_before();
@@ -520,7 +565,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     for (int G = 0; G < total; ++G) {
       const int slot = G % NSLOT;
       mbar_wait(&bars[BAR_WEMPTY + slot], ((uint32_t)(G / NSLOT) & 1u) ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t bytes = (uint32_t)pkt_bytes(G % PKT_PER_LAYER);
         mbar_arrive_expect_tx(&bars[BAR_WFULL + slot], bytes);
         bulk_g2s(smem + SM_RING + slot * SLOT_BYTES, P.stream + (size_t)G * SLOT_BYTES, bytes, &bars[BAR_WFULL + slot]);
