@@ -162,6 +162,7 @@ struct TcParams {
   float* eps_out;
   int N, depth, flags;
   long long M;
+  long long* dbg;  // optional timeline buffer (DFB200_TC_TIMELINE env): CTA 0 records clock64() at phase boundaries
 };
 
 // Packed fp32x2 math (FFMA2 on sm_100): the CUDA-core epilogues are the bottleneck of this kernel (the
@@ -183,6 +184,12 @@ __device__ __forceinline__ float2 geglu2(float2 a_half, float2 g) {
   const float2 ag = __fmul2_rn(a_half, g);
   return __ffma2_rn(ag, t, ag);
 }
+
+// timeline instrumentation (off unless a buffer is supplied): slot layout [who][event], who 0 = tile-0 row 0, 1 = MMA lane
+#define TL(who, ev)                                                                                  \
+  do {                                                                                               \
+    if (P.dbg != nullptr && blockIdx.x == 0 && tl_on) P.dbg[(who) * 512 + (ev)] = clock64();         \
+  } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -240,6 +247,18 @@ __device__ __forceinline__ void umma_gemm(uint32_t d_tmem, uint32_t a_addr, uint
               idesc, ks > 0 ? 1u : acc_first);
 }
 
+// Same for both tiles of the CTA against ONE weight tile, K-steps interleaved (T0,k),(T1,k).
+template <int NB, int KSTEPS>
+__device__ __forceinline__ void umma_gemm2(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a1, uint32_t b_addr, uint32_t idesc,
+                                           uint32_t acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint64_t bd = make_smem_desc(b_addr + ks * (NB * 32), NB * 16, TILE_SBO);
+    umma_bf16(d0, make_smem_desc(a0 + ks * 4096, 2048, TILE_SBO), bd, idesc, ks > 0 ? 1u : acc_first);
+    umma_bf16(d1, make_smem_desc(a1 + ks * 4096, 2048, TILE_SBO), bd, idesc, ks > 0 ? 1u : acc_first);
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -275,6 +294,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     float* kvs = reinterpret_cast<float*>(smem + SM_KV) + T * 1024;
     const long long tile_tok0 = ((long long)blockIdx.x * 2 + T) * 128;
     const bool tile_ok = tile_tok0 < P.M;
+    const bool tl_on = tid == 0;
+    TL(0, 0);
     const long long tok = tile_ok ? tile_tok0 + r : (P.M - 128 + r);  // an out-of-range tile recomputes the last one
     const long long b = tok / P.N;
     const int p = (int)(tok - b * P.N);
@@ -284,7 +305,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     for (int j = 0; j < MAX_TOKENS; ++j) vm[j] = P.valid != nullptr ? __ldg(P.valid + b * MAX_TOKENS + j) : 1.f;
 
     // ---- proj_in (13 -> 128) + pre_norm, result (the residual stream) into TMEM ----
+    // proj_in weights are staged transposed ([feature][output], fp32) in the (still unused) U-tile region so that one
+    // broadcast LDS.128 feeds two FFMA2 (4 outputs) -- the straightforward per-output uniform LDG version of this
+    // prologue cost 11% of the kernel.
     {
+      float* wt = reinterpret_cast<float*>(smem + SM_U);  // [13][128] weights, [128] bias, [128] pre_norm.w, [128] pre_norm.b
+      const int et = tid;                                  // 256 epilogue threads
+      for (int i = et; i < D_MODEL * 13; i += 256) {
+        const int k = i / 13, c = i - k * 13;              // coalesced read of w_in[k][c]
+        wt[c * D_MODEL + k] = __ldg(P.w_in + i);
+      }
+      if (et < D_MODEL) {
+        wt[13 * D_MODEL + et] = __ldg(P.b_in + et);
+        wt[14 * D_MODEL + et] = __ldg(P.pre_w + et);
+        wt[15 * D_MODEL + et] = __ldg(P.pre_b + et);
+      }
       float f[13];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -296,37 +331,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       const int part = __ldg(P.assign + tok);
 #pragma unroll
       for (int c = 0; c < 4; ++c) f[9 + c] = part == c ? 1.f : 0.f;
-      float s = 0.f, q = 0.f;
+      named_bar_sync(3, 256);
+      float2 s2 = f2s(0.f), q2 = f2s(0.f);
+#pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
         float h[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float* w = P.w_in + (cb * 32 + k) * 13;
-          float acc = __ldg(P.b_in + cb * 32 + k);
+        for (int kq = 0; kq < 8; ++kq) {
+          const float4 bi = *reinterpret_cast<const float4*>(wt + 13 * D_MODEL + cb * 32 + kq * 4);
+          float2 a0 = f2(bi.x, bi.y), a1 = f2(bi.z, bi.w);
 #pragma unroll
-          for (int c = 0; c < 13; ++c) acc = fmaf(f[c], __ldg(w + c), acc);
-          h[k] = acc;
-          s += acc;
-          q = fmaf(acc, acc, q);
+          for (int c = 0; c < 13; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + c * D_MODEL + cb * 32 + kq * 4);
+            a0 = __ffma2_rn(f2s(f[c]), f2(w.x, w.y), a0);
+            a1 = __ffma2_rn(f2s(f[c]), f2(w.z, w.w), a1);
+          }
+          h[kq * 4] = a0.x; h[kq * 4 + 1] = a0.y; h[kq * 4 + 2] = a1.x; h[kq * 4 + 3] = a1.y;
+          s2 = __fadd2_rn(s2, __fadd2_rn(a0, a1));
+          q2 = __ffma2_rn(a0, a0, q2);
+          q2 = __ffma2_rn(a1, a1, q2);
         }
         tmem_st32(X + cb * 32, h);
       }
       tmem_wait_st();
-      const float mean = s * (1.f / D_MODEL);
-      const float rstd = rsqrtf(fmaxf(q * (1.f / D_MODEL) - mean * mean, 0.f) + LN_EPS);
+      const float mean = (s2.x + s2.y) * (1.f / D_MODEL);
+      const float rstd = rsqrtf(fmaxf((q2.x + q2.y) * (1.f / D_MODEL) - mean * mean, 0.f) + LN_EPS);
+      const float2 rs = f2s(rstd), nm = f2s(-mean * rstd);
+#pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
         float h[32];
         tmem_ld32(X + cb * 32, h);
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          h[k] = fmaf((h[k] - mean) * rstd, __ldg(P.pre_w + cb * 32 + k), __ldg(P.pre_b + cb * 32 + k));
+        for (int k = 0; k < 16; ++k) {
+          const float2 g = *reinterpret_cast<const float2*>(wt + 14 * D_MODEL + cb * 32 + 2 * k);
+          const float2 be = *reinterpret_cast<const float2*>(wt + 15 * D_MODEL + cb * 32 + 2 * k);
+          const float2 y = __ffma2_rn(__ffma2_rn(f2(h[2 * k], h[2 * k + 1]), rs, nm), g, be);
+          h[2 * k] = y.x; h[2 * k + 1] = y.y;
+        }
         tmem_st32(X + cb * 32, h);
       }
       tmem_wait_st();
+      named_bar_sync(3, 256);  // everyone is done with the staged weights before the U region is reused
     }
 
+    TL(0, 1);
     for (int l = 0; l < P.depth; ++l) {
+      TL(0, 2 + l * 40);
       // K/V of this sample and block -> smem (every row of the tile belongs to the same sample)
       {
         const float4* src = reinterpret_cast<const float4*>(P.kv + ((size_t)b * P.depth + l) * 1024);
@@ -342,11 +393,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       tc_fence_before();
       mbar_arrive(&bars[BAR_A + T]);
       named_bar_sync(1 + T, 128);  // kvs visible to the tile's 128 threads
+      TL(0, 3 + l * 40);
 
       // ---- attention over the 4 part tokens, head by head, out of the Q accumulator ----
       mbar_wait(&bars[BAR_ACC + T * 2 + 0], ph_acc[0]);
       ph_acc[0] ^= 1;
       tc_fence_after();
+      TL(0, 4 + l * 40);
 #pragma unroll 1
       for (int h = 0; h < 8; ++h) {
         float qv[16];
@@ -394,16 +447,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       tc_fence_before();
       mbar_arrive(&bars[BAR_A + T]);
 
+      TL(0, 5 + l * 40);
       // ---- x += attn @ Wo^T + bo (accumulated in TMEM by the MMA warp);  LN3 -> A ----
       mbar_wait(&bars[BAR_X + T], ph_x);
       ph_x ^= 1;
       tc_fence_after();
+      TL(0, 6 + l * 40);
       row_stats(X, mean, rstd);
       row_normalize_to_tile(X, mean, rstd, a_tile, r);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[BAR_A + T]);
 
+      TL(0, 7 + l * 40);
       // ---- GEGLU feed-forward, 16 chunks of 32 value + 32 gate columns ----
 #pragma unroll 1
       for (int c = 0; c < FF_CHUNKS; ++c) {
@@ -412,6 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         mbar_wait(&bars[BAR_ACC + T * 2 + hb], ph_acc[hb]);
         ph_acc[hb] ^= 1;
         tc_fence_after();
+        TL(0, 8 + l * 40 + c * 2);
         float a[32], gt[32];
         tmem_ld32(ACC + hb * 64, a);
         tmem_ld32(ACC + hb * 64 + 32, gt);
@@ -431,12 +488,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bars[BAR_UREADY + T * 2 + hb]);
+        TL(0, 9 + l * 40 + c * 2);
       }
       mbar_wait(&bars[BAR_X + T], ph_x);
       ph_x ^= 1;
       tc_fence_after();
     }
 
+    TL(0, 2 + P.depth * 40);
     // ---- post_norm (folded) + proj_out (128 -> 3) ----
     {
       float mean, rstd;
@@ -447,11 +506,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         tmem_ld32(X + cb * 32, h);
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float y = (h[k] - mean) * rstd;
-          o0 = fmaf(y, __ldg(P.head + cb * 32 + k), o0);
-          o1 = fmaf(y, __ldg(P.head + D_MODEL + cb * 32 + k), o1);
-          o2 = fmaf(y, __ldg(P.head + 2 * D_MODEL + cb * 32 + k), o2);
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.head + cb * 32) + k4);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.head + D_MODEL + cb * 32) + k4);
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(P.head + 2 * D_MODEL + cb * 32) + k4);
+          const float y0 = (h[4 * k4] - mean) * rstd, y1 = (h[4 * k4 + 1] - mean) * rstd;
+          const float y2 = (h[4 * k4 + 2] - mean) * rstd, y3 = (h[4 * k4 + 3] - mean) * rstd;
+          o0 = fmaf(y3, w0.w, fmaf(y2, w0.z, fmaf(y1, w0.y, fmaf(y0, w0.x, o0))));
+          o1 = fmaf(y3, w1.w, fmaf(y2, w1.z, fmaf(y1, w1.y, fmaf(y0, w1.x, o1))));
+          o2 = fmaf(y3, w2.w, fmaf(y2, w2.z, fmaf(y1, w2.y, fmaf(y0, w2.x, o2))));
         }
       }
       if (tile_ok) {
@@ -460,6 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         P.eps_out[(b * 3 + 2) * P.N + p] = o2 + __ldg(P.head + 3 * D_MODEL + 2);
       }
     }
+    TL(0, 3 + P.depth * 40);
     tc_fence_before();
   } else if (warp == 8) {
     // =========================== MMA issuer ===========================
@@ -470,7 +534,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     const uint32_t sbase = smem_u32(smem);
     const uint32_t ring = sbase + SM_RING, a_base = sbase + SM_A, u_base = sbase + SM_U;
     const uint64_t ones_desc = make_smem_desc(sbase + SM_ONES, 2048, TILE_SBO);
-    uint32_t ph_a0 = 0, ph_a1 = 0, ph_u = 0;  // ph_u: bit (T*2+hb)
+    uint32_t ph_a0 = 0, ph_a1 = 0, ph_u = 0;  // ph_u: bit hb (both tiles advance together)
+    const bool tl_on = lane == 0;
     auto pkt_addr = [&](int G) -> uint32_t {  // wait until packet G has landed; its smem address
       mbar_wait(&bars[BAR_WFULL + G % NSLOT], (uint32_t)(G / NSLOT) & 1u);
       return ring + (uint32_t)(G % NSLOT) * SLOT_BYTES;
@@ -479,81 +544,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       if (T == 0) { mbar_wait(&bars[BAR_A + 0], ph_a0); ph_a0 ^= 1; }
       else { mbar_wait(&bars[BAR_A + 1], ph_a1); ph_a1 ^= 1; }
     };
+    // Both tiles advance in LOCKSTEP through the MMA schedule and their K-steps are interleaved (T0,k),(T1,k): one set of
+    // barrier/packet waits serves both tiles, and the epilogues of the two tiles (8 warps) run concurrently.  MMA/epilogue
+    // overlap comes from the double-buffered FF hidden chunks (ACC halves), not from skewing the tiles.
     for (int l = 0; l < P.depth; ++l) {
       const int G0 = l * PKT_PER_LAYER;
+      TL(1, 2 + l * 40);
       // ---- Q = LN2(x) Wq'^T + bq' ----
-#pragma unroll
-      for (int T = 0; T < 2; ++T) {
-        wait_a(T);
+      {
+        wait_a(0); wait_a(1);
         const uint32_t p0 = pkt_addr(G0 + 0), p1 = pkt_addr(G0 + 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = 256 + T * 128;
-          umma_gemm<128, 4>(d, a_base + T * 32768, p0, idesc128, 0u);
-          umma_gemm<128, 4>(d, a_base + T * 32768 + 4 * 4096, p1, idesc128, 1u);
-          umma_bf16(d, ones_desc, make_smem_desc(p0 + BIAS_OFF_W128, 0, TILE_SBO), idesc128, 1u);
-          umma_commit(&bars[BAR_ACC + T * 2 + 0]);
+          umma_gemm2<128, 4>(256, 384, a_base, a_base + 32768, p0, idesc128, 0u);
+          umma_gemm2<128, 4>(256, 384, a_base + 4 * 4096, a_base + 32768 + 4 * 4096, p1, idesc128, 1u);
+          const uint64_t bdsc = make_smem_desc(p0 + BIAS_OFF_W128, 0, TILE_SBO);
+          umma_bf16(256, ones_desc, bdsc, idesc128, 1u);
+          umma_bf16(384, ones_desc, bdsc, idesc128, 1u);
+          umma_commit(&bars[BAR_ACC + 0]);
+          umma_commit(&bars[BAR_ACC + 2]);
+          umma_commit(&bars[BAR_WEMPTY + (G0 + 0) % NSLOT]);
+          umma_commit(&bars[BAR_WEMPTY + (G0 + 1) % NSLOT]);
         }
         __syncwarp();
       }
-      if (elect_one()) { umma_commit(&bars[BAR_WEMPTY + (G0 + 0) % NSLOT]); umma_commit(&bars[BAR_WEMPTY + (G0 + 1) % NSLOT]); }
-      __syncwarp();
+      TL(1, 3 + l * 40);
       // ---- x += O Wo^T + bo ----
-#pragma unroll
-      for (int T = 0; T < 2; ++T) {
-        wait_a(T);
+      {
+        wait_a(0);
+        TL(1, 4 + l * 40);
+        wait_a(1);
         const uint32_t p2 = pkt_addr(G0 + 2), p3 = pkt_addr(G0 + 3);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = T * 128;
-          umma_gemm<128, 4>(d, a_base + T * 32768, p2, idesc128, 1u);
-          umma_gemm<128, 4>(d, a_base + T * 32768 + 4 * 4096, p3, idesc128, 1u);
-          umma_bf16(d, ones_desc, make_smem_desc(p2 + BIAS_OFF_W128, 0, TILE_SBO), idesc128, 1u);
-          umma_commit(&bars[BAR_X + T]);
+          umma_gemm2<128, 4>(0, 128, a_base, a_base + 32768, p2, idesc128, 1u);
+          umma_gemm2<128, 4>(0, 128, a_base + 4 * 4096, a_base + 32768 + 4 * 4096, p3, idesc128, 1u);
+          const uint64_t bdsc = make_smem_desc(p2 + BIAS_OFF_W128, 0, TILE_SBO);
+          umma_bf16(0, ones_desc, bdsc, idesc128, 1u);
+          umma_bf16(128, ones_desc, bdsc, idesc128, 1u);
+          umma_commit(&bars[BAR_X + 0]);
+          umma_commit(&bars[BAR_X + 1]);
+          umma_commit(&bars[BAR_WEMPTY + (G0 + 2) % NSLOT]);
+          umma_commit(&bars[BAR_WEMPTY + (G0 + 3) % NSLOT]);
         }
         __syncwarp();
       }
-      if (elect_one()) { umma_commit(&bars[BAR_WEMPTY + (G0 + 2) % NSLOT]); umma_commit(&bars[BAR_WEMPTY + (G0 + 3) % NSLOT]); }
-      __syncwarp();
       // ---- feed-forward ----
-      auto ff_in = [&](int T, int c) {  // H_c = LN3(x) W1'_c^T + b1'_c -> ACC_T half (c & 1)
-        const uint32_t pw = pkt_addr(G0 + pkt_w1(c));
+      // H_c = LN3(x) W1'_c^T + b1'_c for both tiles -> ACC_T half (c & 1); issued inside an elected region
+      auto ff_in2 = [&](uint32_t pw, int c) {
+        const uint32_t d0 = 256 + (c & 1) * 64, d1 = 384 + (c & 1) * 64;
+        umma_gemm2<64, 8>(d0, d1, a_base, a_base + 32768, pw, idesc64, 0u);
+        const uint64_t bdsc = make_smem_desc(pw + BIAS_OFF_W128, 0, TILE_SBO);
+        umma_bf16(d0, ones_desc, bdsc, idesc64, 1u);
+        umma_bf16(d1, ones_desc, bdsc, idesc64, 1u);
+        umma_commit(&bars[BAR_ACC + (c & 1)]);
+        umma_commit(&bars[BAR_ACC + 2 + (c & 1)]);
+      };
+      TL(1, 5 + l * 40);
+      wait_a(0); wait_a(1);
+      TL(1, 6 + l * 40);
+      {
+        const uint32_t pa = pkt_addr(G0 + 4), pb = pkt_addr(G0 + 5);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = 256 + T * 128 + (c & 1) * 64;
-          umma_gemm<64, 8>(d, a_base + T * 32768, pw, idesc64, 0u);
-          umma_bf16(d, ones_desc, make_smem_desc(pw + BIAS_OFF_W128, 0, TILE_SBO), idesc64, 1u);
-          umma_commit(&bars[BAR_ACC + T * 2 + (c & 1)]);
+          ff_in2(pa, 0);
+          ff_in2(pb, 1);
+          umma_commit(&bars[BAR_WEMPTY + (G0 + 4) % NSLOT]);
+          umma_commit(&bars[BAR_WEMPTY + (G0 + 5) % NSLOT]);
         }
         __syncwarp();
-      };
-      wait_a(0); wait_a(1);
-      ff_in(0, 0); ff_in(1, 0); ff_in(0, 1); ff_in(1, 1);
-      if (elect_one()) { umma_commit(&bars[BAR_WEMPTY + (G0 + 4) % NSLOT]); umma_commit(&bars[BAR_WEMPTY + (G0 + 5) % NSLOT]); }
-      __syncwarp();
+      }
+      TL(1, 7 + l * 40);
 #pragma unroll 1
       for (int c = 0; c < FF_CHUNKS; ++c) {
         const int hb = c & 1;
-#pragma unroll
-        for (int T = 0; T < 2; ++T) {
-          const int ub = T * 2 + hb;
-          mbar_wait(&bars[BAR_UREADY + ub], (ph_u >> ub) & 1u);
-          ph_u ^= 1u << ub;
-          const uint32_t pw = pkt_addr(G0 + pkt_w2(c));
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t d = T * 128;
-            umma_gemm<128, 2>(d, u_base + ub * 8192, pw, idesc128, 1u);
-            if (c == FF_CHUNKS - 1) umma_bf16(d, ones_desc, make_smem_desc(pw + BIAS_OFF_W2, 0, TILE_SBO), idesc128, 1u);
-            umma_commit(&bars[BAR_UFREE + ub]);
-            if (c == FF_CHUNKS - 1) umma_commit(&bars[BAR_X + T]);
-          }
-          __syncwarp();
-          if (c + 2 < FF_CHUNKS) ff_in(T, c + 2);
-        }
+        TL(1, 8 + l * 40 + c * 2);
+        mbar_wait(&bars[BAR_UREADY + hb], (ph_u >> hb) & 1u);
+        mbar_wait(&bars[BAR_UREADY + 2 + hb], (ph_u >> hb) & 1u);
+        ph_u ^= 1u << hb;
+        TL(1, 9 + l * 40 + c * 2);
+        const uint32_t pw2 = pkt_addr(G0 + pkt_w2(c));
+        uint32_t pw1 = 0;
+        if (c + 2 < FF_CHUNKS) pw1 = pkt_addr(G0 + pkt_w1(c + 2));
+        tc_fence_after();
         if (elect_one()) {
+          umma_gemm2<128, 2>(0, 128, u_base + hb * 8192, u_base + (2 + hb) * 8192, pw2, idesc128, 1u);
+          if (c == FF_CHUNKS - 1) {
+            const uint64_t bdsc = make_smem_desc(pw2 + BIAS_OFF_W2, 0, TILE_SBO);
+            umma_bf16(0, ones_desc, bdsc, idesc128, 1u);
+            umma_bf16(128, ones_desc, bdsc, idesc128, 1u);
+          }
+          umma_commit(&bars[BAR_UFREE + hb]);
+          umma_commit(&bars[BAR_UFREE + 2 + hb]);
+          if (c == FF_CHUNKS - 1) { umma_commit(&bars[BAR_X + 0]); umma_commit(&bars[BAR_X + 1]); }
           umma_commit(&bars[BAR_WEMPTY + (G0 + pkt_w2(c)) % NSLOT]);
-          if (c + 2 < FF_CHUNKS) umma_commit(&bars[BAR_WEMPTY + (G0 + pkt_w1(c + 2)) % NSLOT]);
+          if (c + 2 < FF_CHUNKS) {
+            ff_in2(pw1, c + 2);
+            umma_commit(&bars[BAR_WEMPTY + (G0 + pkt_w1(c + 2)) % NSLOT]);
+          }
         }
         __syncwarp();
       }
@@ -580,6 +668,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
   }
 }
 
+static long long* g_tc_timeline = nullptr;  // set by dfb200_debug_tc_timeline
+
 int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
                         const float* variances, const int* assign, const float* valid_id, float* eps_out, Workspace& ws,
                         cudaStream_t st) {
@@ -600,6 +690,7 @@ int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, c
   p.eps_out = eps_out;
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
   p.M = (long long)B * N;
+  p.dbg = g_tc_timeline;
   const int grid = cdiv(p.M, 256);
   denoiser_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
   DFB_LAUNCH_CHECK();
@@ -706,9 +797,81 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// UMMA issue-rate microbenchmark: `iters` back-to-back K=16 MMAs (M=128, N) from smem operands, cycles from the
+// first issue to the commit's arrival.  layout 0 = no-swizzle canonical tiles (as used by the fused kernel),
+// 1 = SWIZZLE_128B descriptors.  Operand contents are irrelevant (timing only).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int layout, int N, int iters, int ksteps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 131072 + 64);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  for (int i = tid; i < 131072 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) { mbar_init(&bars[0], 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    const bool same_acc = (layout & 2) != 0;  // every MMA accumulates into the same TMEM tile (dependent chain)
+    layout &= 1;
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      // descriptors precomputed; the issue loop is 8 unrolled MMAs per iteration (like the fused kernel's sequences)
+      uint64_t ad[8], bd[8];
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int kk = ks % ksteps;
+        if (layout == 0) {
+          ad[ks] = make_smem_desc(sbase + kk * 4096, 2048, TILE_SBO);
+          bd[ks] = make_smem_desc(sbase + 65536 + kk * (N * 32), N * 16, TILE_SBO);
+        } else {  // SWIZZLE_128B K-major: rows of 128 B, 8-row atoms of 1024 B; a K=16 step advances the start by 32 B
+          ad[ks] = make_smem_desc(sbase + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024) | ((uint64_t)2 << 61);
+          bd[ks] = make_smem_desc(sbase + 65536 + (kk >> 2) * (N * 128) + (kk & 3) * 32, 16, 1024) | ((uint64_t)2 << 61);
+        }
+      }
+      t0 = clock64();
+      for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_bf16(tmem + (same_acc ? 0 : (ks & 1) * 256), ad[ks], bd[ks], idesc, 1u);
+      }
+      umma_commit(&bars[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], 0);
+    t1 = clock64();
+    if (elect_one()) { out[0] = t1 - t0; }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 }  // namespace dfb200
 
 using namespace dfb200;
+
+extern "C" int dfb200_bench_umma(int layout, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream) {
+  DFB_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && ksteps >= 1 && ksteps <= 8, DFB200_ERR_INVALID_ARG, "bench_umma: bad shape");
+  const int smem = 131072 + 128;
+  DFB_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<1, 128, smem, as_stream(stream)>>>(layout, N, iters, ksteps, out_cycles);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+// Debug hook: device buffer of 1024 int64 that CTA 0 of the fused kernel fills with clock64() stamps (NULL = off).
+extern "C" int dfb200_debug_tc_timeline(long long* device_buffer) {
+  g_tc_timeline = device_buffer;
+  return DFB200_OK;
+}
 
 extern "C" int dfb200_selftest_umma(int variant, int N, int K, const float* A, const float* W, const float* bias,
                                     const float* Cin, float* D, void* scratch, dfb200_stream_t stream) {

@@ -215,6 +215,14 @@ int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uint64_t offse
 int dfb200_selftest_umma(int variant, int N, int K, const float* A, const float* W, const float* bias,
                          const float* Cin, float* D, void* scratch, dfb200_stream_t stream);
 
+/* Microbenchmark: SM cycles for `iters` back-to-back tcgen05.mma (M=128, N, K=16, bf16) from shared-memory operands
+ * cycling over `ksteps` K-slabs; layout 0 = canonical no-swizzle tiles, 1 = SWIZZLE_128B.  out_cycles: device int64. */
+int dfb200_bench_umma(int layout, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream);
+
+/* Profiling hook: a device buffer of 1024 int64 that CTA 0 of the fused bf16 denoiser kernel fills with
+ * clock64() stamps at its phase boundaries ([0..511] tile-0 epilogue, [512..1023] MMA issuer); NULL disables. */
+int dfb200_debug_tc_timeline(long long* device_buffer);
+
 /* Scratch bytes for dfb200_ddpm_sample_loop. */
 size_t dfb200_ddpm_sample_loop_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B,
                                                int N, int T);

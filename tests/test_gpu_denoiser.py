@@ -198,7 +198,7 @@ def test_philox_loop_equals_explicit_noise_loop():
 
 def test_seeded_torch_rng_reproducibility():
     d = build(4, "fp32")
-    i = dev(R.synthetic_inputs(3, 2, 64, True))
+    i = dev(R.synthetic_inputs(3, 2, 128, True))
     kw = dict(ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"], valid_id=i["valid"])
     torch.manual_seed(7)
     a = d.p_sample_loop([2, 3, 128], i["anchors"], **kw)

@@ -1,0 +1,33 @@
+"""Diagnostic (GPU box): phase timeline (SM cycles) of CTA 0 of the fused bf16 denoiser kernel."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from difffacto_b200 import _lib
+from oracle import denoiser_ref as R
+d = bench.build_model(1000, "bf16").cuda().eval()
+inp = R.synthetic_inputs(5, 32, 2048, False)
+i = {k: v.cuda() for k, v in inp.items()}
+f = lambda: d.model(i["x"], i["t"], [i["code"], i["params"]], anchors=i["anchors"].transpose(1, 2),
+                    anchor_assignment=i["assign"], variances=i["variance"].transpose(1, 2), valid_id=i["valid"])
+with torch.no_grad():
+    f(); f()
+    buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    _lib.load().dfb200_debug_tc_timeline(_lib.ptr(buf))
+    f(); torch.cuda.synchronize()
+    _lib.load().dfb200_debug_tc_timeline(None)
+b = buf.cpu().tolist()
+E, M = b[:512], b[512:]
+t0 = E[0]
+rel = lambda v: v - t0 if v else None
+print("epilogue(tile0,row0): start 0, init done", rel(E[1]), " end", rel(E[3 + 5 * 40]), " (final head start", rel(E[2 + 5 * 40]), ")")
+for l in range(5):
+    o = l * 40
+    print(f"layer {l}: start {rel(E[2+o])}  LN2+kv done {rel(E[3+o])}  Q ready {rel(E[4+o])}  attn done {rel(E[5+o])}  "
+          f"x ready {rel(E[6+o])}  LN3 done {rel(E[7+o])}")
+    ff = [(rel(E[8 + o + 2 * c]), rel(E[9 + o + 2 * c])) for c in range(16)]
+    print("   FF chunks (acc ready -> u ready):", " ".join(f"{a}->{b_}" for a, b_ in ff))
+    print(f"   MMA: layer start {rel(M[2+o])} Q issued {rel(M[3+o])} O tile ready {rel(M[4+o])} out issued {rel(M[5+o])} "
+          f"LN3 tiles ready {rel(M[6+o])} first FF-in issued {rel(M[7+o])}")
+    mm = [(rel(M[8 + o + 2 * c]), rel(M[9 + o + 2 * c])) for c in range(16)]
+    print("   MMA FF units T0 (begin wait u_ready -> got it):", " ".join(f"{a}->{b_}" for a, b_ in mm))
