@@ -52,6 +52,7 @@ struct Workspace {
   float* x;       // [M, 128]   residual stream (fp32 path)
   float* q;       // [M, 128]   q, then attention output in place (fp32 path)
   float* u;       // [M, 512]   GEGLU output (fp32 path)
+  void* fold;     // [B, depth] folded attention packets (bf16 path)
   size_t bytes;
 };
 Workspace carve_workspace(const NetDims& d, int mode, int B, int N, void* base);

@@ -59,6 +59,7 @@ size_t param_numel(const NetDims& d, bool global, int which) {
 }
 
 size_t tc_stream_bytes_for(const NetDims& d);  // denoiser_tc.cu
+size_t tc_fold_bytes_for(const NetDims& d, int B);
 
 int make_pack_layout(const dfb200_denoiser_cfg* cfg, PackLayout* L) {
   int rc = make_net_dims(cfg, &L->d);
@@ -92,6 +93,8 @@ Workspace carve_workspace(const NetDims& d, int mode, int B, int N, void* base) 
     w.x = take(M * D_MODEL);
     w.q = take(M * D_MODEL);
     w.u = take(M * D_FF);
+  } else {
+    w.fold = take((tc_fold_bytes_for(d, B) + 3) / 4);
   }
   w.bytes = off;
   return w;
