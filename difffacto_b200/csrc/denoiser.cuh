@@ -62,6 +62,28 @@ Workspace carve_workspace(const NetDims& d, int mode, int B, int N, void* base);
 int launch_context_kv(const PackLayout& L, const float* packed, int B, const float* t, const float* ctx,
                       Workspace& ws, cudaStream_t st);
 
+// Time-independent / sample-independent halves of the K/V projection (used by the fused sampling loop):
+//   kv_static[b,l,{k,v},j,:] = W[:, :c_static] . [ctx[b,:,j] | onehot(j)]      kv_time[t,l,{k,v},:] = W[:, c_static:] . temb(t)
+int launch_context_kv_static(const PackLayout& L, const float* packed, int B, const float* ctx, float* kv_static, cudaStream_t st);
+int launch_context_kv_time(const PackLayout& L, const float* packed, int T, const float* t_values, float* temb_h, float* temb,
+                           float* kv_time, cudaStream_t st);
+
+// fused-update arguments of the bf16 kernel (all-zero = plain forward writing eps)
+struct TcUpdate {
+  const float* sched;  // device schedule table [DFB200_SCHED_ROWS][T]
+  int T, t;            // timestep of this launch (same for every sample of the batch)
+  const float* noise;  // (B,3,N) N(0,1) for this step, or NULL -> Philox(seed, offset = t)
+  uint64_t seed;
+  float* x_out;        // x_{t-1}; may alias x
+};
+int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
+                     const float* variances, const int* assign, const float* valid_id, const void* fold, float* eps_out,
+                     const TcUpdate* upd, cudaStream_t st);
+// fold tiles for `steps` consecutive timesteps t_first, t_first-1, ...: fold[(s*B + b)*depth + l]
+int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time,
+                        int t_first, int steps, void* fold, cudaStream_t st);
+size_t tc_fold_bytes_for(const NetDims& d, int B);
+
 int denoiser_forward_fp32(const PackLayout& L, const float* packed, int B, int N, const float* x,
                           const float* anchors, const float* variances, const int* assign,
                           const float* valid_id, float* eps_out, Workspace& ws, cudaStream_t st);

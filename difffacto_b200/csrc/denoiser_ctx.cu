@@ -59,7 +59,6 @@ size_t param_numel(const NetDims& d, bool global, int which) {
 }
 
 size_t tc_stream_bytes_for(const NetDims& d);  // denoiser_tc.cu
-size_t tc_fold_bytes_for(const NetDims& d, int B);
 
 int make_pack_layout(const dfb200_denoiser_cfg* cfg, PackLayout* L) {
   int rc = make_net_dims(cfg, &L->d);
@@ -225,6 +224,93 @@ int launch_context_kv(const PackLayout& L, const float* P, int B, const float* t
   DFB_REQUIRE(smem <= 48 * 1024, DFB200_ERR_UNSUPPORTED, "denoiser: context width %d too large", L.d.c_ctx);
   context_kv_kernel<<<dim3(B, L.d.depth * 2), 256, smem, st>>>(a, L.d.c_ctx, L.d.c_ctx_static - L.d.n_tok, L.d.n_tok,
                                                                  ctx, ws.temb, ws.kv);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+// grid (B, depth*2): static half of K/V: 128 outputs x 4 tokens over the first c_static context columns
+__global__ void __launch_bounds__(256)
+context_kv_static_kernel(KvArgs args, int c_ctx, int c_raw, int n_tok, const float* __restrict__ ctx, float* __restrict__ kv) {
+  extern __shared__ float cs[];  // [n_tok][c_static]
+  const int b = blockIdx.x;
+  const int l = blockIdx.y >> 1, which = blockIdx.y & 1;
+  const int c_static = c_raw + n_tok;
+  for (int i = threadIdx.x; i < n_tok * c_static; i += blockDim.x) {
+    const int j = i / c_static, k = i - j * c_static;
+    cs[i] = k < c_raw ? __ldg(ctx + ((size_t)b * c_raw + k) * n_tok + j) : ((k - c_raw) == j ? 1.f : 0.f);
+  }
+  __syncthreads();
+  const float* W = args.w[l][which];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* out = kv + (((size_t)b * gridDim.y + blockIdx.y) * n_tok) * D_MODEL;
+  for (int o = warp; o < D_MODEL; o += 8) {
+    const float* w = W + (size_t)o * c_ctx;
+    float s[MAX_TOKENS] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < c_static; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int j = 0; j < MAX_TOKENS; ++j) s[j] += wv * cs[j * c_static + k];
+    }
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) {
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) s[j] += __shfl_xor_sync(0xFFFFFFFFu, s[j], d);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < MAX_TOKENS; ++j) out[(size_t)j * D_MODEL + o] = s[j];
+    }
+  }
+}
+
+// grid (T, depth*2): time half of K/V: kv_time[t, l, which, :] = W[:, c_static:] . temb[t]
+__global__ void __launch_bounds__(256)
+context_kv_time_kernel(KvArgs args, int c_ctx, int c_static, const float* __restrict__ temb, float* __restrict__ kv_time) {
+  __shared__ float te[D_TEMB];
+  const int t = blockIdx.x;
+  const int l = blockIdx.y >> 1, which = blockIdx.y & 1;
+  for (int i = threadIdx.x; i < D_TEMB; i += blockDim.x) te[i] = temb[(size_t)t * D_TEMB + i];
+  __syncthreads();
+  const float* W = args.w[l][which];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* out = kv_time + ((size_t)t * gridDim.y + blockIdx.y) * D_MODEL;
+  for (int o = warp; o < D_MODEL; o += 8) {
+    const float* w = W + (size_t)o * c_ctx + c_static;
+    float s = 0.f;
+    for (int k = lane; k < D_TEMB; k += 32) s += __ldg(w + k) * te[k];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    if (lane == 0) out[o] = s;
+  }
+}
+
+static KvArgs make_kv_args(const PackLayout& L, const float* P) {
+  KvArgs a{};
+  for (int l = 0; l < L.d.depth; ++l) {
+    a.w[l][0] = P + L.blk[l][B_WK];
+    a.w[l][1] = P + L.blk[l][B_WV];
+  }
+  return a;
+}
+
+int launch_context_kv_static(const PackLayout& L, const float* P, int B, const float* ctx, float* kv_static, cudaStream_t st) {
+  if (B == 0) return DFB200_OK;
+  const size_t smem = sizeof(float) * L.d.n_tok * L.d.c_ctx_static;
+  DFB_REQUIRE(smem <= 48 * 1024, DFB200_ERR_UNSUPPORTED, "denoiser: context width %d too large", L.d.c_ctx_static);
+  context_kv_static_kernel<<<dim3(B, L.d.depth * 2), 256, smem, st>>>(make_kv_args(L, P), L.d.c_ctx, L.d.c_ctx_static - L.d.n_tok,
+                                                                        L.d.n_tok, ctx, kv_static);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+int launch_context_kv_time(const PackLayout& L, const float* P, int T, const float* t_values, float* temb_h, float* temb,
+                           float* kv_time, cudaStream_t st) {
+  if (T == 0) return DFB200_OK;
+  temb_hidden_kernel<<<dim3(T, D_TEMB_H / 64), 256, 0, st>>>(t_values, P + L.freqs, P + L.g[P_TE0_W], P + L.g[P_TE0_B], temb_h);
+  DFB_LAUNCH_CHECK();
+  temb_out_kernel<<<dim3(T, D_TEMB / 32), 256, 0, st>>>(temb_h, P + L.g[P_TE2_W], P + L.g[P_TE2_B], temb);
+  DFB_LAUNCH_CHECK();
+  context_kv_time_kernel<<<dim3(T, L.d.depth * 2), 256, 0, st>>>(make_kv_args(L, P), L.d.c_ctx, L.d.c_ctx_static, temb, kv_time);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

@@ -22,7 +22,9 @@
 // TMEM map (512 columns): X0 [0,128) X1 [128,256) ACC0 [256,384) ACC1 [384,512).
 #include <float.h>
 
+#include "ddpm.cuh"
 #include "denoiser.cuh"
+#include "philox.cuh"
 #include "tc_common.cuh"
 
 namespace dfb200 {
@@ -171,12 +173,25 @@ int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
 //   W_pv[c][(h,j)]  = sum_d Wo[c][16h+d] V[j][16h+d]
 // written as bf16 UMMA tiles (the "fold" packet of (b, l)).  grid (B, depth), 256 threads.
 // ---------------------------------------------------------------------------------------------
+// kv: [B][depth][2][4][128] (full K/V, or their static half when kv_time != NULL);  kv_time: [T][depth][2][128] time half of
+// timestep (t_first - blockIdx.z), broadcast over the 4 tokens.  grid (B, depth, steps).
 __global__ void __launch_bounds__(256)
-context_fold_kernel(int depth, const float* __restrict__ kv, const float* __restrict__ extras, uint8_t* __restrict__ fold) {
+context_fold_kernel(int depth, const float* __restrict__ kv, const float* __restrict__ kv_time, int t_first,
+                    const float* __restrict__ extras, uint8_t* __restrict__ fold_all) {
   __shared__ float K[MAX_TOKENS][D_MODEL], V[MAX_TOKENS][D_MODEL];
   const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
   const float* src = kv + ((size_t)b * depth + l) * 1024;
-  for (int i = t; i < 512; i += 256) { (&K[0][0])[i] = __ldg(src + i); (&V[0][0])[i] = __ldg(src + 512 + i); }
+  uint8_t* fold = fold_all + (size_t)blockIdx.z * gridDim.x * depth * FOLD_BYTES;
+  for (int i = t; i < 512; i += 256) {
+    float kt = 0.f, vt = 0.f;
+    if (kv_time != nullptr) {
+      const float* tt = kv_time + ((size_t)(t_first - (int)blockIdx.z) * depth + l) * 2 * D_MODEL;
+      kt = __ldg(tt + (i & 127));
+      vt = __ldg(tt + D_MODEL + (i & 127));
+    }
+    (&K[0][0])[i] = __ldg(src + i) + kt;
+    (&V[0][0])[i] = __ldg(src + 512 + i) + vt;
+  }
   __syncthreads();
   const float* WqG = extras + HEAD_FLOATS + (size_t)l * FOLDW_FLOATS;
   const float* bqG = WqG + D_MODEL * D_MODEL;
@@ -249,6 +264,8 @@ struct TcParams {
   int N, depth, flags;
   long long M;
   long long* dbg;  // optional timeline buffer: CTA 0 records clock64() at phase boundaries
+  // fused eps -> x_{t-1} update (sampling loop): active when upd_sched != NULL
+  const float* upd_sched; int upd_T, upd_t; const float* upd_noise; uint64_t upd_seed; float* x_out;
 };
 
 // Packed fp32x2 math (FFMA2 on sm_100): the CUDA-core epilogues are the bottleneck of this kernel (the
@@ -566,10 +583,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           o2 = fmaf(y3, w2.w, fmaf(y2, w2.z, fmaf(y1, w2.y, fmaf(y0, w2.x, o2))));
         }
       }
-      if (tile_ok) {
-        P.eps_out[(b * 3 + 0) * P.N + p] = o0 + __ldg(P.head + 3 * D_MODEL + 0);
-        P.eps_out[(b * 3 + 1) * P.N + p] = o1 + __ldg(P.head + 3 * D_MODEL + 1);
-        P.eps_out[(b * 3 + 2) * P.N + p] = o2 + __ldg(P.head + 3 * D_MODEL + 2);
+      const float eps3[3] = {o0 + __ldg(P.head + 3 * D_MODEL + 0), o1 + __ldg(P.head + 3 * D_MODEL + 1),
+                             o2 + __ldg(P.head + 3 * D_MODEL + 2)};
+      if (tile_ok && P.eps_out != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) P.eps_out[(b * 3 + c) * P.N + p] = eps3[c];
+      }
+      if (P.upd_sched != nullptr) {
+        // anchored DDPM update fused into the epilogue (same arithmetic as dfb200_ddpm_step; every sample shares t)
+        const StepCoef cf = load_step_coef(P.upd_sched, P.upd_T, P.upd_t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const long long e = (b * 3 + c) * P.N + p;
+          const float xv = __ldg(P.x + e), av = __ldg(P.anchors + e), vv = __ldg(P.variances + e);
+          float z;
+          if (P.upd_noise != nullptr) {
+            z = __ldg(P.upd_noise + e);
+          } else {
+            const float4 z4 = philox_normal4((uint64_t)(e >> 2), (uint64_t)P.upd_t, P.upd_seed);
+            const int ln = (int)(e & 3);
+            z = ln == 0 ? z4.x : ln == 1 ? z4.y : ln == 2 ? z4.z : z4.w;
+          }
+          const float x0 = ddpm_xstart(cf, xv, av, vv, eps3[c]);
+          const float xp = ddpm_prev(cf, xv, av, vv, x0, z);
+          if (tile_ok) P.x_out[e] = xp;
+        }
       }
     }
     TL(0, 3 + P.depth * 40);
@@ -718,9 +756,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
 
 static long long* g_tc_timeline = nullptr;  // set by dfb200_debug_tc_timeline
 
-int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
-                        const float* variances, const int* assign, const float* valid_id, float* eps_out, Workspace& ws,
-                        cudaStream_t st) {
+static const float* tc_extras(const PackLayout& L, const void* packed) {
+  const uint8_t* S = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
+  return reinterpret_cast<const float*>(S + (size_t)L.d.depth * STATIC_PER_LAYER * SLOT_BYTES);
+}
+
+int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time, int t_first,
+                        int steps, void* fold, cudaStream_t st) {
+  if (B == 0 || steps == 0) return DFB200_OK;
+  context_fold_kernel<<<dim3(B, L.d.depth, steps), 256, 0, st>>>(L.d.depth, kv_static, kv_time, t_first, tc_extras(L, packed),
+                                                                  reinterpret_cast<uint8_t*>(fold));
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
+                     const float* variances, const int* assign, const float* valid_id, const void* fold, float* eps_out,
+                     const TcUpdate* upd, cudaStream_t st) {
   DFB_REQUIRE(N % 128 == 0, DFB200_ERR_UNSUPPORTED, "denoiser (bf16 mode): N must be a multiple of 128 (got %d); use fp32 mode", N);
   static bool attr_set = false;
   if (!attr_set) {
@@ -728,25 +780,31 @@ int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, c
     attr_set = true;
   }
   const float* Pf = reinterpret_cast<const float*>(packed);
-  const uint8_t* S = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
-  const float* extras = reinterpret_cast<const float*>(S + (size_t)L.d.depth * STATIC_PER_LAYER * SLOT_BYTES);
-  // K/V (ws.kv, from launch_context_kv) -> per-(sample, block) folded attention tiles
-  context_fold_kernel<<<dim3(B, L.d.depth), 256, 0, st>>>(L.d.depth, ws.kv, extras, reinterpret_cast<uint8_t*>(ws.fold));
-  DFB_LAUNCH_CHECK();
   TcParams p{};
-  p.stream = S;
-  p.fold = reinterpret_cast<const uint8_t*>(ws.fold);
-  p.head = extras;
+  p.stream = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
+  p.fold = reinterpret_cast<const uint8_t*>(fold);
+  p.head = tc_extras(L, packed);
   p.w_in = Pf + L.g[P_IN_W]; p.b_in = Pf + L.g[P_IN_B]; p.pre_w = Pf + L.g[P_PRE_W]; p.pre_b = Pf + L.g[P_PRE_B];
   p.x = x; p.anchors = anchors; p.variances = variances; p.assign = assign; p.valid = valid_id;
   p.eps_out = eps_out;
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
   p.M = (long long)B * N;
   p.dbg = g_tc_timeline;
-  const int grid = cdiv(p.M, 256);
-  denoiser_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+  if (upd != nullptr) {
+    p.upd_sched = upd->sched; p.upd_T = upd->T; p.upd_t = upd->t; p.upd_noise = upd->noise; p.upd_seed = upd->seed; p.x_out = upd->x_out;
+  }
+  denoiser_tc_kernel<<<cdiv(p.M, 256), TC_THREADS, TC_SMEM_BYTES, st>>>(p);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
+}
+
+int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
+                        const float* variances, const int* assign, const float* valid_id, float* eps_out, Workspace& ws,
+                        cudaStream_t st) {
+  // K/V (ws.kv, from launch_context_kv) -> per-(sample, block) folded attention tiles -> fused kernel
+  int rc = launch_context_fold(L, packed, B, ws.kv, nullptr, 0, 1, ws.fold, st);
+  if (rc != DFB200_OK) return rc;
+  return denoiser_step_tc(L, packed, B, N, x, anchors, variances, assign, valid_id, ws.fold, eps_out, nullptr, st);
 }
 
 }  // namespace dfb200

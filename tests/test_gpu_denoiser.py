@@ -207,3 +207,41 @@ def test_seeded_torch_rng_reproducibility():
     for t, o in d.p_sample_loop_progressive([2, 3, 128], i["anchors"], **kw):
         final = o["sample"]
     assert (a - final).abs().max().item() < 1e-5  # same torch generator consumption order in both paths
+
+
+def test_bf16_fused_loop_philox_equals_supplied_noise():
+    """bf16 sampling loop (hoisted time/sample tables, chunked fold tiles, eps -> x_{t-1} fused into the denoiser kernel):
+    in-kernel Philox must reproduce, bit for bit, the run fed with the same draws through the noise argument, and both
+    must track the fp32 step-wise path."""
+    from difffacto_b200 import _lib
+    lib = _lib.load()
+    T, B, N = 7, 3, 256
+    d = build(T, "bf16")
+    i = dev(R.synthetic_inputs(44, B, N, False))
+    ctx = torch.cat([i["code"], i["params"]], 1).contiguous()
+    seed = 99
+    cfg, mode = d.model.c_cfg(), d.model.mode()
+    nws = lib.dfb200_ddpm_sample_loop_workspace_bytes(cfg, mode, B, N, T)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    packed, sched = d.model.packed_weights(), d._sched(torch.device("cuda"))
+
+    def run(x, from_noise, noise):
+        _lib.check(lib.dfb200_ddpm_sample_loop(cfg, _lib.ptr(packed), mode, B, N, T, _lib.ptr(sched), _lib.ptr(x), from_noise,
+                                               _lib.ptr(ctx), _lib.ptr(i["anchors"]), _lib.ptr(i["variance"]), _lib.ptr(i["assign"]),
+                                               _lib.ptr(i["valid"]), _lib.ptr(noise), seed, None, 1, _lib.ptr(ws), nws, _lib.stream()))
+        return x
+
+    a = run(torch.empty(B, 3, N, device="cuda"), 2, None)
+    draws = torch.empty(T + 1, B, 3, N, device="cuda")
+    for k in range(T + 1):
+        _lib.check(lib.dfb200_philox_normal(_lib.ptr(draws[k]), B * 3 * N, seed, k, _lib.stream()))
+    step_noise = torch.stack([draws[t] for t in range(T - 1, -1, -1)]).contiguous()  # loop order: t = T-1 first
+    b = run(draws[T].clone(), 1, step_noise)
+    assert torch.equal(a, b)
+    d32 = build(T, "fp32")
+    x = torch.sqrt(i["variance"]) * draws[T] + i["anchors"]
+    for step in range(T - 1, -1, -1):
+        tt = torch.full((B,), step, dtype=torch.long, device="cuda")
+        x = d32.p_sample(x, tt, i["anchors"], ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"],
+                         valid_id=i["valid"], noise=draws[step])["sample"]
+    assert (a - x).abs().max().item() < 5e-2
