@@ -71,10 +71,14 @@ int launch_context_kv_time(const PackLayout& L, const float* packed, int T, cons
 // fused-update arguments of the bf16 kernel (all-zero = plain forward writing eps)
 struct TcUpdate {
   const float* sched;  // device schedule table [DFB200_SCHED_ROWS][T]
-  int T, t;            // timestep of this launch (same for every sample of the batch)
-  const float* noise;  // (B,3,N) N(0,1) for this step, or NULL -> Philox(seed, offset = t)
+  int T, t;            // first timestep of this launch (same for every sample of the batch)
+  int n_steps;         // timesteps t, t-1, ..., t-n_steps+1 run inside ONE persistent launch
+  size_t fold_step_bytes;  // distance between consecutive steps' fold packets
+  const float* noise;  // (n_steps,B,3,N) N(0,1), first slice = step t, or NULL -> Philox(seed, offset = timestep)
   uint64_t seed;
-  float* x_out;        // x_{t-1}; may alias x
+  float* x_out;        // x_{t-1}; must alias x when n_steps > 1
+  int* done;           // per 256-token unit: tile-steps completed since the loop began (zeroed by the caller); required if n_steps > 1
+  float* traj; int traj_interval;  // optional trajectory slots (see dfb200_ddpm_sample_loop)
 };
 int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
                      const float* variances, const int* assign, const float* valid_id, const void* fold, float* eps_out,

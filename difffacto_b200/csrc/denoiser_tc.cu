@@ -249,7 +249,8 @@ constexpr uint32_t SM_ONES = 98304;        // 4096  ones tile (128 x 16 bf16: k=
 constexpr uint32_t SM_RING = 102400;       // 6 x 18432
 constexpr uint32_t SM_BAR = 212992;        // mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t TC_SMEM_BYTES = SM_TMEM + 64;
+constexpr uint32_t SM_WIN = SM_BAR + 512;  // 8192: proj_in weights transposed [13][128] | bias | pre_norm.w | pre_norm.b (fp32), staged once
+constexpr uint32_t TC_SMEM_BYTES = SM_WIN + 8192;
 
 enum Bar { BAR_A = 0 /*[2]*/, BAR_ACC = 2 /*[2]*/, BAR_UREADY = 4 /*[2]*/, BAR_X = 6 /*[2]*/, BAR_WFULL = 8 /*[6]*/,
            BAR_WEMPTY = 14 /*[6]*/, BAR_COUNT = 20 };
@@ -264,8 +265,13 @@ struct TcParams {
   int N, depth, flags;
   long long M;
   long long* dbg;  // optional timeline buffer: CTA 0 records clock64() at phase boundaries
+  // persistent work list: item idx = step_local * n_units + unit, CTA c takes idx = c, c + gridDim.x, ...
+  int n_units, n_steps, t_first;  // units of 2 tiles; timesteps t_first, t_first-1, ... (n_steps of them)
+  size_t fold_step_bytes;         // distance between the fold packets of consecutive steps
+  int* done;                      // per unit: number of tile-steps completed since the loop began (cross-CTA dependency), or NULL
   // fused eps -> x_{t-1} update (sampling loop): active when upd_sched != NULL
-  const float* upd_sched; int upd_T, upd_t; const float* upd_noise; uint64_t upd_seed; float* x_out;
+  const float* upd_sched; int upd_T; const float* upd_noise; size_t noise_step_elems; uint64_t upd_seed; float* x_out;
+  float* traj; int traj_interval;
 };
 
 // Packed fp32x2 math (FFMA2 on sm_100): the CUDA-core epilogues are the bottleneck of this kernel (the
@@ -291,7 +297,7 @@ __device__ __forceinline__ float2 geglu2(float2 a_half, float2 g) {
 // timeline instrumentation (off unless a buffer is supplied): slot layout [who][event], who 0 = tile-0 row 0, 1 = MMA lane
 #define TL(who, ev)                                                                                  \
   do {                                                                                               \
-    if (P.dbg != nullptr && blockIdx.x == 0 && tl_on) P.dbg[(who) * 512 + (ev)] = clock64();         \
+    if (P.dbg != nullptr && blockIdx.x == 0 && item_n == 0 && tl_on) P.dbg[(who) * 512 + (ev)] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -371,6 +377,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     uint4 v = make_uint4(tid < 128 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(smem + SM_ONES + tid * 16) = v;
   }
+  {
+    // proj_in weights staged transposed ([feature][output], fp32) so that one broadcast LDS.128 feeds two FFMA2 (4 outputs)
+    float* wt = reinterpret_cast<float*>(smem + SM_WIN);
+    for (int i = tid; i < D_MODEL * 13; i += TC_THREADS) {
+      const int k = i / 13, c = i - k * 13;  // coalesced read of w_in[k][c]
+      wt[c * D_MODEL + k] = __ldg(P.w_in + i);
+    }
+    if (tid < D_MODEL) {
+      wt[13 * D_MODEL + tid] = __ldg(P.b_in + tid);
+      wt[14 * D_MODEL + tid] = __ldg(P.pre_w + tid);
+      wt[15 * D_MODEL + tid] = __ldg(P.pre_b + tid);
+    }
+  }
   fence_proxy_async();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
   // sample index of each tile (all 128 rows of a tile belong to one sample: N % 128 == 0); an out-of-range second tile
   // recomputes the last valid one
   const long long n_tiles = P.M / 128;
-  const long long tile_id0 = (long long)blockIdx.x * 2;
+  const long long total_items = (long long)P.n_units * P.n_steps;
 
   if (warp < 8) {
     // =========================== epilogue warps: one thread per token row ===========================
@@ -391,38 +410,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     const uint32_t X = lane_base + T * 128, ACC = lane_base + 256 + T * 128;
     uint8_t* a_tile = smem + SM_A + T * 32768;
     uint8_t* u_tile = smem + SM_U + T * 16384;
+    const bool tl_on = tid == 0;
+    uint32_t ph_acc = 0, ph_x = 0;
+    int item_n = 0;
+#pragma unroll 1
+    for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++item_n) {
+    const int unit = (int)(idx % P.n_units), step_local = (int)(idx / P.n_units);
+    const int t_cur = P.t_first - step_local;
+    const long long tile_id0 = (long long)unit * 2;
     const bool tile_ok = tile_id0 + T < n_tiles;
     const long long tok = (tile_ok ? tile_id0 + T : n_tiles - 1) * 128 + r;
     const long long b = tok / P.N;
     const int p = (int)(tok - b * P.N);
-    const bool tl_on = tid == 0;
-    uint32_t ph_acc = 0, ph_x = 0;
     uint32_t vmask = 0;  // bit j set = part token j is valid
 #pragma unroll
     for (int j = 0; j < MAX_TOKENS; ++j)
       if (P.valid == nullptr || __ldg(P.valid + b * MAX_TOKENS + j) != 0.f) vmask |= 1u << j;
     TL(0, 0);
+    if (P.done != nullptr) {
+      // x of this unit at this timestep is produced by the item (unit, previous step), possibly on another SM
+      if (r == 0) {
+        const int need = 2 * (P.upd_T - 1 - t_cur);
+        int have;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(P.done + unit) : "memory");
+        } while (have < need);
+      }
+      named_bar_sync(1 + T, 128);
+    }
 
     // ---- proj_in (13 -> 128) + pre_norm, result (the residual stream) into TMEM ----
-    // proj_in weights are staged transposed ([feature][output], fp32) in the (still unused) U-tile region so that one
-    // broadcast LDS.128 feeds two FFMA2 (4 outputs) -- the straightforward per-output uniform LDG version of this
-    // prologue cost 11% of the kernel.
     {
-      float* wt = reinterpret_cast<float*>(smem + SM_U);  // [13][128] weights, [128] bias, [128] pre_norm.w, [128] pre_norm.b
-      const int et = tid;                                  // 256 epilogue threads
-      for (int i = et; i < D_MODEL * 13; i += 256) {
-        const int k = i / 13, c = i - k * 13;              // coalesced read of w_in[k][c]
-        wt[c * D_MODEL + k] = __ldg(P.w_in + i);
-      }
-      if (et < D_MODEL) {
-        wt[13 * D_MODEL + et] = __ldg(P.b_in + et);
-        wt[14 * D_MODEL + et] = __ldg(P.pre_w + et);
-        wt[15 * D_MODEL + et] = __ldg(P.pre_b + et);
-      }
+      const float* wt = reinterpret_cast<const float*>(smem + SM_WIN);
       float f[13];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        f[c] = __ldg(P.x + (b * 3 + c) * P.N + p);
+        f[c] = __ldcg(P.x + (b * 3 + c) * P.N + p);  // x is rewritten every step by other SMs: read through L2
         f[3 + c] = __ldg(P.anchors + (b * 3 + c) * P.N + p);
         const float v = __ldg(P.variances + (b * 3 + c) * P.N + p);
         f[6 + c] = (P.flags & DFB200_NET_INCLUDE_STD) ? sqrtf(v) : v;
@@ -430,7 +453,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       const int part = __ldg(P.assign + tok);
 #pragma unroll
       for (int c = 0; c < 4; ++c) f[9 + c] = part == c ? 1.f : 0.f;
-      named_bar_sync(3, 256);
       float2 s2 = f2s(0.f), q2 = f2s(0.f);
 #pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
@@ -471,7 +493,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         tmem_st32(X + cb * 32, h);
       }
       tmem_wait_st();
-      named_bar_sync(3, 256);  // everyone is done with the staged weights before the U region is reused
     }
 
     TL(0, 1);
@@ -591,26 +612,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       }
       if (P.upd_sched != nullptr) {
         // anchored DDPM update fused into the epilogue (same arithmetic as dfb200_ddpm_step; every sample shares t)
-        const StepCoef cf = load_step_coef(P.upd_sched, P.upd_T, P.upd_t);
+        const StepCoef cf = load_step_coef(P.upd_sched, P.upd_T, t_cur);
+        const float* znoise = P.upd_noise != nullptr ? P.upd_noise + (size_t)step_local * P.noise_step_elems : nullptr;
+        const bool keep = P.traj != nullptr && t_cur > 0 && t_cur % P.traj_interval == 0;
+        float* tr = keep ? P.traj + (size_t)(t_cur / P.traj_interval - 1) * (size_t)P.M * 3 : nullptr;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const long long e = (b * 3 + c) * P.N + p;
-          const float xv = __ldg(P.x + e), av = __ldg(P.anchors + e), vv = __ldg(P.variances + e);
+          const float xv = __ldcg(P.x + e), av = __ldg(P.anchors + e), vv = __ldg(P.variances + e);
           float z;
-          if (P.upd_noise != nullptr) {
-            z = __ldg(P.upd_noise + e);
+          if (znoise != nullptr) {
+            z = __ldg(znoise + e);
           } else {
-            const float4 z4 = philox_normal4((uint64_t)(e >> 2), (uint64_t)P.upd_t, P.upd_seed);
+            const float4 z4 = philox_normal4((uint64_t)(e >> 2), (uint64_t)t_cur, P.upd_seed);
             const int ln = (int)(e & 3);
             z = ln == 0 ? z4.x : ln == 1 ? z4.y : ln == 2 ? z4.z : z4.w;
           }
           const float x0 = ddpm_xstart(cf, xv, av, vv, eps3[c]);
           const float xp = ddpm_prev(cf, xv, av, vv, x0, z);
-          if (tile_ok) P.x_out[e] = xp;
+          if (tile_ok) {
+            P.x_out[e] = xp;
+            if (keep) tr[e] = xp;
+          }
         }
       }
     }
     TL(0, 3 + P.depth * 40);
+    if (P.done != nullptr) {
+      __threadfence();                 // this thread's x_out stores are visible GPU-wide ...
+      named_bar_sync(1 + T, 128);      // ... for all 128 rows of the tile ...
+      if (r == 0) atomicAdd(P.done + unit, 1);  // ... before the tile-step is published
+    }
+    }  // items
     tc_fence_before();
   } else if (warp == 8) {
     // =========================== MMA issuer ===========================
@@ -643,8 +676,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       umma_bf16(d, ones_desc, make_smem_desc(pa + SLAB_OFF, 0, TILE_SBO), idesc128, 1u);
       umma_commit(&bars[BAR_ACC + T]);
     };
+    int item_n = 0;
+#pragma unroll 1
+    for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++item_n)
     for (int l = 0; l < P.depth; ++l) {
-      const int G0 = l * PKT_PER_LAYER;
+      const int G0 = (item_n * P.depth + l) * PKT_PER_LAYER;
       TL(1, 2 + l * 40);
       // ---- logits: S_T = LN2(x_T) W_sim^T + b_sim -> ACC_T columns [0,32) ----
       uint32_t pf0 = 0, pf1 = 0;
@@ -730,21 +766,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     tc_fence_before();
   } else {
     // =========================== weight producer ===========================
-    const long long t0 = tile_id0 < n_tiles ? tile_id0 : n_tiles - 1, t1 = tile_id0 + 1 < n_tiles ? tile_id0 + 1 : n_tiles - 1;
-    const long long b0 = t0 * 128 / P.N, b1 = t1 * 128 / P.N;
-    const int total = P.depth * PKT_PER_LAYER;
-    for (int G = 0; G < total; ++G) {
-      const int slot = G % NSLOT;
-      mbar_wait(&bars[BAR_WEMPTY + slot], ((uint32_t)(G / NSLOT) & 1u) ^ 1u);
-      if (elect_one()) {
-        const int l = G / PKT_PER_LAYER, p = G - l * PKT_PER_LAYER;
-        const uint32_t bytes = (uint32_t)pkt_bytes(p);
-        const uint8_t* src = p < 2 ? P.fold + ((size_t)(p == 0 ? b0 : b1) * P.depth + l) * FOLD_BYTES
-                                   : P.stream + ((size_t)l * STATIC_PER_LAYER + (p - 2)) * SLOT_BYTES;
-        mbar_arrive_expect_tx(&bars[BAR_WFULL + slot], bytes);
-        bulk_g2s(smem + SM_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_WFULL + slot]);
+    int G = 0;
+#pragma unroll 1
+    for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
+      const int unit = (int)(idx % P.n_units), step_local = (int)(idx / P.n_units);
+      const long long tile_id0 = (long long)unit * 2;
+      const long long t0 = tile_id0 < n_tiles ? tile_id0 : n_tiles - 1, t1 = tile_id0 + 1 < n_tiles ? tile_id0 + 1 : n_tiles - 1;
+      const long long b0 = t0 * 128 / P.N, b1 = t1 * 128 / P.N;
+      const uint8_t* fold = P.fold + (size_t)step_local * P.fold_step_bytes;
+      for (int lp = 0; lp < P.depth * PKT_PER_LAYER; ++lp, ++G) {
+        const int slot = G % NSLOT;
+        mbar_wait(&bars[BAR_WEMPTY + slot], ((uint32_t)(G / NSLOT) & 1u) ^ 1u);
+        if (elect_one()) {
+          const int l = lp / PKT_PER_LAYER, p = lp - l * PKT_PER_LAYER;
+          const uint32_t bytes = (uint32_t)pkt_bytes(p);
+          const uint8_t* src = p < 2 ? fold + ((size_t)(p == 0 ? b0 : b1) * P.depth + l) * FOLD_BYTES
+                                     : P.stream + ((size_t)l * STATIC_PER_LAYER + (p - 2)) * SLOT_BYTES;
+          mbar_arrive_expect_tx(&bars[BAR_WFULL + slot], bytes);
+          bulk_g2s(smem + SM_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_WFULL + slot]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __syncthreads();
@@ -790,10 +832,24 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
   p.M = (long long)B * N;
   p.dbg = g_tc_timeline;
+  p.n_units = cdiv(p.M, 256);
+  p.n_steps = 1;
+  p.t_first = 0;
   if (upd != nullptr) {
-    p.upd_sched = upd->sched; p.upd_T = upd->T; p.upd_t = upd->t; p.upd_noise = upd->noise; p.upd_seed = upd->seed; p.x_out = upd->x_out;
+    p.upd_sched = upd->sched; p.upd_T = upd->T; p.t_first = upd->t; p.upd_noise = upd->noise; p.upd_seed = upd->seed; p.x_out = upd->x_out;
+    p.n_steps = upd->n_steps; p.fold_step_bytes = upd->fold_step_bytes; p.noise_step_elems = (size_t)p.M * 3;
+    p.done = upd->done; p.traj = upd->traj; p.traj_interval = upd->traj_interval;
   }
-  denoiser_tc_kernel<<<cdiv(p.M, 256), TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    DFB_CUDA(cudaGetDevice(&dev));
+    DFB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // persistent: one CTA per SM walks the (step, unit) work list; dependencies between steps of a unit go through P.done
+  const long long items = (long long)p.n_units * p.n_steps;
+  const int grid = (int)(items < n_sm ? items : n_sm);
+  denoiser_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

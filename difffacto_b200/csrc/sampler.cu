@@ -37,7 +37,8 @@ struct LoopWorkspace {
   float* kv_time;    // [T,depth,2,128]
   float* kv_static;  // [B,depth,2,4,128]
   void* fold;        // [chunk][B][depth] fold packets
-  int chunk;         // sampling steps per fold launch
+  int* done;         // [units] cross-step dependency counters of the persistent kernel
+  int chunk;         // sampling steps per fold launch / persistent kernel launch
   size_t net_bytes;
   size_t bytes;
 };
@@ -69,6 +70,7 @@ static LoopWorkspace carve_loop(const NetDims& d, int mode, int B, int N, int T,
     if (chunk > T) chunk = T;
     w.chunk = (int)chunk;
     w.fold = take(per_step * (size_t)chunk);
+    w.done = reinterpret_cast<int*>(take(sizeof(int) * (size_t)cdiv((long long)B * N, 256)));
   }
   w.bytes = off;
   return w;
@@ -151,23 +153,22 @@ extern "C" int dfb200_ddpm_sample_loop(const dfb200_denoiser_cfg* cfg, const voi
   rc = launch_context_kv_static(L, P, B, ctx, lw.kv_static, st);
   if (rc != DFB200_OK) return rc;
   const size_t per_step = tc_fold_bytes_for(L.d, B);
+  DFB_CUDA(cudaMemsetAsync(lw.done, 0, sizeof(int) * (size_t)cdiv((long long)B * N, 256), st));
   for (int i0 = T - 1; i0 >= 0; i0 -= lw.chunk) {
     const int steps = i0 + 1 < lw.chunk ? i0 + 1 : lw.chunk;
     rc = launch_context_fold(L, packed, B, lw.kv_static, lw.kv_time, i0, steps, lw.fold, st);
     if (rc != DFB200_OK) return rc;
-    for (int s = 0; s < steps; ++s) {
-      const int i = i0 - s;
-      TcUpdate u{};
-      u.sched = sched; u.T = T; u.t = i;
-      u.noise = philox ? nullptr : noise + (size_t)(T - 1 - i) * total;
-      u.seed = seed;
-      u.x_out = x;
-      rc = denoiser_step_tc(L, packed, B, N, x, anchors, variance, anchor_assignment, valid,
-                            reinterpret_cast<const char*>(lw.fold) + (size_t)s * per_step, nullptr, &u, st);
-      if (rc != DFB200_OK) return rc;
-      rc = keep_traj(i);
-      if (rc != DFB200_OK) return rc;
-    }
+    // ONE persistent launch runs `steps` timesteps for every 256-token unit (148 CTAs walk the (step, unit) list; a unit's
+    // next step waits on its previous one through lw.done), so no SM idles at step boundaries.
+    TcUpdate u{};
+    u.sched = sched; u.T = T; u.t = i0; u.n_steps = steps; u.fold_step_bytes = per_step;
+    u.noise = philox ? nullptr : noise + (size_t)(T - 1 - i0) * total;
+    u.seed = seed;
+    u.x_out = x;
+    u.done = lw.done;
+    u.traj = traj; u.traj_interval = traj_interval;
+    rc = denoiser_step_tc(L, packed, B, N, x, anchors, variance, anchor_assignment, valid, lw.fold, nullptr, &u, st);
+    if (rc != DFB200_OK) return rc;
   }
   return DFB200_OK;
 }
