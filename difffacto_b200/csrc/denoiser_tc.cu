@@ -264,7 +264,8 @@ struct TcParams {
   float* eps_out;
   int N, depth, flags;
   long long M;
-  long long* dbg;  // optional timeline buffer: CTA 0 records clock64() at phase boundaries
+  long long* dbg;  // optional timeline buffer: CTA 0 records clock64() at the phase boundaries of its dbg_item-th work item
+  int dbg_item;
   // persistent work list: item idx = step_local * n_units + unit, CTA c takes idx = c, c + gridDim.x, ...
   int n_units, n_steps, t_first;  // units of 2 tiles; timesteps t_first, t_first-1, ... (n_steps of them)
   size_t fold_step_bytes;         // distance between the fold packets of consecutive steps
@@ -297,7 +298,7 @@ __device__ __forceinline__ float2 geglu2(float2 a_half, float2 g) {
 // timeline instrumentation (off unless a buffer is supplied): slot layout [who][event], who 0 = tile-0 row 0, 1 = MMA lane
 #define TL(who, ev)                                                                                  \
   do {                                                                                               \
-    if (P.dbg != nullptr && blockIdx.x == 0 && item_n == 0 && tl_on) P.dbg[(who) * 512 + (ev)] = clock64(); \
+    if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) P.dbg[(who) * 512 + (ev)] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -797,6 +798,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
 }
 
 static long long* g_tc_timeline = nullptr;  // set by dfb200_debug_tc_timeline
+static int g_tc_timeline_item = 0;
 
 static const float* tc_extras(const PackLayout& L, const void* packed) {
   const uint8_t* S = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
@@ -832,6 +834,7 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
   p.M = (long long)B * N;
   p.dbg = g_tc_timeline;
+  p.dbg_item = g_tc_timeline_item;
   p.n_units = cdiv(p.M, 256);
   p.n_steps = 1;
   p.t_first = 0;
@@ -868,7 +871,8 @@ int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, c
 using namespace dfb200;
 
 // Debug hook: device buffer of 1024 int64 that CTA 0 of the fused kernel fills with clock64() stamps (NULL = off).
-extern "C" int dfb200_debug_tc_timeline(long long* device_buffer) {
+extern "C" int dfb200_debug_tc_timeline(long long* device_buffer, int item) {
   g_tc_timeline = device_buffer;
+  g_tc_timeline_item = item;
   return DFB200_OK;
 }

@@ -54,9 +54,73 @@ group_points_kernel(int c, int n, long long S, int c_per_block, const float* __r
   }
 }
 
+// Shared-memory staged variant for large S (grouping: npoints*nsample outputs per source row).  A CTA owns a tile of
+// GS_S consecutive outputs and a tile of channels: the idx tile is read ONCE into registers, then for every channel the
+// source row (n floats) is staged in shared memory with coalesced loads (double-buffered) and gathered from there, so
+// the random 4-byte reads never leave the SM and HBM/L2 see only the streaming idx read and the streaming output
+// write.  Without staging every 16 B of output costs up to 4 x 32 B sectors of L2 reads.
+constexpr int GS_THREADS = 256;
+constexpr int GS_PER_THREAD = 8;                       // outputs per thread (two float4 stores per channel)
+constexpr int GS_S = GS_THREADS * GS_PER_THREAD;       // 2048 outputs per CTA
+__global__ void __launch_bounds__(GS_THREADS)
+group_points_smem_kernel(int c, int n, long long S, int c_per_block, const float* __restrict__ points,
+                         const int* __restrict__ idx, float* __restrict__ out) {
+  extern __shared__ float gs_rows[];  // [2][n]
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * c_per_block, c1 = min(c, c0 + c_per_block);
+  const float* pts = points + (size_t)b * c * n;
+  const long long s0 = (long long)blockIdx.x * GS_S + threadIdx.x * 4;
+  const long long s1 = s0 + GS_THREADS * 4;
+  const int* id = idx + (size_t)b * S;
+  float* o = out + (size_t)b * c * S;
+  int4 ia = make_int4(0, 0, 0, 0), ib = ia;
+  const bool va = s0 < S, vb = s1 < S;
+  if (va) ia = __ldg(reinterpret_cast<const int4*>(id + s0));
+  if (vb) ib = __ldg(reinterpret_cast<const int4*>(id + s1));
+  auto stage = [&](int l, int buf) {
+    const float* row = pts + (size_t)l * n;
+    float* dst = gs_rows + (size_t)buf * n;
+    for (int i = threadIdx.x * 4; i < n; i += GS_THREADS * 4) {
+      if (i + 3 < n && ((reinterpret_cast<uintptr_t>(row + i) & 15) == 0)) {
+        *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(row + i));
+      } else {
+        for (int k = i; k < min(i + 4, n); ++k) dst[k] = __ldg(row + k);
+      }
+    }
+  };
+  stage(c0, 0);
+  __syncthreads();
+  for (int l = c0; l < c1; ++l) {
+    const int buf = (l - c0) & 1;
+    if (l + 1 < c1) stage(l + 1, buf ^ 1);
+    const float* r = gs_rows + (size_t)buf * n;
+    if (va) __stcs(reinterpret_cast<float4*>(o + (size_t)l * S + s0), make_float4(r[ia.x], r[ia.y], r[ia.z], r[ia.w]));
+    if (vb) __stcs(reinterpret_cast<float4*>(o + (size_t)l * S + s1), make_float4(r[ib.x], r[ib.y], r[ib.z], r[ib.w]));
+    __syncthreads();
+  }
+}
+
 static int launch_group(int b, int c, int n, long long S, const float* points, const int* idx,
                         float* out, cudaStream_t st) {
   if (b == 0 || c == 0 || S == 0) return DFB200_OK;
+  {
+    // staged path: 16 B-aligned vectorisable outputs, a source row that fits twice in shared memory, enough reuse of it
+    const bool vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const size_t smem = sizeof(float) * 2 * (size_t)n;
+    if (vec_ok && S >= 4 * (long long)n && smem <= 96 * 1024 && b <= 65535) {
+      const int gx = cdiv(S, GS_S);
+      int cpb = c;
+      while (cpb > 8 && (long long)gx * b * cdiv(c, cpb) < 148 * 6) cpb = (cpb + 1) / 2;
+      dim3 grid(gx, cdiv(c, cpb), b);
+      if (grid.y <= 65535) {
+        if (smem > 48 * 1024)
+          DFB_CUDA(cudaFuncSetAttribute(group_points_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_points_smem_kernel<<<grid, GS_THREADS, smem, st>>>(c, n, S, cpb, points, idx, out);
+        DFB_LAUNCH_CHECK();
+        return DFB200_OK;
+      }
+    }
+  }
   const bool vec = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const long long work = vec ? S / 4 : S;

@@ -220,8 +220,9 @@ int dfb200_selftest_umma(int variant, int N, int K, const float* A, const float*
 int dfb200_bench_umma(int layout, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream);
 
 /* Profiling hook: a device buffer of 1024 int64 that CTA 0 of the fused bf16 denoiser kernel fills with
- * clock64() stamps at its phase boundaries ([0..511] tile-0 epilogue, [512..1023] MMA issuer); NULL disables. */
-int dfb200_debug_tc_timeline(long long* device_buffer);
+ * clock64() stamps at the phase boundaries of its `item`-th work item ([0..511] tile-0 epilogue, [512..1023] MMA
+ * issuer); NULL disables. */
+int dfb200_debug_tc_timeline(long long* device_buffer, int item);
 
 /* Scratch bytes for dfb200_ddpm_sample_loop. */
 size_t dfb200_ddpm_sample_loop_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B,

@@ -105,7 +105,7 @@ def main():
         a, b = torch.rand(B, n, 3, device="cuda"), torch.rand(B, n, 3, device="cuda")
         o = timeit(lambda: chamfer_forward(a, b))
         r = timeit(lambda: C.forward(a, b)) if C else None
-        report("chamfer_forward", f"B={B} n=m={n}", o, r, B * (24 * n + 16 * n), f"{2 * B * n * n / o / 1e6:.1f} Gpair/s (FP32 ALU bound)")
+        report("chamfer_forward", f"B={B} n=m={n}", o, r, B * (24 * n + 16 * n), f"{2 * B * n * n / o / 1e6:.2f} Tpair/s (FP32 ALU bound)")
     Em = REF.get("ref_emd")
     for (B, n, eps, iters) in ((32, 2048, 0.005, 50), (32, 2048, 0.002, 10000), (4, 8192, 0.005, 50)):
         a, b = torch.rand(B, n, 3, device="cuda"), torch.rand(B, n, 3, device="cuda")
