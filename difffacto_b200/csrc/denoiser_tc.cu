@@ -242,6 +242,11 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
+// FF-out A operand (the gated activations U) is handed to the tensor core through TENSOR MEMORY: the epilogue writes the
+// bf16 pairs over the value columns of the hidden chunk it has just consumed (ACC columns [0,32)) and the FF-out MMA runs in
+// TS form.  This removes 16 KB of st.shared + 16 KB of MMA operand reads per tile-chunk from the shared-memory pipe,
+// which is what bounds the feed-forward phase.
+constexpr bool U_IN_TMEM = true;
 constexpr int TC_THREADS = 320;  // warps 0-3: tile 0 epilogue, 4-7: tile 1 epilogue, 8: MMA issuer, 9: weight producer
 constexpr uint32_t SM_A = 0;               // 2 x 32768  A operand tiles (128 x 128 bf16)
 constexpr uint32_t SM_U = 65536;           // 2 x 16384  gated FF activations (128 x 64 bf16), one per tile
@@ -569,11 +574,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
             const float2 y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]));
             u[k] = pack_bf16(y.x, y.y);
           }
+          if (U_IN_TMEM) {
+            tmem_st16(ACC + hf * 16, u);  // value columns [0,32) of this chunk are dead: hf=0 consumed [0,32), hf=1 reads [32,64)
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(u_tile + (hf * 4 + j) * 2048 + r * 16) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(u_tile + (hf * 4 + j) * 2048 + r * 16) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+          }
         }
-        fence_proxy_async();
+        if (U_IN_TMEM) tmem_wait_st();
+        else fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bars[BAR_UREADY + T]);
         TL(0, 9 + l * 40 + c * 2);
@@ -744,7 +754,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d = T * 128;
-            umma_gemm<128, 4>(d, u_base + T * 16384, pw2, idesc128, 1u);  // x_T += U_T W2_c^T
+            if (U_IN_TMEM) {  // x_T += U_T W2_c^T with U read from TMEM (8 columns per K=16 step)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16_ts(d, 256 + T * 128 + ks * 8, make_smem_desc(pw2 + ks * 4096, 2048, TILE_SBO), idesc128, 1u);
+            } else {
+              umma_gemm<128, 4>(d, u_base + T * 16384, pw2, idesc128, 1u);
+            }
             if (last) {
               umma_bf16(d, ones_desc, make_smem_desc(pw2 + SLAB_OFF, 0, TILE_SBO), idesc128, 1u);
               umma_commit(&bars[BAR_X + T]);

@@ -107,7 +107,7 @@ static int launch_group(int b, int c, int n, long long S, const float* points, c
     // staged path: 16 B-aligned vectorisable outputs, a source row that fits twice in shared memory, enough reuse of it
     const bool vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const size_t smem = sizeof(float) * 2 * (size_t)n;
-    if (vec_ok && S >= 4 * (long long)n && smem <= 96 * 1024 && b <= 65535) {
+    if (vec_ok && n >= 1024 && S >= 4 * (long long)n && smem <= 96 * 1024 && b <= 65535) {
       const int gx = cdiv(S, GS_S);
       int cpb = c;
       while (cpb > 8 && (long long)gx * b * cdiv(c, cpb) < 148 * 6) cpb = (cpb + 1) / 2;

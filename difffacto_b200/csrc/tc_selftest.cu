@@ -22,7 +22,7 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 73728);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 73728 + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool swap_lbo_sbo = variant & 1, bias_two_slabs = variant & 2, use_bulk = variant & 4;
+  const bool swap_lbo_sbo = variant & 1, bias_two_slabs = variant & 2, use_bulk = variant & 4, a_in_tmem = variant & 8;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
   // A: row tid
   for (int k = 0; k < K; k += 2)
@@ -46,7 +46,7 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
   }
   fence_proxy_async();
   __threadfence();
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -55,6 +55,17 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
   if (use_bulk && tid == 0) {
     mbar_arrive_expect_tx(&bars[1], (uint32_t)(N * K * 2));
     bulk_g2s(b_tile, scratch, (uint32_t)(N * K * 2), &bars[1]);
+  }
+  if (a_in_tmem) {  // A (bf16, two k per 32-bit column) into TMEM columns [128, 128 + K/2)
+    for (int cb = 0; cb < (K / 2 + 31) / 32; ++cb) {
+      float h[32];
+      for (int j = 0; j < 32; ++j) {
+        const int k = (cb * 32 + j) * 2;
+        h[j] = k + 1 < K ? __uint_as_float(pack_bf16(A[tid * K + k], A[tid * K + k + 1])) : 0.f;
+      }
+      tmem_st32(row_addr + 128 + cb * 32, h);
+    }
+    tmem_wait_st();
   }
   if (Cin != nullptr) {
     for (int cb = 0; cb < N / 32; ++cb) {
@@ -76,7 +87,8 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
       for (int ks = 0; ks < K / 16; ++ks) {
         const uint64_t ad = make_smem_desc(smem_u32(a_tile) + ks * 4096, a_lbo, a_sbo);
         const uint64_t bd = make_smem_desc(smem_u32(b_tile) + ks * (N * 32), b_lbo, b_sbo);
-        umma_bf16(tmem, ad, bd, idesc, (ks > 0 || Cin != nullptr) ? 1u : 0u);
+        if (a_in_tmem) umma_bf16_ts(tmem, tmem + 128 + ks * 8, bd, idesc, (ks > 0 || Cin != nullptr) ? 1u : 0u);
+        else umma_bf16(tmem, ad, bd, idesc, (ks > 0 || Cin != nullptr) ? 1u : 0u);
       }
       if (bias != nullptr) {
         const uint64_t od = make_smem_desc(smem_u32(ones), a_lbo, a_sbo);
@@ -101,7 +113,7 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, 256);
   }
 }
 

@@ -36,7 +36,7 @@ def run(variant, N, K, use_bias, use_cin):
 
 
 if __name__ == "__main__":
-    for variant in range(8):
+    for variant in (0, 2, 4, 6, 8, 10, 12):
         for (N, K) in [(128, 16), (128, 128), (64, 128), (32, 32)]:
             try:
                 print(f"variant={variant} N={N} K={K}: plain {run(variant, N, K, False, False)}  "
