@@ -41,7 +41,7 @@ using namespace tc;
 // 512+64c..; W1' = W1.diag(norm3.w), b1' = b1 + W1.norm3.b.  W2_c: 128 rows x k[64c, 64c+64).
 // ---------------------------------------------------------------------------------------------
 constexpr int SLOT_BYTES = 18432;
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 8;
 constexpr int STATIC_PER_LAYER = 24;
 constexpr int PKT_PER_LAYER = 26;
 constexpr int FF_CHUNKS = 8;
@@ -243,22 +243,20 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 // FF-out A operand (the gated activations U) is handed to the tensor core through TENSOR MEMORY: the epilogue writes the
-// bf16 pairs over the value columns of the hidden chunk it has just consumed (ACC columns [0,32)) and the FF-out MMA runs in
-// TS form.  This removes 16 KB of st.shared + 16 KB of MMA operand reads per tile-chunk from the shared-memory pipe,
-// which is what bounds the feed-forward phase.
-constexpr bool U_IN_TMEM = true;
+// bf16 pairs over the value columns of the hidden chunk it has just consumed and the FF-out MMA runs in TS form.  This
+// removes 16 KB of st.shared + 16 KB of MMA operand reads per tile-chunk from the shared-memory pipe.
 constexpr int TC_THREADS = 320;  // warps 0-3: tile 0 epilogue, 4-7: tile 1 epilogue, 8: MMA issuer, 9: weight producer
 constexpr uint32_t SM_A = 0;               // 2 x 32768  A operand tiles (128 x 128 bf16)
-constexpr uint32_t SM_U = 65536;           // 2 x 16384  gated FF activations (128 x 64 bf16), one per tile
-constexpr uint32_t SM_ONES = 98304;        // 4096  ones tile (128 x 16 bf16: k=0,1 -> 1)
-constexpr uint32_t SM_RING = 102400;       // 6 x 18432
-constexpr uint32_t SM_BAR = 212992;        // mbarriers
+constexpr uint32_t SM_ONES = 65536;        // 4096  ones tile (128 x 16 bf16: k=0,1 -> 1)
+constexpr uint32_t SM_RING = 69632;        // NSLOT x 18432
+constexpr uint32_t SM_BAR = SM_RING + NSLOT * SLOT_BYTES;  // mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
 constexpr uint32_t SM_WIN = SM_BAR + 512;  // 8192: proj_in weights transposed [13][128] | bias | pre_norm.w | pre_norm.b (fp32), staged once
 constexpr uint32_t TC_SMEM_BYTES = SM_WIN + 8192;
 
-enum Bar { BAR_A = 0 /*[2]*/, BAR_ACC = 2 /*[2]*/, BAR_UREADY = 4 /*[2]*/, BAR_X = 6 /*[2]*/, BAR_WFULL = 8 /*[6]*/,
-           BAR_WEMPTY = 14 /*[6]*/, BAR_COUNT = 20 };
+enum Bar { BAR_A = 0 /*[2]*/, BAR_ACC = 2 /*[2]*/, BAR_UREADY = 4 /*[2]*/, BAR_X = 6 /*[2]*/, BAR_WFULL = 8 /*[NSLOT]*/,
+           BAR_WEMPTY = 8 + NSLOT /*[NSLOT]*/, BAR_COUNT = 8 + 2 * NSLOT };
+static_assert(BAR_COUNT * 8 <= 256, "barrier block");
 
 struct TcParams {
   const uint8_t* stream;  // static packets
@@ -374,7 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
   if (warp == 8 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[BAR_A + i], 128); mbar_init(&bars[BAR_X + i], 1);
-      mbar_init(&bars[BAR_ACC + i], 1); mbar_init(&bars[BAR_UREADY + i], 128);
+      mbar_init(&bars[BAR_ACC + i], 1); mbar_init(&bars[BAR_UREADY + i], 256);
     }
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&bars[BAR_WFULL + i], 1); mbar_init(&bars[BAR_WEMPTY + i], 1); }
     fence_barrier_init();
@@ -415,9 +413,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t X = lane_base + T * 128, ACC = lane_base + 256 + T * 128;
     uint8_t* a_tile = smem + SM_A + T * 32768;
-    uint8_t* u_tile = smem + SM_U + T * 16384;
     const bool tl_on = tid == 0;
-    uint32_t ph_acc = 0, ph_x = 0;
+    uint32_t ph_acc = 0, ph_acc_oth = 0, ph_x = 0;  // ph_acc_oth: BAR_ACC of the OTHER tile (FF phase works on both)
     int item_n = 0;
 #pragma unroll 1
     for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++item_n) {
@@ -556,17 +553,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       TL(0, 7 + l * 40);
 
       // ---- GEGLU feed-forward: 8 chunks of 64 value + 64 gate columns ----
+      // All 8 epilogue warps work on EACH tile's chunk: warps 0-3 take value/gate columns [0,32), warps 4-7 columns
+      // [32,64) of the same 128 rows (warp w and w+4 own the same TMEM lanes).  The GEGLU latency of a tile-chunk is
+      // halved, which takes it below the tensor-pipe time of the other tile's FF-out + FF-in: the FF phase becomes
+      // MMA bound.  The gated activations go back to TMEM over the value columns this thread has just consumed
+      // (U columns [32h, 32h+16) for column half h) and FF-out reads them in TS form.
+      // Skip the other tile's logits phase of BAR_ACC: it has completed (this thread is past its own tile's P.W_pv commit,
+      // which the MMA warp issued after both logits MMAs), and it must NOT be waited for here: the barrier may already be
+      // two phases on (the other tile's H_0 does not depend on this thread), where a parity wait would never return.
+      ph_acc_oth ^= 1;
 #pragma unroll 1
       for (int c = 0; c < FF_CHUNKS; ++c) {
-        mbar_wait(&bars[BAR_ACC + T], ph_acc);  // H_c ready; the MMAs are in order, so FF-out of chunk c-1 (reader of U) is done too
-        ph_acc ^= 1;
-        tc_fence_after();
-        TL(0, 8 + l * 40 + c * 2);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int TT = 0; TT < 2; ++TT) {
+          const uint32_t ACCt = lane_base + 256 + TT * 128 + T * 32;
+          mbar_wait(&bars[BAR_ACC + TT], TT == T ? ph_acc : ph_acc_oth);  // H_c of tile TT is ready
+          if (TT == T) ph_acc ^= 1; else ph_acc_oth ^= 1;
+          tc_fence_after();
+          if (TT == 0) TL(0, 8 + l * 40 + c * 2);
           float a[32], gt[32];
-          tmem_ld32(ACC + hf * 32, a);
-          tmem_ld32(ACC + 64 + hf * 32, gt);
+          tmem_ld32(ACCt, a);
+          tmem_ld32(ACCt + 64, gt);
           tmem_wait_ld();
           uint32_t u[16];
 #pragma unroll
@@ -574,19 +581,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
             const float2 y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]));
             u[k] = pack_bf16(y.x, y.y);
           }
-          if (U_IN_TMEM) {
-            tmem_st16(ACC + hf * 16, u);  // value columns [0,32) of this chunk are dead: hf=0 consumed [0,32), hf=1 reads [32,64)
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(u_tile + (hf * 4 + j) * 2048 + r * 16) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-          }
+          tmem_st16(ACCt, u);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bars[BAR_UREADY + TT]);
+          if (TT == 0) TL(0, 9 + l * 40 + c * 2);
         }
-        if (U_IN_TMEM) tmem_wait_st();
-        else fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bars[BAR_UREADY + T]);
-        TL(0, 9 + l * 40 + c * 2);
       }
       mbar_wait(&bars[BAR_X + T], ph_x);
       ph_x ^= 1;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     // base which is 0 for a 512-column allocation), so the issue sequence stays on the uniform datapath.
     constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc32 = make_idesc_bf16(128, 32);
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t ring = sbase + SM_RING, a_base = sbase + SM_A, u_base = sbase + SM_U;
+    const uint32_t ring = sbase + SM_RING, a_base = sbase + SM_A;
     const uint64_t ones_desc = make_smem_desc(sbase + SM_ONES, 2048, TILE_SBO);
     uint32_t ph_a0 = 0, ph_a1 = 0, ph_u0 = 0, ph_u1 = 0;
     const bool tl_on = lane == 0;
@@ -754,13 +754,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d = T * 128;
-            if (U_IN_TMEM) {  // x_T += U_T W2_c^T with U read from TMEM (8 columns per K=16 step)
+            // x_T += U_T W2_c^T with U read from TMEM (8 columns per K=16 step; k [0,32) at columns [0,16), k [32,64) at [32,48))
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_ts(d, 256 + T * 128 + ks * 8, make_smem_desc(pw2 + ks * 4096, 2048, TILE_SBO), idesc128, 1u);
-            } else {
-              umma_gemm<128, 4>(d, u_base + T * 16384, pw2, idesc128, 1u);
-            }
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_ts(d, 256 + T * 128 + (ks >> 1) * 32 + (ks & 1) * 8, make_smem_desc(pw2 + ks * 4096, 2048, TILE_SBO), idesc128, 1u);
             if (last) {
               umma_bf16(d, ones_desc, make_smem_desc(pw2 + SLAB_OFF, 0, TILE_SBO), idesc128, 1u);
               umma_commit(&bars[BAR_X + T]);
