@@ -54,49 +54,56 @@ group_points_kernel(int c, int n, long long S, int c_per_block, const float* __r
   }
 }
 
-// Shared-memory staged variant for large S (grouping: npoints*nsample outputs per source row).  A CTA owns a tile of
-// GS_S consecutive outputs and a tile of channels: the idx tile is read ONCE into registers, then for every channel the
-// source row (n floats) is staged in shared memory with coalesced loads (double-buffered) and gathered from there, so
-// the random 4-byte reads never leave the SM and HBM/L2 see only the streaming idx read and the streaming output
-// write.  Without staging every 16 B of output costs up to 4 x 32 B sectors of L2 reads.
-constexpr int GS_THREADS = 256;
-constexpr int GS_PER_THREAD = 8;                       // outputs per thread (two float4 stores per channel)
-constexpr int GS_S = GS_THREADS * GS_PER_THREAD;       // 2048 outputs per CTA
-__global__ void __launch_bounds__(GS_THREADS)
-group_points_smem_kernel(int c, int n, long long S, int c_per_block, const float* __restrict__ points,
-                         const int* __restrict__ idx, float* __restrict__ out) {
-  extern __shared__ float gs_rows[];  // [2][n]
-  const int b = blockIdx.z;
-  const int c0 = blockIdx.y * c_per_block, c1 = min(c, c0 + c_per_block);
+// Shared-memory staged variant for large S (grouping: npoints*nsample outputs per source row).
+// A CTA owns a tile of G4_S consecutive outputs and a tile of channel QUADS.  The idx tile is read ONCE into registers
+// (4 x int4 per thread).  For every quad of channels the source rows are staged in shared memory INTERLEAVED, one
+// float4 = (ch0, ch1, ch2, ch3) per point, with coalesced row reads and conflict-free STS.128; the gather is then one
+// random LDS.128 per output position that serves four channels (a quarter-warp phase moves 8 x 16 B, so the expected
+// bank-conflict cost per gathered byte is a third of a 4-byte gather's), a 4x4 register transpose, and one streaming
+// STG.128 per channel.  The random reads never leave the SM; HBM sees only the streaming idx read and output write, L2
+// one extra read of the (L2-resident) source per G4_S outputs.
+constexpr int G4_THREADS = 512;
+constexpr int G4_VEC = 4;                               // int4 idx vectors (16 outputs) per thread
+constexpr int G4_S = G4_THREADS * G4_VEC * 4;           // 8192 outputs per CTA
+__global__ void __launch_bounds__(G4_THREADS)
+group_points_c4_kernel(int c, int n, long long S, int quads_per_block, const float* __restrict__ points,
+                       const int* __restrict__ idx, float* __restrict__ out) {
+  extern __shared__ float4 g4_tile[];  // [n]
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int nquad = (c + 3) >> 2;
+  const int q0 = blockIdx.y * quads_per_block, q1 = min(nquad, q0 + quads_per_block);
   const float* pts = points + (size_t)b * c * n;
-  const long long s0 = (long long)blockIdx.x * GS_S + threadIdx.x * 4;
-  const long long s1 = s0 + GS_THREADS * 4;
   const int* id = idx + (size_t)b * S;
   float* o = out + (size_t)b * c * S;
-  int4 ia = make_int4(0, 0, 0, 0), ib = ia;
-  const bool va = s0 < S, vb = s1 < S;
-  if (va) ia = __ldg(reinterpret_cast<const int4*>(id + s0));
-  if (vb) ib = __ldg(reinterpret_cast<const int4*>(id + s1));
-  auto stage = [&](int l, int buf) {
-    const float* row = pts + (size_t)l * n;
-    float* dst = gs_rows + (size_t)buf * n;
-    for (int i = threadIdx.x * 4; i < n; i += GS_THREADS * 4) {
-      if (i + 3 < n && ((reinterpret_cast<uintptr_t>(row + i) & 15) == 0)) {
-        *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(row + i));
-      } else {
-        for (int k = i; k < min(i + 4, n); ++k) dst[k] = __ldg(row + k);
-      }
-    }
-  };
-  stage(c0, 0);
-  __syncthreads();
-  for (int l = c0; l < c1; ++l) {
-    const int buf = (l - c0) & 1;
-    if (l + 1 < c1) stage(l + 1, buf ^ 1);
-    const float* r = gs_rows + (size_t)buf * n;
-    if (va) __stcs(reinterpret_cast<float4*>(o + (size_t)l * S + s0), make_float4(r[ia.x], r[ia.y], r[ia.z], r[ia.w]));
-    if (vb) __stcs(reinterpret_cast<float4*>(o + (size_t)l * S + s1), make_float4(r[ib.x], r[ib.y], r[ib.z], r[ib.w]));
+  const long long sbase = (long long)blockIdx.x * G4_S + tid * 4;
+  int4 ii[G4_VEC];
+  bool ok[G4_VEC];
+#pragma unroll
+  for (int j = 0; j < G4_VEC; ++j) {
+    const long long s = sbase + (long long)j * G4_THREADS * 4;
+    ok[j] = s < S;
+    ii[j] = ok[j] ? __ldg(reinterpret_cast<const int4*>(id + s)) : make_int4(0, 0, 0, 0);
+  }
+  for (int q = q0; q < q1; ++q) {
+    const int l0 = q * 4, nl = min(4, c - l0);
+    const float* r0 = pts + (size_t)l0 * n;
+    const float* r1 = r0 + (nl > 1 ? n : 0);
+    const float* r2 = r0 + (nl > 2 ? 2 * (size_t)n : 0);
+    const float* r3 = r0 + (nl > 3 ? 3 * (size_t)n : 0);
+    __syncthreads();  // the previous quad's gathers are done
+    for (int i = tid; i < n; i += G4_THREADS) g4_tile[i] = make_float4(__ldg(r0 + i), __ldg(r1 + i), __ldg(r2 + i), __ldg(r3 + i));
     __syncthreads();
+    float* o0 = o + (size_t)l0 * S;
+#pragma unroll
+    for (int j = 0; j < G4_VEC; ++j) {
+      if (!ok[j]) continue;
+      const long long s = sbase + (long long)j * G4_THREADS * 4;
+      const float4 a = g4_tile[ii[j].x], bq = g4_tile[ii[j].y], cq = g4_tile[ii[j].z], d = g4_tile[ii[j].w];
+      __stcs(reinterpret_cast<float4*>(o0 + s), make_float4(a.x, bq.x, cq.x, d.x));
+      if (nl > 1) __stcs(reinterpret_cast<float4*>(o0 + (size_t)S + s), make_float4(a.y, bq.y, cq.y, d.y));
+      if (nl > 2) __stcs(reinterpret_cast<float4*>(o0 + 2 * (size_t)S + s), make_float4(a.z, bq.z, cq.z, d.z));
+      if (nl > 3) __stcs(reinterpret_cast<float4*>(o0 + 3 * (size_t)S + s), make_float4(a.w, bq.w, cq.w, d.w));
+    }
   }
 }
 
@@ -104,18 +111,22 @@ static int launch_group(int b, int c, int n, long long S, const float* points, c
                         float* out, cudaStream_t st) {
   if (b == 0 || c == 0 || S == 0) return DFB200_OK;
   {
-    // staged path: 16 B-aligned vectorisable outputs, a source row that fits twice in shared memory, enough reuse of it
+    // staged path: 16 B-aligned vectorisable outputs, an interleaved source tile that fits in shared memory, enough reuse of it
     const bool vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const size_t smem = sizeof(float) * 2 * (size_t)n;
-    if (vec_ok && n >= 1024 && S >= 4 * (long long)n && smem <= 96 * 1024 && b <= 65535) {
-      const int gx = cdiv(S, GS_S);
-      int cpb = c;
-      while (cpb > 8 && (long long)gx * b * cdiv(c, cpb) < 148 * 6) cpb = (cpb + 1) / 2;
-      dim3 grid(gx, cdiv(c, cpb), b);
+    const size_t smem = sizeof(float4) * (size_t)n;
+    if (vec_ok && S >= 4 * (long long)n && S >= 4096 && smem <= 96 * 1024 && b <= 65535) {
+      const int gx = cdiv(S, G4_S);
+      const int nquad = (c + 3) / 4;
+      int qpb = nquad;
+      while (qpb > 1 && (long long)gx * b * cdiv(nquad, qpb) < 148 * 4) qpb = (qpb + 1) / 2;
+      dim3 grid(gx, cdiv(nquad, qpb), b);
       if (grid.y <= 65535) {
-        if (smem > 48 * 1024)
-          DFB_CUDA(cudaFuncSetAttribute(group_points_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        group_points_smem_kernel<<<grid, GS_THREADS, smem, st>>>(c, n, S, cpb, points, idx, out);
+        static size_t smem_set = 48 * 1024;
+        if (smem > smem_set) {
+          DFB_CUDA(cudaFuncSetAttribute(group_points_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+          smem_set = 96 * 1024;
+        }
+        group_points_c4_kernel<<<grid, G4_THREADS, smem, st>>>(c, n, S, qpb, points, idx, out);
         DFB_LAUNCH_CHECK();
         return DFB200_OK;
       }
