@@ -54,6 +54,7 @@ SIGNATURES = {
     "dfb200_bench_umma": (c_int, [c_int, c_int, c_int, c_int, P, P]),
     "dfb200_debug_tc_timeline": (c_int, [P, c_int]),
     "dfb200_selftest_umma": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "dfb200_selftest_umma2": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "dfb200_ddpm_sample_loop_workspace_bytes": (c_size_t, [_CFG, c_int, c_int, c_int, c_int]),
     "dfb200_ddpm_sample_loop": (c_int, [_CFG, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_u64, P,
                                          c_int, P, c_size_t, P]),

@@ -118,6 +118,116 @@ umma_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair UMMA self-test: D[256 x N] = Cin + A[256 x K] . W[N x K]^T + bias with cta_group::2 (M = 256).
+// CTA rank r: A rows [128r, 128r+128) (shared memory, or its TMEM when variant&8), B rows [r*N/2, (r+1)*N/2) as an
+// (N/2)-row tile, bias slab rows likewise; rank 1 tells rank 0 "my operands are in place" with one remote mbarrier
+// arrive per warp (variant&4: B arrives by bulk copy and the full-barrier completion is relayed); rank 0 issues the
+// MMAs and the multicast commit; each CTA reads its 128 rows of D out of its own TMEM.
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma2_selftest_kernel(int variant, int N, int K, const float* __restrict__ A, const float* __restrict__ W,
+                      const float* __restrict__ bias, const float* __restrict__ Cin, float* __restrict__ D,
+                      uint8_t* __restrict__ scratch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_tile = smem;                 // 128 x 128 bf16 max = 32768
+  uint8_t* b_tile = smem + 32768;         // 64 x 128 bf16 max = 16384
+  uint8_t* ones = smem + 49152;           // 4096
+  uint8_t* bslab = smem + 53248;          // 64 rows x 16 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 57344);  // 0: D ready (both), 1: local bulk full, 2: operands ready (rank 0; 8 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 57344 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool use_bulk = variant & 4, a_in_tmem = variant & 8;
+  const int NH = N / 2;
+  const float* Ar = A + (size_t)rank * 128 * K;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 8); fence_barrier_init(); }
+  for (int k = 0; k < K; k += 2)
+    *reinterpret_cast<uint32_t*>(a_tile + tile_off(128, tid, k)) = pack_bf16(Ar[tid * K + k], Ar[tid * K + k + 1]);
+  uint8_t* bdst = use_bulk ? scratch + (size_t)rank * NH * K * 2 : b_tile;
+  for (int i = tid; i < NH * K / 2; i += 128) {
+    const int n = i / (K / 2), k = (i - n * (K / 2)) * 2;
+    const float* w = W + (size_t)(rank * NH + n) * K + k;
+    *reinterpret_cast<uint32_t*>(bdst + tile_off(NH, n, k)) = pack_bf16(w[0], w[1]);
+  }
+  *reinterpret_cast<uint4*>(ones + tid * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(ones + 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < NH) {
+    const float v = bias != nullptr ? bias[rank * NH + tid] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    uint32_t w0 = (uint32_t)(*reinterpret_cast<const uint16_t*>(&hi)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&lo)) << 16);
+    *reinterpret_cast<uint4*>(bslab + tid * 16) = make_uint4(w0, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  __threadfence();
+  cluster_sync_all();  // barriers initialised in both CTAs before any remote arrive / multicast commit
+  if (warp == 0) tmem_alloc2(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t row_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  if (use_bulk && tid == 0) {
+    mbar_arrive_expect_tx(&bars[1], (uint32_t)(NH * K * 2));
+    bulk_g2s(b_tile, bdst, (uint32_t)(NH * K * 2), &bars[1]);
+  }
+  if (a_in_tmem) {
+    for (int cb = 0; cb < (K / 2 + 31) / 32; ++cb) {
+      float h[32];
+      for (int j = 0; j < 32; ++j) {
+        const int k = (cb * 32 + j) * 2;
+        h[j] = k + 1 < K ? __uint_as_float(pack_bf16(Ar[tid * K + k], Ar[tid * K + k + 1])) : 0.f;
+      }
+      tmem_st32(row_addr + 128 + cb * 32, h);
+    }
+    tmem_wait_st();
+  }
+  if (Cin != nullptr) {
+    for (int cb = 0; cb < N / 32; ++cb) {
+      float h[32];
+      for (int k = 0; k < 32; ++k) h[k] = Cin[(size_t)(rank * 128 + tid) * N + cb * 32 + k];
+      tmem_st32(row_addr + cb * 32, h);
+    }
+    tmem_wait_st();
+  }
+  if (use_bulk) mbar_wait(&bars[1], 0);  // every thread observes its CTA's B half before signalling
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars[2]), 0));
+  if (rank == 0 && warp == 0) {
+    mbar_wait_cluster(&bars[2], 0);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, N);
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ad = make_smem_desc(smem_u32(a_tile) + ks * 4096, 2048, TILE_SBO);
+        const uint64_t bd = make_smem_desc(smem_u32(b_tile) + ks * (NH * 32), NH * 16, TILE_SBO);
+        if (a_in_tmem) umma2_bf16_ts(tmem, tmem + 128 + ks * 8, bd, idesc, (ks > 0 || Cin != nullptr) ? 1u : 0u);
+        else umma2_bf16(tmem, ad, bd, idesc, (ks > 0 || Cin != nullptr) ? 1u : 0u);
+      }
+      if (bias != nullptr)
+        umma2_bf16(tmem, make_smem_desc(smem_u32(ones), 2048, TILE_SBO), make_smem_desc(smem_u32(bslab), 0u, TILE_SBO), idesc, 1u);
+      umma2_commit(&bars[0]);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bars[0], 0);
+  tc_fence_after();
+  for (int cb = 0; cb < N / 32; ++cb) {
+    float h[32];
+    tmem_ld32(row_addr + cb * 32, h);
+    tmem_wait_ld();
+    for (int k = 0; k < 32; ++k) D[(size_t)(rank * 128 + tid) * N + cb * 32 + k] = h[k];
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc2(tmem, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // UMMA issue-rate microbenchmark: `iters` back-to-back K=16 MMAs (M=128, N) from smem operands, cycles from the
 // first issue to the commit's arrival.  layout 0 = no-swizzle canonical tiles (as used by the fused kernel),
 // 1 = SWIZZLE_128B descriptors.  Operand contents are irrelevant (timing only).
@@ -195,6 +305,18 @@ extern "C" int dfb200_selftest_umma(int variant, int N, int K, const float* A, c
   const int smem = 73728 + 128;
   DFB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(variant, N, K, A, W, bias, Cin, D, reinterpret_cast<uint8_t*>(scratch));
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_selftest_umma2(int variant, int N, int K, const float* A, const float* W, const float* bias,
+                                     const float* Cin, float* D, void* scratch, dfb200_stream_t stream) {
+  DFB_REQUIRE((N == 32 || N == 64 || N == 128) && K >= 16 && K <= 128 && K % 16 == 0, DFB200_ERR_INVALID_ARG,
+              "selftest_umma2: N in {32,64,128}, K multiple of 16 in [16,128]");
+  DFB_REQUIRE(!(variant & 4) || scratch != nullptr, DFB200_ERR_INVALID_ARG, "selftest_umma2: bulk variant needs scratch");
+  const int smem = 57344 + 128;
+  DFB_CUDA(cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma2_selftest_kernel<<<2, 128, smem, as_stream(stream)>>>(variant, N, K, A, W, bias, Cin, D, reinterpret_cast<uint8_t*>(scratch));
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

@@ -215,6 +215,13 @@ int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uint64_t offse
 int dfb200_selftest_umma(int variant, int N, int K, const float* A, const float* W, const float* bias,
                          const float* Cin, float* D, void* scratch, dfb200_stream_t stream);
 
+/* The same with a CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256): D[256,N] = Cin + A[256,K].W[N,K]^T + bias.
+ * CTA rank r stages A rows [128r,128r+128) and W rows [r*N/2,(r+1)*N/2); rank 1 signals rank 0 by remote mbarrier
+ * arrives, rank 0 issues the MMAs and a multicast commit.  variant: bit2 stage W through `scratch` with cp.async.bulk,
+ * bit3 A operand from tensor memory (TS form). */
+int dfb200_selftest_umma2(int variant, int N, int K, const float* A, const float* W, const float* bias,
+                          const float* Cin, float* D, void* scratch, dfb200_stream_t stream);
+
 /* Microbenchmark: SM cycles for `iters` back-to-back tcgen05.mma (M=128, N, K=16, bf16) from shared-memory operands
  * cycling over `ksteps` K-slabs; layout 0 = canonical no-swizzle tiles, 1 = SWIZZLE_128B.  out_cycles: device int64. */
 int dfb200_bench_umma(int layout, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream);
