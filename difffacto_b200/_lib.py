@@ -52,6 +52,7 @@ SIGNATURES = {
     "dfb200_q_sample": (c_int, [c_int] * 3 + [P] * 8),
     "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),
     "dfb200_bench_umma": (c_int, [c_int, c_int, c_int, c_int, P, P]),
+    "dfb200_bench_umma2": (c_int, [c_int, c_int, c_int, c_int, P, P]),
     "dfb200_debug_tc_timeline": (c_int, [P, c_int]),
     "dfb200_selftest_umma": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "dfb200_selftest_umma2": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),

@@ -284,6 +284,61 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int layout, int N, in
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// CTA-pair variant of the rate microbenchmark: cta_group::2 MMAs (M = 256, N) issued by rank 0; mode bit0: A from tensor
+// memory (TS form), bit1: every MMA accumulates into the same TMEM tile.  The B half tile has N/2 rows per CTA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma2_rate_kernel(int mode, int N, int iters, int ksteps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 131072 + 64);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  const uint32_t rank = cluster_ctarank();
+  for (int i = tid; i < 131072 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) { mbar_init(&bars[0], 1); fence_barrier_init(); }
+  fence_proxy_async();
+  cluster_sync_all();
+  if (warp == 0) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  cluster_sync_all();
+  if (warp == 0 && rank == 0) {
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t idesc = make_idesc_bf16(256, N);
+    const bool ts = mode & 1, same_acc = mode & 2;
+    const int NH = N / 2;
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      uint64_t ad[8], bd[8];
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int kk = ks % ksteps;
+        ad[ks] = make_smem_desc(sbase + kk * 4096, 2048, TILE_SBO);
+        bd[ks] = make_smem_desc(sbase + 65536 + kk * (NH * 32), NH * 16, TILE_SBO);
+      }
+      t0 = clock64();
+      for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t d = tmem + (same_acc ? 0 : (ks & 1) * 256);
+          if (ts) umma2_bf16_ts(d, tmem + 128 + (ks % ksteps) * 8, bd[ks], idesc, 1u);
+          else umma2_bf16(d, ad[ks], bd[ks], idesc, 1u);
+        }
+      }
+      umma2_commit(&bars[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], 0);
+    t1 = clock64();
+    if (elect_one()) { out[0] = t1 - t0; }
+    __syncwarp();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc2(tmem, 512); }
+}
+
 }  // namespace dfb200
 
 using namespace dfb200;
@@ -317,6 +372,16 @@ extern "C" int dfb200_selftest_umma2(int variant, int N, int K, const float* A, 
   const int smem = 57344 + 128;
   DFB_CUDA(cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma2_selftest_kernel<<<2, 128, smem, as_stream(stream)>>>(variant, N, K, A, W, bias, Cin, D, reinterpret_cast<uint8_t*>(scratch));
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_bench_umma2(int mode, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream) {
+  DFB_REQUIRE(N >= 32 && N <= 256 && N % 32 == 0 && ksteps >= 1 && ksteps <= 8, DFB200_ERR_INVALID_ARG, "bench_umma2: bad shape");
+  DFB_REQUIRE(!(mode & 1) || N <= 128 || (mode & 2), DFB200_ERR_INVALID_ARG, "bench_umma2: TS mode keeps A in TMEM columns [128,192)");
+  const int smem = 131072 + 128;
+  DFB_CUDA(cudaFuncSetAttribute(umma2_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma2_rate_kernel<<<2, 128, smem, as_stream(stream)>>>(mode, N, iters, ksteps, out_cycles);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

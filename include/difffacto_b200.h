@@ -225,6 +225,8 @@ int dfb200_selftest_umma2(int variant, int N, int K, const float* A, const float
 /* Microbenchmark: SM cycles for `iters` back-to-back tcgen05.mma (M=128, N, K=16, bf16) from shared-memory operands
  * cycling over `ksteps` K-slabs; layout 0 = canonical no-swizzle tiles, 1 = SWIZZLE_128B.  out_cycles: device int64. */
 int dfb200_bench_umma(int layout, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream);
+/* Same for a CTA pair (cta_group::2, M = 256); mode bit0: A operand from tensor memory, bit1: single accumulator. */
+int dfb200_bench_umma2(int mode, int N, int iters, int ksteps, long long* out_cycles, dfb200_stream_t stream);
 
 /* Profiling hook: a device buffer of 1024 int64 that CTA 0 of the fused bf16 denoiser kernel fills with
  * clock64() stamps at the phase boundaries of its `item`-th work item ([0..511] tile-0 epilogue, [512..1023] MMA

@@ -15,3 +15,14 @@ for layout in (0, 2):
                 res.append(out.item())
             print(f"{'alternating accumulators' if layout == 0 else 'same accumulator (dependent chain)'} N={N} iters={iters}: cycles {res} -> {min(res) / iters:.1f} cyc/MMA "
                   f"(math floor {N // 2})", flush=True)
+for mode in (0, 1, 2, 3):
+    for N in (64, 128, 256):
+        if (mode & 1) and N > 128 and not (mode & 2):
+            continue
+        res = []
+        for rep in range(3):
+            _lib.check(lib.dfb200_bench_umma2(mode, N, 512, 8, _lib.ptr(out), _lib.stream()))
+            torch.cuda.synchronize()
+            res.append(out.item())
+        print(f"CTA pair (cta_group::2, M=256) {'TS' if mode & 1 else 'SS'} {'same acc' if mode & 2 else 'alternating acc'} N={N} iters=512: "
+              f"{min(res) / 512:.1f} cyc/MMA (per-SM math floor {N // 2})", flush=True)
