@@ -25,6 +25,9 @@ METRIC = "shapes/sec reverse DDPM (2048 pts, 4 parts, 1000 steps)"
 UNIT = "shapes/s"
 B_PER_GPU, NPTS, T_STEPS = 32, 2048, 1000
 FLOP_PER_POINT_STEP = 2308096  # proj_in + 5 x (Q, QK^T, PV, out, GEGLU-in, FF-out) + proj_out
+# dram__bytes_read.sum + dram__bytes_write.sum of one persistent denoiser launch (24 sampling steps of this workload) from the
+# committed `ncu --set full` capture profiles/ncu_denoiser_tc_r1_v7.csv: 69.73 MB + 1.89 MB, i.e. per sampling step:
+NCU_DRAM_BYTES_PER_STEP = (69.734912e6 + 1.889280e6) / 24
 WORKLOAD = "gen_chair full 1000-step reverse sampling, batch=32 per GPU, 2048 pts x 4 parts"
 
 
@@ -241,10 +244,11 @@ def run_ours(args):
                        "global_batch": B * world, "parallelism": f"batch-sharded x{world}, one all-gather of final points",
                        "precision": args.precision, "rng": "in-kernel philox", "l2": "flushed (256 MB write) between timed iterations"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None,
+                         "traffic": NCU_DRAM_BYTES_PER_STEP * 1e-9,
                          "note": f"algorithmic {flop / 1e9:.1f} GFLOP per denoiser step (B*N*{FLOP_PER_POINT_STEP}) / mean time of one "
                                  f"sampling step ({ms_per_net_step * 1e3:.1f} us: context kernels + fused denoiser + update), CUDA events "
-                                 f"over the timed region; peak {peak_src}"},
+                                 f"over the timed region; peak {peak_src}; traffic = measured DRAM GB per sampling step (ncu), algorithmic "
+                                 f"{B * N * 64 / 1e9:.4f} GB"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -21,6 +21,7 @@
 //     FF-out + next FF-in.
 // TMEM map (512 columns): X0 [0,128) X1 [128,256) ACC0 [256,384) ACC1 [384,512).
 #include <float.h>
+#include <stdlib.h>
 
 #include "ddpm.cuh"
 #include "denoiser.cuh"
@@ -61,9 +62,16 @@ __host__ __device__ inline int spkt_w1a(int c) { return c == 0 ? 0 : 3 + 3 * (c 
 __host__ __device__ inline int spkt_w1b(int c) { return spkt_w1a(c) + 1; }
 __host__ __device__ inline int spkt_w2(int c) { return 2 + 3 * c; }
 
-// fp32 extras appended after the static stream: folded head (3x128 + 4), then per block WqG (128x128, = 0.25*Wq.diag(norm2.w)),
-// bqG (128, = 0.25*Wq.norm2.b) and WoT (128x128, = Wo^T) for the fold kernel.
-constexpr size_t HEAD_FLOATS = 3 * D_MODEL + 4;
+// Extras appended after the static stream:
+//   the "in/head" image (INHEAD_BYTES, copied into shared memory once per CTA):
+//     IH_INTILE   proj_in + pre_norm as ONE K=32 UMMA B tile (128 x 32 bf16), see pack_inhead_kernel
+//     IH_HEADTILE post_norm + proj_out as a 16 x 128 bf16 B tile (rows 3..15 zero), IH_HEADSLAB its bias slab
+//     IH_CONST    fp32 constants of the analytic pre_norm variance: Gt[45] | gp[4][9] | cp[4]
+//   then per block WqG (128x128, = 0.25*Wq.diag(norm2.w)), bqG (128, = 0.25*Wq.norm2.b) and WoT (128x128, = Wo^T) for the
+//   fold kernel (fp32).
+constexpr uint32_t IH_INTILE = 0, IH_HEADTILE = 8192, IH_HEADSLAB = 12288, IH_CONST = 12544, INHEAD_BYTES = 13056;
+constexpr int IHC_GT = 0, IHC_GP = 45, IHC_CP = 81;  // float offsets inside IH_CONST (85 floats)
+constexpr size_t HEAD_FLOATS = INHEAD_BYTES / 4;
 constexpr size_t FOLDW_FLOATS = (size_t)D_MODEL * D_MODEL * 2 + D_MODEL;
 
 size_t tc_stream_bytes_for(const NetDims& d) {
@@ -105,18 +113,84 @@ __global__ void pack_bias_kernel(uint8_t* __restrict__ dst, int R, const float* 
 #pragma unroll
   for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
 }
-// folded head: w_out' = w_out.diag(post_norm.w), b_out' = b_out + w_out.post_norm.b   (fp32)
-__global__ void pack_head_kernel(float* __restrict__ dst, const float* __restrict__ w_out, const float* __restrict__ b_out,
-                                 const float* __restrict__ g, const float* __restrict__ be) {
-  const int c = blockIdx.x;
-  float acc = 0.f;
-  for (int k = threadIdx.x; k < D_MODEL; k += 32) {
-    const float w = __ldg(w_out + c * D_MODEL + k);
-    dst[c * D_MODEL + k] = w * __ldg(g + k);
-    acc = fmaf(w, __ldg(be + k), acc);
+// proj_in (13 -> 128) + pre_norm as one MMA.  With h = W f + b (f = the 13 point features, of which f[9..12] is a one-hot
+// class p), LN(h)_n = rstd * ((W_n - wbar).f + (b_n - bbar)) * g_n + beta_n where wbar/bbar are the means over the 128
+// outputs, and var(h) is a quadratic form of f that every token evaluates on CUDA cores from 58 constants (IH_CONST):
+//   var = f9' Gt f9 + gp[p].f9 + cp[p]          (f9 = f[0..8]; Gt upper-triangular with doubled off-diagonals)
+// so the token scales its features by rstd itself and the MMA produces the normalised residual stream directly.
+// A row (K = 32 bf16), written by the token's thread:   k = 2i, 2i+1 : hi, lo of rstd*f_i (i < 9)
+//   k = 18+3c+{0,1,2} : (rhi, rlo, rhi) of rstd if c == p else 0          k = 30, 31 : 1, 1
+// B row n (this kernel):   k = 2i, 2i+1 : W''_ni = (W_ni - wbar_i) g_n      k = 18+3c+{0,1,2} : (chi, chi, clo) of
+//   W''_n,9+c + (b_n - bbar) g_n          k = 30, 31 : hi, lo of beta_n.
+// Also the folded head: w_out' = w_out.diag(post_norm.w) (bf16 tile), b_out' = b_out + w_out.post_norm.b (hi+lo slab).
+__global__ void __launch_bounds__(128)
+pack_inhead_kernel(uint8_t* __restrict__ dst, const float* __restrict__ w_in, const float* __restrict__ b_in,
+                   const float* __restrict__ pre_w, const float* __restrict__ pre_b, const float* __restrict__ w_out,
+                   const float* __restrict__ b_out, const float* __restrict__ post_w, const float* __restrict__ post_b) {
+  __shared__ float wc[D_MODEL][14];  // centred [W_n - wbar | b_n - bbar]
+  __shared__ float mean14[14];
+  __shared__ float G[14][14];
+  const int n = threadIdx.x;
+  for (int c = 0; c < 13; ++c) wc[n][c] = __ldg(w_in + n * 13 + c);
+  wc[n][13] = __ldg(b_in + n);
+  __syncthreads();
+  if (n < 14) {
+    float m = 0.f;
+    for (int k = 0; k < D_MODEL; ++k) m += wc[k][n];
+    mean14[n] = m * (1.f / D_MODEL);
   }
-  for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
-  if (threadIdx.x == 0) dst[3 * D_MODEL + c] = acc + __ldg(b_out + c);
+  __syncthreads();
+  for (int c = 0; c < 14; ++c) wc[n][c] -= mean14[c];
+  __syncthreads();
+  for (int e = n; e < 196; e += 128) {
+    const int i = e / 14, j = e - i * 14;
+    float a = 0.f;
+    for (int k = 0; k < D_MODEL; ++k) a = fmaf(wc[k][i], wc[k][j], a);
+    G[i][j] = a * (1.f / D_MODEL);
+  }
+  __syncthreads();
+  float* cst = reinterpret_cast<float*>(dst + IH_CONST);
+  if (n < 45) {  // upper triangle of the 9 x 9 feature block, row-major (i, j >= i)
+    int i = 0, e = n;
+    while (e >= 9 - i) { e -= 9 - i; ++i; }
+    const int j = i + e;
+    cst[IHC_GT + n] = G[i][j] * (i == j ? 1.f : 2.f);
+  } else if (n < 81) {
+    const int c = (n - 45) / 9, i = (n - 45) - c * 9;
+    cst[IHC_GP + c * 9 + i] = 2.f * (G[i][9 + c] + G[i][13]);
+  } else if (n < 85) {
+    const int c = n - 81;
+    cst[IHC_CP + c] = G[9 + c][9 + c] + 2.f * G[9 + c][13] + G[13][13];
+  }
+  // B tile row n
+  const float g = __ldg(pre_w + n), beta = __ldg(pre_b + n);
+  auto put = [&](int k, float v) { *reinterpret_cast<__nv_bfloat16*>(dst + IH_INTILE + tile_off(128, n, k)) = __float2bfloat16_rn(v); };
+  for (int i = 0; i < 9; ++i) { put(2 * i, wc[n][i] * g); put(2 * i + 1, wc[n][i] * g); }
+  for (int c = 0; c < 4; ++c) {
+    const float v = (wc[n][9 + c] + wc[n][13]) * g;
+    const float hi = __bfloat162float(__float2bfloat16_rn(v));
+    put(18 + 3 * c, hi); put(19 + 3 * c, hi); put(20 + 3 * c, v - hi);
+  }
+  {
+    const float hi = __bfloat162float(__float2bfloat16_rn(beta));
+    put(30, hi); put(31, beta - hi);
+  }
+  // head tile (16 rows) + slab
+  for (int r = 0; r < 16; ++r)
+    *reinterpret_cast<__nv_bfloat16*>(dst + IH_HEADTILE + tile_off(16, r, n)) =
+        __float2bfloat16_rn(r < 3 ? __ldg(w_out + r * D_MODEL + n) * __ldg(post_w + n) : 0.f);
+  if (n < 16) {
+    float v = 0.f;
+    if (n < 3) {
+      v = __ldg(b_out + n);
+      for (int k = 0; k < D_MODEL; ++k) v = fmaf(__ldg(w_out + n * D_MODEL + k), __ldg(post_b + k), v);
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dst + IH_HEADSLAB + n * 16);
+    o[0] = hi; o[1] = lo;
+    for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
+  }
 }
 // fold-kernel weights: WqG[n][k] = 0.25 Wq[n][k] g2[k];  bqG[n] = 0.25 sum_k Wq[n][k] b2[k];  WoT[k][c] = Wo[c][k]
 __global__ void pack_foldw_kernel(float* __restrict__ dst, const float* __restrict__ wq, const float* __restrict__ g2,
@@ -161,7 +235,9 @@ int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
                                                    P + o[B_N2_B], P + o[B_WO]);
     count_launch();
   }
-  pack_head_kernel<<<3, 32, 0, st>>>(extras, P + L.g[P_OUT_W], P + L.g[P_OUT_B], P + L.g[P_POST_W], P + L.g[P_POST_B]);
+  pack_inhead_kernel<<<1, 128, 0, st>>>(reinterpret_cast<uint8_t*>(extras), P + L.g[P_IN_W], P + L.g[P_IN_B], P + L.g[P_PRE_W], P + L.g[P_PRE_B],
+                                        P + L.g[P_OUT_W], P + L.g[P_OUT_B], P + L.g[P_POST_W], P + L.g[P_POST_B]);
+  count_launch();
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }
@@ -251,8 +327,9 @@ constexpr uint32_t SM_ONES = 65536;        // 4096  ones tile (128 x 16 bf16: k=
 constexpr uint32_t SM_RING = 69632;        // NSLOT x 18432
 constexpr uint32_t SM_BAR = SM_RING + NSLOT * SLOT_BYTES;  // mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t SM_WIN = SM_BAR + 512;  // 8192: proj_in weights transposed [13][128] | bias | pre_norm.w | pre_norm.b (fp32), staged once
-constexpr uint32_t TC_SMEM_BYTES = SM_WIN + 8192;
+constexpr uint32_t SM_INHEAD = SM_BAR + 512;  // the in/head image (INHEAD_BYTES), staged once per CTA
+constexpr uint32_t TC_SMEM_BYTES = SM_INHEAD + INHEAD_BYTES;
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
 
 enum Bar { BAR_A = 0 /*[2]*/, BAR_ACC = 2 /*[2]*/, BAR_UREADY = 4 /*[2]*/, BAR_X = 6 /*[2]*/, BAR_WFULL = 8 /*[NSLOT]*/,
            BAR_WEMPTY = 8 + NSLOT /*[NSLOT]*/, BAR_COUNT = 8 + 2 * NSLOT };
@@ -261,8 +338,7 @@ static_assert(BAR_COUNT * 8 <= 256, "barrier block");
 struct TcParams {
   const uint8_t* stream;  // static packets
   const uint8_t* fold;    // [B][depth] fold packets
-  const float* head;      // folded proj_out: [3][128] weights, then 3 biases
-  const float* w_in; const float* b_in; const float* pre_w; const float* pre_b;
+  const uint8_t* inhead;  // in/head image (see IH_*)
   const float* x; const float* anchors; const float* variances; const int* assign; const float* valid;
   float* eps_out;
   int N, depth, flags;
@@ -381,19 +457,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     uint4 v = make_uint4(tid < 128 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(smem + SM_ONES + tid * 16) = v;
   }
-  {
-    // proj_in weights staged transposed ([feature][output], fp32) so that one broadcast LDS.128 feeds two FFMA2 (4 outputs)
-    float* wt = reinterpret_cast<float*>(smem + SM_WIN);
-    for (int i = tid; i < D_MODEL * 13; i += TC_THREADS) {
-      const int k = i / 13, c = i - k * 13;  // coalesced read of w_in[k][c]
-      wt[c * D_MODEL + k] = __ldg(P.w_in + i);
-    }
-    if (tid < D_MODEL) {
-      wt[13 * D_MODEL + tid] = __ldg(P.b_in + tid);
-      wt[14 * D_MODEL + tid] = __ldg(P.pre_w + tid);
-      wt[15 * D_MODEL + tid] = __ldg(P.pre_b + tid);
-    }
-  }
+  for (int i = tid; i < (int)(INHEAD_BYTES / 16); i += TC_THREADS)
+    reinterpret_cast<uint4*>(smem + SM_INHEAD)[i] = __ldg(reinterpret_cast<const uint4*>(P.inhead) + i);
   fence_proxy_async();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -430,6 +495,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     for (int j = 0; j < MAX_TOKENS; ++j)
       if (P.valid == nullptr || __ldg(P.valid + b * MAX_TOKENS + j) != 0.f) vmask |= 1u << j;
     TL(0, 0);
+    const long long dbg_t0 = (P.dbg != nullptr && tl_on) ? clock64() : 0;
+    if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      P.dbg[220] = (long long)ns;
+    }
     if (P.done != nullptr) {
       // x of this unit at this timestep is produced by the item (unit, previous step), possibly on another SM
       if (r == 0) {
@@ -441,11 +512,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       }
       named_bar_sync(1 + T, 128);
     }
+    TL(0, 210);
+    if (P.dbg != nullptr && tl_on && blockIdx.x < 148) P.dbg[742 + blockIdx.x] += clock64() - dbg_t0;  // per-CTA dependency-wait cycles
 
-    // ---- proj_in (13 -> 128) + pre_norm, result (the residual stream) into TMEM ----
+    // ---- proj_in (13 -> 128) + pre_norm on the tensor core: analytic variance -> scaled K=32 A row -> one MMA into X ----
     {
-      const float* wt = reinterpret_cast<const float*>(smem + SM_WIN);
-      float f[13];
+      const float* cst = reinterpret_cast<const float*>(smem + SM_INHEAD + IH_CONST);
+      float f[9];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         f[c] = __ldcg(P.x + (b * 3 + c) * P.N + p);  // x is rewritten every step by other SMs: read through L2
@@ -454,48 +527,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         f[6 + c] = (P.flags & DFB200_NET_INCLUDE_STD) ? sqrtf(v) : v;
       }
       const int part = __ldg(P.assign + tok);
+      TL(0, 211);
+      float var = cst[IHC_CP + part];
+      {
+        int e = 0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) f[9 + c] = part == c ? 1.f : 0.f;
-      float2 s2 = f2s(0.f), q2 = f2s(0.f);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        float h[32];
+        for (int i = 0; i < 9; ++i) {
+          float t = cst[IHC_GP + part * 9 + i];
 #pragma unroll
-        for (int kq = 0; kq < 8; ++kq) {
-          const float4 bi = *reinterpret_cast<const float4*>(wt + 13 * D_MODEL + cb * 32 + kq * 4);
-          float2 a0 = f2(bi.x, bi.y), a1 = f2(bi.z, bi.w);
-#pragma unroll
-          for (int c = 0; c < 13; ++c) {
-            const float4 w = *reinterpret_cast<const float4*>(wt + c * D_MODEL + cb * 32 + kq * 4);
-            a0 = __ffma2_rn(f2s(f[c]), f2(w.x, w.y), a0);
-            a1 = __ffma2_rn(f2s(f[c]), f2(w.z, w.w), a1);
-          }
-          h[kq * 4] = a0.x; h[kq * 4 + 1] = a0.y; h[kq * 4 + 2] = a1.x; h[kq * 4 + 3] = a1.y;
-          s2 = __fadd2_rn(s2, __fadd2_rn(a0, a1));
-          q2 = __ffma2_rn(a0, a0, q2);
-          q2 = __ffma2_rn(a1, a1, q2);
+          for (int j = i; j < 9; ++j, ++e) t = fmaf(cst[IHC_GT + e], f[j], t);
+          var = fmaf(f[i], t, var);
         }
-        tmem_st32(X + cb * 32, h);
       }
-      tmem_wait_st();
-      const float mean = (s2.x + s2.y) * (1.f / D_MODEL);
-      const float rstd = rsqrtf(fmaxf((q2.x + q2.y) * (1.f / D_MODEL) - mean * mean, 0.f) + LN_EPS);
-      const float2 rs = f2s(rstd), nm = f2s(-mean * rstd);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        float h[32];
-        tmem_ld32(X + cb * 32, h);
-        tmem_wait_ld();
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + LN_EPS);
+      uint32_t w[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float2 g = *reinterpret_cast<const float2*>(wt + 14 * D_MODEL + cb * 32 + 2 * k);
-          const float2 be = *reinterpret_cast<const float2*>(wt + 15 * D_MODEL + cb * 32 + 2 * k);
-          const float2 y = __ffma2_rn(__ffma2_rn(f2(h[2 * k], h[2 * k + 1]), rs, nm), g, be);
-          h[2 * k] = y.x; h[2 * k + 1] = y.y;
-        }
-        tmem_st32(X + cb * 32, h);
+      for (int i = 0; i < 9; ++i) {
+        const float sv = rstd * f[i];
+        const float hi = __bfloat162float(__float2bfloat16_rn(sv));
+        w[i] = pack_bf16(hi, sv - hi);
       }
-      tmem_wait_st();
+      {
+        const float rhi = __bfloat162float(__float2bfloat16_rn(rstd));
+        const float rlo = rstd - rhi;
+        // entries k = 18 + 3c + m: (rhi, rlo, rhi) for c == part, else 0; two entries per word, word 9 starts at k = 18
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int k0 = 2 * q, k1 = 2 * q + 1;  // entry indices inside the 12-entry class block
+          const float e0 = (k0 / 3 == part) ? (k0 % 3 == 1 ? rlo : rhi) : 0.f;
+          const float e1 = (k1 / 3 == part) ? (k1 % 3 == 1 ? rlo : rhi) : 0.f;
+          w[9 + q] = pack_bf16(e0, e1);
+        }
+      }
+      w[15] = 0x3F803F80u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(a_tile + j * 2048 + r * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_A + T]);
+      TL(0, 212);
+      mbar_wait(&bars[BAR_X + T], ph_x);  // x = pre_norm(proj_in(features)) is in TMEM
+      ph_x ^= 1;
+      tc_fence_after();
     }
 
     TL(0, 1);
@@ -594,53 +668,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     }
 
     TL(0, 2 + P.depth * 40);
-    // ---- post_norm (folded) + proj_out (128 -> 3) ----
+    // ---- post_norm (folded) + proj_out (128 -> 3) on the tensor core (N = 16 MMA, 3 live columns) ----
     {
       float mean, rstd;
       row_stats(X, mean, rstd);
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-      for (int cb = 0; cb < 4; ++cb) {
-        float h[32];
-        tmem_ld32(X + cb * 32, h);
-        tmem_wait_ld();
+      TL(0, 204);
+      row_normalize_to_tile(X, mean, rstd, a_tile, r);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_A + T]);
+      ph_acc_oth ^= 1;  // the other tile's head phase of BAR_ACC (never waited for here; see the FF loop)
+      // While the head MMA runs: everything of the anchored DDPM update that does not depend on eps (operand loads, noise).
+      const bool upd = P.upd_sched != nullptr;
+      StepCoef cf{};
+      float xv[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f}, zq[3] = {0.f, 0.f, 0.f};
+      if (upd) {
+        cf = load_step_coef(P.upd_sched, P.upd_T, t_cur);
+        const float* znoise = P.upd_noise != nullptr ? P.upd_noise + (size_t)step_local * P.noise_step_elems : nullptr;
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.head + cb * 32) + k4);
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.head + D_MODEL + cb * 32) + k4);
-          const float4 w2 = __ldg(reinterpret_cast<const float4*>(P.head + 2 * D_MODEL + cb * 32) + k4);
-          const float y0 = (h[4 * k4] - mean) * rstd, y1 = (h[4 * k4 + 1] - mean) * rstd;
-          const float y2 = (h[4 * k4 + 2] - mean) * rstd, y3 = (h[4 * k4 + 3] - mean) * rstd;
-          o0 = fmaf(y3, w0.w, fmaf(y2, w0.z, fmaf(y1, w0.y, fmaf(y0, w0.x, o0))));
-          o1 = fmaf(y3, w1.w, fmaf(y2, w1.z, fmaf(y1, w1.y, fmaf(y0, w1.x, o1))));
-          o2 = fmaf(y3, w2.w, fmaf(y2, w2.z, fmaf(y1, w2.y, fmaf(y0, w2.x, o2))));
+        for (int c = 0; c < 3; ++c) {
+          const long long e = (b * 3 + c) * P.N + p;
+          xv[c] = __ldcg(P.x + e); av[c] = __ldg(P.anchors + e); vv[c] = __ldg(P.variances + e);
+          if (znoise != nullptr) zq[c] = __ldg(znoise + e);
+        }
+        if (znoise == nullptr) {
+          // Philox: the 4 lanes of a quad own 4 consecutive points, i.e. the 4 outputs of ONE Philox call per channel.
+          // Lane j of the quad (j < 3) draws channel j's float4; 4 shuffle rounds transpose it (round m: lane j reads lane
+          // (j+m)%4, which exposes component (src - m) % 4 = j).  One call per thread instead of three.
+          const int j = lane & 3;
+          float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < 3) z4 = philox_normal4((uint64_t)(((b * 3 + j) * P.N + (p & ~3)) >> 2), (uint64_t)t_cur, P.upd_seed);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int comp = (j - m) & 3;  // component this lane exposes in round m
+            const float mine = comp == 0 ? z4.x : comp == 1 ? z4.y : comp == 2 ? z4.z : z4.w;
+            const int src = (j + m) & 3;   // channel received in round m
+            const float got = __shfl_sync(0xFFFFFFFFu, mine, (lane & ~3) | src);
+            if (src == 0) zq[0] = got; else if (src == 1) zq[1] = got; else if (src == 2) zq[2] = got;
+          }
         }
       }
-      const float eps3[3] = {o0 + __ldg(P.head + 3 * D_MODEL + 0), o1 + __ldg(P.head + 3 * D_MODEL + 1),
-                             o2 + __ldg(P.head + 3 * D_MODEL + 2)};
+      mbar_wait(&bars[BAR_ACC + T], ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+      float ev[16];
+      tmem_ld16(ACC, ev);
+      tmem_wait_ld();
+      const float eps3[3] = {ev[0], ev[1], ev[2]};
+      TL(0, 205);
       if (tile_ok && P.eps_out != nullptr) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) P.eps_out[(b * 3 + c) * P.N + p] = eps3[c];
       }
-      if (P.upd_sched != nullptr) {
+      if (upd) {
         // anchored DDPM update fused into the epilogue (same arithmetic as dfb200_ddpm_step; every sample shares t)
-        const StepCoef cf = load_step_coef(P.upd_sched, P.upd_T, t_cur);
-        const float* znoise = P.upd_noise != nullptr ? P.upd_noise + (size_t)step_local * P.noise_step_elems : nullptr;
         const bool keep = P.traj != nullptr && t_cur > 0 && t_cur % P.traj_interval == 0;
         float* tr = keep ? P.traj + (size_t)(t_cur / P.traj_interval - 1) * (size_t)P.M * 3 : nullptr;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const long long e = (b * 3 + c) * P.N + p;
-          const float xv = __ldcg(P.x + e), av = __ldg(P.anchors + e), vv = __ldg(P.variances + e);
-          float z;
-          if (znoise != nullptr) {
-            z = __ldg(znoise + e);
-          } else {
-            const float4 z4 = philox_normal4((uint64_t)(e >> 2), (uint64_t)t_cur, P.upd_seed);
-            const int ln = (int)(e & 3);
-            z = ln == 0 ? z4.x : ln == 1 ? z4.y : ln == 2 ? z4.z : z4.w;
-          }
-          const float x0 = ddpm_xstart(cf, xv, av, vv, eps3[c]);
-          const float xp = ddpm_prev(cf, xv, av, vv, x0, z);
+          const float x0 = ddpm_xstart(cf, xv[c], av[c], vv[c], eps3[c]);
+          const float xp = ddpm_prev(cf, xv[c], av[c], vv[c], x0, zq[c]);
           if (tile_ok) {
             P.x_out[e] = xp;
             if (keep) tr[e] = xp;
@@ -648,11 +736,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         }
       }
     }
-    TL(0, 3 + P.depth * 40);
+    TL(0, 206);
     if (P.done != nullptr) {
-      __threadfence();                 // this thread's x_out stores are visible GPU-wide ...
-      named_bar_sync(1 + T, 128);      // ... for all 128 rows of the tile ...
-      if (r == 0) atomicAdd(P.done + unit, 1);  // ... before the tile-step is published
+      named_bar_sync(1 + T, 128);      // all 128 rows of the tile have stored x_{t-1} (CTA-scope order) ...
+      if (r == 0)                      // ... and ONE gpu-scope release publishes the tile-step (cumulative over the barrier)
+        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(P.done + unit), "r"(1) : "memory");
+    }
+    TL(0, 3 + P.depth * 40);
+    if (P.dbg != nullptr && tl_on && blockIdx.x < 148) P.dbg[230 + blockIdx.x] += clock64() - dbg_t0;  // per-CTA item cycles
+    if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      P.dbg[221] = (long long)ns;
     }
     }  // items
     tc_fence_before();
@@ -661,7 +756,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     // The whole warp runs this control flow (waits included); one elected lane issues tcgen05.mma / commit.
     // Everything that feeds a descriptor is warp-uniform by construction (constants, loop counters, the TMEM
     // base which is 0 for a 512-column allocation), so the issue sequence stays on the uniform datapath.
-    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc32 = make_idesc_bf16(128, 32);
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc32 = make_idesc_bf16(128, 32), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t ring = sbase + SM_RING, a_base = sbase + SM_A;
     const uint64_t ones_desc = make_smem_desc(sbase + SM_ONES, 2048, TILE_SBO);
@@ -689,7 +784,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     };
     int item_n = 0;
 #pragma unroll 1
-    for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++item_n)
+    for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++item_n) {
+    // ---- x_T = pre_norm(proj_in(features)): one K=32 GEMM against the resident in-tile ----
+#pragma unroll
+    for (int T = 0; T < 2; ++T) {
+      wait_a(T);
+      tc_fence_after();
+      if (elect_one()) {
+        umma_gemm<128, 2>(T * 128, a_base + T * 32768, sbase + SM_INHEAD + IH_INTILE, idesc128, 0u);
+        umma_commit(&bars[BAR_X + T]);
+      }
+      __syncwarp();
+    }
     for (int l = 0; l < P.depth; ++l) {
       const int G0 = (item_n * P.depth + l) * PKT_PER_LAYER;
       TL(1, 2 + l * 40);
@@ -777,6 +883,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         __syncwarp();
       }
     }
+    // ---- eps = proj_out(post_norm(x_T)): N=16 GEMM against the resident head tile -> ACC_T columns [0,16) ----
+#pragma unroll
+    for (int T = 0; T < 2; ++T) {
+      wait_a(T);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = 256 + T * 128;
+        umma_gemm<16, 8>(d, a_base + T * 32768, sbase + SM_INHEAD + IH_HEADTILE, idesc16, 0u);
+        umma_bf16(d, ones_desc, make_smem_desc(sbase + SM_INHEAD + IH_HEADSLAB, 0, TILE_SBO), idesc16, 1u);
+        umma_commit(&bars[BAR_ACC + T]);
+      }
+      __syncwarp();
+    }
+    }  // items
     tc_fence_before();
   } else {
     // =========================== weight producer ===========================
@@ -836,12 +956,10 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
     DFB_CUDA(cudaFuncSetAttribute(denoiser_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr_set = true;
   }
-  const float* Pf = reinterpret_cast<const float*>(packed);
   TcParams p{};
   p.stream = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
   p.fold = reinterpret_cast<const uint8_t*>(fold);
-  p.head = tc_extras(L, packed);
-  p.w_in = Pf + L.g[P_IN_W]; p.b_in = Pf + L.g[P_IN_B]; p.pre_w = Pf + L.g[P_PRE_W]; p.pre_b = Pf + L.g[P_PRE_B];
+  p.inhead = reinterpret_cast<const uint8_t*>(tc_extras(L, packed));
   p.x = x; p.anchors = anchors; p.variances = variances; p.assign = assign; p.valid = valid_id;
   p.eps_out = eps_out;
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
@@ -864,7 +982,8 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   }
   // persistent: one CTA per SM walks the (step, unit) work list; dependencies between steps of a unit go through P.done
   const long long items = (long long)p.n_units * p.n_steps;
-  const int grid = (int)(items < n_sm ? items : n_sm);
+  int grid = (int)(items < n_sm ? items : n_sm);
+  if (const char* g = getenv("DFB200_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // experiment knob
   denoiser_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;

@@ -27,6 +27,11 @@ E, M = b[:512], b[512:]
 t0 = E[0]
 rel = lambda v: v - t0 if v else None
 print("epilogue(tile0,row0): start 0, init done", rel(E[1]), " end", rel(E[3 + 5 * 40]), " (final head start", rel(E[2 + 5 * 40]), ")")
+if E[221] > E[220] > 0:
+    print(f"item wall time {E[221] - E[220]} ns -> SM clock {(E[3 + 5 * 40] - E[0]) / (E[221] - E[220]) * 1e3:.0f} MHz")
+print("init: dependency wait done", rel(E[210]), " inputs loaded", rel(E[211]), " proj_in done", rel(E[212]), " pre_norm done", rel(E[1]))
+hs = E[2 + 5 * 40]
+print("head (rel. to head start): post_norm stats", E[204] - hs, " proj_out", E[205] - hs, " update stored", E[206] - hs, " published", E[3 + 5 * 40] - hs)
 for l in range(5):
     o = l * 40
     print(f"layer {l}: start {rel(E[2+o])}  LN2+kv done {rel(E[3+o])}  Q ready {rel(E[4+o])}  attn done {rel(E[5+o])}  "
@@ -37,3 +42,11 @@ for l in range(5):
           f"LN3 tiles ready {rel(M[6+o])} first FF-in issued {rel(M[7+o])}")
     mm = [(rel(M[8 + o + 2 * c]), rel(M[9 + o + 2 * c])) for c in range(8)]
     print("   MMA FF units T0 (begin wait u_ready -> got it):", " ".join(f"{a}->{b_}" for a, b_ in mm))
+
+import statistics
+it = [v for v in b[230:378] if v]
+wt = b[742:890][:len(it)]
+if it:
+    print(f"per-CTA busy cycles over the launch (tile-0 thread 0): min {min(it)} median {statistics.median(it):.0f} max {max(it)}; "
+          f"dependency-wait cycles: min {min(wt)} median {statistics.median(wt):.0f} max {max(wt)}")
+    print("  slowest CTAs:", sorted(range(len(it)), key=lambda i: -it[i])[:8], " busy/wait of CTA 0:", it[0], wt[0])
