@@ -3,6 +3,7 @@
 // Reference behaviour reproduced:
 //   python/difffacto/metrics/chamfer_dist/chamfer.cu:15-145 (forward), :173-201 (grad)
 //   python/difffacto/metrics/emd/emd_cuda.cu:23-226 (8 kernels), :256-269 (host round loop), :284-300 (grad)
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -98,33 +99,108 @@ chamfer_grad_kernel(int n, int m, const float* __restrict__ xyz1, const float* _
 }
 
 // ============================================================================================
-// EMD (auction).  ONE persistent CTA per cloud pair runs every auction round: list unassigned ->
-// bid -> pick the highest bidder per target -> assign, separated by __syncthreads instead of the
-// reference's 7 kernel launches per round (70 000 launches at the evaluation setting
-// iters=10000), and leaves the loop as soon as no point is unassigned (later rounds are no-ops in
-// the reference too, so the result is unchanged).  price / max_increments / max_idx / the
-// unassigned list live in shared memory; the target cloud is streamed through an smem tile.
-// The reference is racy among equal bids (emd_cuda.cu:188-191); here ties go to the largest
-// point index, deterministically.  Parity with the reference is therefore tolerance-based.
+// EMD (auction).  ONE persistent thread-block CLUSTER per cloud pair runs every auction round: list unassigned ->
+// bid -> pick the highest bidder per target -> assign, separated by cluster barriers instead of the reference's 7
+// kernel launches per round (70 000 launches at the evaluation setting iters=10000), and leaves the loop as soon as
+// no point is unassigned (later rounds are no-ops in the reference too, so the result is unchanged).
+//   * The O(U.n) bid scan is split over the C CTAs of the cluster (C = 1..8, chosen so that batch x C fills the SMs):
+//     every CTA keeps a replica of price[] and its own staged target tile; per-target max increment / winner live in
+//     rank 0's shared memory and are updated with distributed-shared-memory atomics; the winner's price update is
+//     written to every replica.  assignment / bids live in global memory (cluster-scope visible across the barriers).
+//   * Once at most EMD_SOLO points are unassigned (the long latency-bound tail of the evaluation setting) the other
+//     ranks retire and rank 0 finishes alone with CTA-local barriers only.
+//   * Winner tags carry the round number, so max_idx never needs a reset pass.
+// The reference is racy among equal bids (emd_cuda.cu:188-191); here ties go to the largest point index,
+// deterministically.  Parity with the reference is therefore tolerance-based.
 // ============================================================================================
 constexpr int EMD_THREADS = 1024;
+constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr int EMD_TILE = 2048;
+constexpr int EMD_SOLO = 256;
+constexpr int EMD_PTS = 4;             // points a warp bids for per pass over the target tiles
+constexpr int EMD_TAG_ROUNDS = 32767;  // rounds per tag epoch (15-bit tag above a 16-bit point index)
+
+struct EmdBest {
+  float best[EMD_PTS], better[EMD_PTS];
+  int best_i[EMD_PTS];
+};
+
+// merge the 32 lanes' (best, better, best_i) of every point: lowest index wins equal bests; result in every lane
+__device__ __forceinline__ void emd_warp_merge(EmdBest& r) {
+#pragma unroll
+  for (int q = 0; q < EMD_PTS; ++q) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const float ob = __shfl_xor_sync(0xFFFFFFFFu, r.best[q], d);
+      const float ot = __shfl_xor_sync(0xFFFFFFFFu, r.better[q], d);
+      const int oi = __shfl_xor_sync(0xFFFFFFFFu, r.best_i[q], d);
+      const bool other_wins = ob > r.best[q] || (ob == r.best[q] && (unsigned)oi < (unsigned)r.best_i[q]);
+      const float lo = other_wins ? r.best[q] : ob;  // the losing best is a runner-up candidate
+      r.better[q] = fmaxf(fmaxf(r.better[q], ot), lo);
+      if (other_wins) { r.best[q] = ob; r.best_i[q] = oi; }
+    }
+  }
+}
+
+// Bid scan (Bid, emd_cuda.cu:95-179) of EMD_PTS points against every target, streamed through the CTA's staged tile.
+// Called by ALL threads of the CTA (the staging barriers are CTA-wide); a warp with active == false only helps staging.
+// This lane visits targets k_off, k_off + k_step, ... of every tile.
+__device__ __forceinline__ void emd_bid_scan(int n, const float* __restrict__ p2, const float* price, float4* tile, bool active,
+                                             const float (&x1)[EMD_PTS], const float (&y1)[EMD_PTS], const float (&z1)[EMD_PTS],
+                                             int k_off, int k_step, EmdBest& r) {
+#pragma unroll
+  for (int q = 0; q < EMD_PTS; ++q) { r.best[q] = -1e9f; r.better[q] = -1e9f; r.best_i[q] = -1; }
+  for (int k0 = 0; k0 < n; k0 += EMD_TILE) {
+    const int len = min(EMD_TILE, n - k0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < len; k += EMD_THREADS) {
+      const float* p = p2 + (size_t)(k0 + k) * 3;
+      tile[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), price[k0 + k]);
+    }
+    __syncthreads();
+    if (active) {
+      for (int k = k_off; k < len; k += k_step) {
+        const float4 t = tile[k];
+#pragma unroll
+        for (int q = 0; q < EMD_PTS; ++q) {
+          // reference: d = 3.0 - sqrtf(|p2-p1|^2) - price   (coordinates in [0,1])
+          const float d = (3.0f - __fsqrt_rn(sq3(t.x - x1[q], t.y - y1[q], t.z - z1[q]))) - t.w;
+          if (d > r.best[q]) {
+            r.better[q] = r.best[q]; r.best[q] = d; r.best_i[q] = k0 + k;
+          } else if (d > r.better[q]) {
+            r.better[q] = d;
+          }
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(EMD_THREADS, 1)
 emd_auction_kernel(int n, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                    float* __restrict__ dist, int* __restrict__ assignment, float* __restrict__ price_g,
                    int* __restrict__ assignment_inv, int* __restrict__ bid, float* __restrict__ bid_inc,
                    float* __restrict__ max_inc_g, int* __restrict__ unass_idx_g,
-                   int* __restrict__ unass_cnt_g, int* __restrict__ max_idx_g, float eps, int iters) {
+                   int* __restrict__ unass_cnt_g, int* __restrict__ rounds_g, int* __restrict__ solo_from_g, int* __restrict__ max_idx_g,
+                   float eps, int iters) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   extern __shared__ unsigned char emd_smem[];
-  float* price = reinterpret_cast<float*>(emd_smem);        // [n]
-  int* max_inc = reinterpret_cast<int*>(price + n);         // [n] float bits (all candidates > 0)
-  int* max_idx = max_inc + n;                               // [n]
-  int* list = max_idx + n;                                  // [n] unassigned points, ascending
+  float* price = reinterpret_cast<float*>(emd_smem);        // [n]  replica
+  int* max_inc_l = reinterpret_cast<int*>(price + n);       // [n] float bits (all candidates > 0); rank 0's copy is THE copy
+  int* max_idx_l = max_inc_l + n;                           // [n] (round tag << 16 | point); rank 0's copy is THE copy
+  int* list = max_idx_l + n;                                // [n] unassigned points, ascending (every CTA builds it)
   float4* tile = reinterpret_cast<float4*>(list + n);       // [EMD_TILE]
-  __shared__ int warp_cnt[EMD_THREADS / 32];
+  __shared__ int warp_cnt[EMD_WARPS];
+  __shared__ int slist[2][EMD_SOLO];  // tail phase: unassigned points, rebuilt incrementally every round
+  __shared__ int scount;
+  __shared__ float sm_best[EMD_WARPS][EMD_PTS], sm_better[EMD_WARPS][EMD_PTS];
+  __shared__ int sm_besti[EMD_WARPS][EMD_PTS];
+  int* max_inc = cluster.map_shared_rank(max_inc_l, 0);
+  int* max_idx = cluster.map_shared_rank(max_idx_l, 0);
 
-  const int i = blockIdx.x;
+  const int i = blockIdx.x / C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* p1 = xyz1 + (size_t)i * n * 3;
   const float* p2 = xyz2 + (size_t)i * n * 3;
@@ -134,19 +210,28 @@ emd_auction_kernel(int n, const float* __restrict__ xyz1, const float* __restric
   float* bdi = bid_inc + (size_t)i * n;
 
   for (int j = tid; j < n; j += EMD_THREADS) {  // emd_module.py:46-57 initial state
+    price[j] = 0.f;
+    max_inc_l[j] = 0;  // 0.0f
+    max_idx_l[j] = 0;
+  }
+  for (int j = rank * EMD_THREADS + tid; j < n; j += C * EMD_THREADS) {
     ass[j] = -1;
     ass_inv[j] = -1;
-    price[j] = 0.f;
-    max_inc[j] = 0;  // 0.0f
-    max_idx[j] = 0;
     bd[j] = 0;
     bdi[j] = 0.f;
   }
-  __syncthreads();
+  cluster.sync();
 
-  int U = n;
-  for (int it = 0; it < iters; ++it) {
+  int U = n, rounds = 0, solo_from = -1, it = 0;
+  bool to_tail = false;
+  // ================= phase 1: the whole cluster shares every round (many unassigned points) =================
+  for (; it < iters; ++it) {
     const bool last = it == iters - 1;
+    const int tag = (it % EMD_TAG_ROUNDS + 1) << 16;
+    if (it > 0 && it % EMD_TAG_ROUNDS == 0) {  // new tag epoch: old tags would outrank new ones
+      if (rank == 0) for (int j = tid; j < n; j += EMD_THREADS) max_idx_l[j] = 0;
+      cluster.sync();
+    }
     // ---- ordered list of unassigned points (calc_unass_cnt/_sum/_idx) ----
     int base = 0;
     for (int j0 = 0; j0 < n; j0 += EMD_THREADS) {
@@ -157,7 +242,7 @@ emd_auction_kernel(int n, const float* __restrict__ xyz1, const float* __restric
       __syncthreads();
       int off = 0, tot = 0;
       {
-        const int c = warp_cnt[lane];  // EMD_THREADS/32 == 32 warps
+        const int c = warp_cnt[lane];  // EMD_WARPS == 32
         int incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -173,115 +258,193 @@ emd_auction_kernel(int n, const float* __restrict__ xyz1, const float* __restric
     }
     U = base;
     if (U == 0) break;
+    if (U <= EMD_SOLO) { to_tail = true; break; }  // uniform over the cluster: every CTA built the same list
+    ++rounds;
 
-    // ---- bid: one warp per unassigned point scans all targets (Bid, emd_cuda.cu:95-179) ----
-    constexpr int PTS = 4;  // points a warp bids for per pass over the target tiles
-    // `passes` is CTA-uniform so the __syncthreads of the tile loop below are too
-    const int passes = (U + (EMD_THREADS / 32) * PTS - 1) / ((EMD_THREADS / 32) * PTS);
+    // ---- bid: one warp per EMD_PTS unassigned points, warps of all CTAs; `passes` is uniform over the cluster ----
+    const int warps_all = C * EMD_WARPS;
+    const int passes = (U + warps_all * EMD_PTS - 1) / (warps_all * EMD_PTS);
     for (int pass = 0; pass < passes; ++pass) {
-      const int u0 = (pass * (EMD_THREADS / 32) + warp) * PTS;
-      float x1[PTS], y1[PTS], z1[PTS], best[PTS], better[PTS];
-      int best_i[PTS];
+      const int u0 = (pass * warps_all + rank * EMD_WARPS + warp) * EMD_PTS;
+      float x1[EMD_PTS], y1[EMD_PTS], z1[EMD_PTS];
 #pragma unroll
-      for (int q = 0; q < PTS; ++q) {
-        const int u = u0 + q;
-        const int j = u < U ? list[u] : 0;
+      for (int q = 0; q < EMD_PTS; ++q) {
+        const int j = u0 + q < U ? list[u0 + q] : 0;
         x1[q] = __ldg(p1 + 3 * j); y1[q] = __ldg(p1 + 3 * j + 1); z1[q] = __ldg(p1 + 3 * j + 2);
-        best[q] = -1e9f; better[q] = -1e9f; best_i[q] = -1;
       }
-      for (int k0 = 0; k0 < n; k0 += EMD_TILE) {
-        const int len = min(EMD_TILE, n - k0);
-        __syncthreads();
-        for (int k = tid; k < len; k += EMD_THREADS) {
-          const float* p = p2 + (size_t)(k0 + k) * 3;
-          tile[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), price[k0 + k]);
-        }
-        __syncthreads();
-        if (u0 < U) {
-          for (int k = lane; k < len; k += 32) {
-            const float4 t = tile[k];
-#pragma unroll
-            for (int q = 0; q < PTS; ++q) {
-              // reference: d = 3.0 - sqrtf(|p2-p1|^2) - price   (coordinates in [0,1])
-              const float d = (3.0f - __fsqrt_rn(sq3(t.x - x1[q], t.y - y1[q], t.z - z1[q]))) - t.w;
-              if (d > best[q]) {
-                better[q] = best[q]; best[q] = d; best_i[q] = k0 + k;
-              } else if (d > better[q]) {
-                better[q] = d;
-              }
-            }
-          }
-        }
-      }
+      EmdBest r;
+      emd_bid_scan(n, p2, price, tile, u0 < U, x1, y1, z1, lane, 32, r);
       if (u0 < U) {
+        emd_warp_merge(r);
 #pragma unroll
-        for (int q = 0; q < PTS; ++q) {
-          // merge the 32 lanes' (best, better, best_i): lowest index wins equal bests
-#pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) {
-            const float ob = __shfl_xor_sync(0xFFFFFFFFu, best[q], d);
-            const float ot = __shfl_xor_sync(0xFFFFFFFFu, better[q], d);
-            const int oi = __shfl_xor_sync(0xFFFFFFFFu, best_i[q], d);
-            const bool other_wins = ob > best[q] || (ob == best[q] && (unsigned)oi < (unsigned)best_i[q]);
-            const float lo = other_wins ? best[q] : ob;  // the losing best is a runner-up candidate
-            better[q] = fmaxf(fmaxf(better[q], ot), lo);
-            if (other_wins) { best[q] = ob; best_i[q] = oi; }
-          }
-          const int u = u0 + q;
-          if (lane == 0 && u < U) {
-            const int j = list[u];
-            const float inc = best[q] - better[q] + eps;
-            bd[j] = best_i[q];
+        for (int q = 0; q < EMD_PTS; ++q) {
+          if (lane == 0 && u0 + q < U) {
+            const int j = list[u0 + q];
+            const float inc = r.best[q] - r.better[q] + eps;
+            bd[j] = r.best_i[q];
             bdi[j] = inc;
-            atomicMax(&max_inc[best_i[q]], __float_as_int(inc));  // inc > 0: int order == float order
+            atomicMax(&max_inc[r.best_i[q]], __float_as_int(inc));  // inc > 0: int order == float order
           }
         }
       }
     }
-    __syncthreads();
+    cluster.sync();
 
     // ---- highest bidder per target (GetMax :181-194); ties -> largest j, deterministically ----
-    for (int u = tid; u < U; u += EMD_THREADS) {
+    for (int u = rank * EMD_THREADS + tid; u < U; u += C * EMD_THREADS) {
       const int j = list[u];
       const int bid_id = bd[j];
       const double bi = (double)bdi[j];
       const double mi = (double)__int_as_float(max_inc[bid_id]);
-      if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMax(&max_idx[bid_id], j | 0x40000000);
+      if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMax(&max_idx[bid_id], tag | j);
     }
-    __syncthreads();
+    cluster.sync();
 
     // ---- assign (Assign :196-215) ----
-    for (int u = tid; u < U; u += EMD_THREADS) {
+    for (int u = rank * EMD_THREADS + tid; u < U; u += C * EMD_THREADS) {
       const int j = list[u];
       const int bid_id = bd[j];
-      if (last || max_idx[bid_id] == (j | 0x40000000)) {
+      if (last || max_idx[bid_id] == (tag | j)) {
         const int prev = ass_inv[bid_id];
         if (!last && prev != -1) ass[prev] = -1;
         ass_inv[bid_id] = j;
         ass[j] = bid_id;
-        price[bid_id] += bdi[j];
+        const float inc = bdi[j];
+        for (int rr = 0; rr < C; ++rr) {  // one winner per target and round: plain read-modify-write on every replica
+          float* pr = cluster.map_shared_rank(price, rr);
+          pr[bid_id] += inc;
+        }
         max_inc[bid_id] = __float_as_int(-1e9f);
       }
     }
-    __syncthreads();
-    // winners' tags must not survive into the next round's atomicMax
-    for (int u = tid; u < U; u += EMD_THREADS) max_idx[bd[list[u]]] = 0;
-    __syncthreads();
+    cluster.sync();
   }
 
+  // ================= phase 2: the tail (<= EMD_SOLO unassigned; U never grows) - rank 0 alone, CTA-local barriers =================
+  // Thousands of rounds with a handful of bidders each at the evaluation setting: what matters is the latency of a
+  // round.  All 32 warps share the target scan of the few point groups (W warps per group, merged through shared
+  // memory), and the unassigned list is maintained incrementally (winner out, evicted previous owner in) - its order
+  // does not influence bids or winners - instead of being recomputed from the n assignments.
+  if (to_tail && rank == 0) {
+    solo_from = it;
+    for (int u = tid; u < U; u += EMD_THREADS) slist[0][u] = list[u];
+    int cur = 0;
+    __syncthreads();
+    for (; it < iters && U > 0; ++it) {
+      const bool last = it == iters - 1;
+      const int tag = (it % EMD_TAG_ROUNDS + 1) << 16;
+      if (it > 0 && it % EMD_TAG_ROUNDS == 0) {
+        for (int j = tid; j < n; j += EMD_THREADS) max_idx_l[j] = 0;
+        __syncthreads();
+      }
+      ++rounds;
+      const int* L = slist[cur];
+      int* Lnext = slist[cur ^ 1];
+      const int G = (U + EMD_PTS - 1) / EMD_PTS;  // point groups (<= 64)
+      int W = 1;                                  // warps sharing one group's scan
+      while (W * 2 * G <= EMD_WARPS) W *= 2;
+      const int passes = (G * W + EMD_WARPS - 1) / EMD_WARPS;  // 1 unless G > 32
+      for (int pass = 0; pass < passes; ++pass) {
+        const int g = (pass * EMD_WARPS + warp) / W, slice = warp % W;
+        const bool active = g < G;
+        const int u0 = g * EMD_PTS;
+        float x1[EMD_PTS], y1[EMD_PTS], z1[EMD_PTS];
+#pragma unroll
+        for (int q = 0; q < EMD_PTS; ++q) {
+          const int j = (active && u0 + q < U) ? L[u0 + q] : 0;
+          x1[q] = __ldg(p1 + 3 * j); y1[q] = __ldg(p1 + 3 * j + 1); z1[q] = __ldg(p1 + 3 * j + 2);
+        }
+        EmdBest r;
+        emd_bid_scan(n, p2, price, tile, active, x1, y1, z1, slice * 32 + lane, W * 32, r);
+        emd_warp_merge(r);
+        if (W > 1) {  // merge the W warps of a group through shared memory (W is CTA-uniform)
+          if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < EMD_PTS; ++q) { sm_best[warp][q] = r.best[q]; sm_better[warp][q] = r.better[q]; sm_besti[warp][q] = r.best_i[q]; }
+          }
+          __syncthreads();
+          if (active && slice == 0) {
+#pragma unroll
+            for (int q = 0; q < EMD_PTS; ++q) {
+              const bool in = lane < W;
+              r.best[q] = in ? sm_best[warp + lane][q] : -1e9f;
+              r.better[q] = in ? sm_better[warp + lane][q] : -1e9f;
+              r.best_i[q] = in ? sm_besti[warp + lane][q] : -1;
+            }
+            emd_warp_merge(r);
+          }
+        }
+        if (active && slice == 0 && lane == 0) {
+#pragma unroll
+          for (int q = 0; q < EMD_PTS; ++q) {
+            if (u0 + q < U) {
+              const int j = L[u0 + q];
+              const float inc = r.best[q] - r.better[q] + eps;
+              bd[j] = r.best_i[q];
+              bdi[j] = inc;
+              atomicMax(&max_inc_l[r.best_i[q]], __float_as_int(inc));
+            }
+          }
+        }
+      }
+      if (tid == 0) scount = 0;
+      __syncthreads();
+      if (tid < U) {  // U <= EMD_SOLO <= EMD_THREADS
+        const int j = L[tid];
+        const int bid_id = bd[j];
+        const double bi = (double)bdi[j];
+        const double mi = (double)__int_as_float(max_inc_l[bid_id]);
+        if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMax(&max_idx_l[bid_id], tag | j);
+      }
+      __syncthreads();
+      if (tid < U) {
+        const int j = L[tid];
+        const int bid_id = bd[j];
+        if (last || max_idx_l[bid_id] == (tag | j)) {
+          const int prev = ass_inv[bid_id];
+          if (!last && prev != -1) {
+            ass[prev] = -1;
+            Lnext[atomicAdd(&scount, 1)] = prev;  // the evicted owner bids next round
+          }
+          ass_inv[bid_id] = j;
+          ass[j] = bid_id;
+          price[bid_id] += bdi[j];
+          max_inc_l[bid_id] = __float_as_int(-1e9f);
+        } else {
+          Lnext[atomicAdd(&scount, 1)] = j;  // outbid: still unassigned
+        }
+      }
+      __syncthreads();
+      U = scount;
+      cur ^= 1;
+      __syncthreads();  // everybody has read scount before thread 0 clears it next round
+    }
+    for (int u = tid; u < U; u += EMD_THREADS) list[u] = slist[cur][u];  // reported back through unass_idx
+    __syncthreads();
+  }
+  if (C > 1) cluster.sync();  // retired ranks wait here for rank 0; global state is visible to everybody afterwards
+
   // ---- CalcDist (:217-226) + write the scratch state back for callers that inspect it ----
-  for (int j = tid; j < n; j += EMD_THREADS) {
+  for (int j = rank * EMD_THREADS + tid; j < n; j += C * EMD_THREADS) {
     const int k = ass[j];
     const float dx = __ldg(p1 + 3 * j) - __ldg(p2 + 3 * k);
     const float dy = __ldg(p1 + 3 * j + 1) - __ldg(p2 + 3 * k + 1);
     const float dz = __ldg(p1 + 3 * j + 2) - __ldg(p2 + 3 * k + 2);
     dist[(size_t)i * n + j] = sq3(dx, dy, dz);
-    price_g[(size_t)i * n + j] = price[j];
-    max_inc_g[(size_t)i * n + j] = __int_as_float(max_inc[j]);
-    max_idx_g[(size_t)i * n + j] = max_idx[j] & 0x3FFFFFFF;
-    unass_idx_g[(size_t)i * n + j] = j < U ? list[j] : 0;
   }
-  if (tid == 0) unass_cnt_g[i] = U;
+  if (rank == 0) {
+    for (int j = tid; j < n; j += EMD_THREADS) {
+      price_g[(size_t)i * n + j] = price[j];
+      max_inc_g[(size_t)i * n + j] = __int_as_float(max_inc_l[j]);
+      max_idx_g[(size_t)i * n + j] = max_idx_l[j] & 0xFFFF;
+      unass_idx_g[(size_t)i * n + j] = j < U ? list[j] : 0;
+    }
+    if (tid == 0) {
+      unass_cnt_g[i] = U;
+      if (rounds_g != nullptr) rounds_g[i] = rounds;        // diagnostics in the reference's otherwise unused scratch (unass_cnt_sum / cnt_tmp):
+      if (solo_from_g != nullptr) solo_from_g[i] = solo_from;  // auction rounds executed, and the round from which rank 0 ran alone (-1: never)
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -352,19 +515,34 @@ extern "C" int dfb200_emd_forward(int b, int n, const float* xyz1, const float* 
                                   float* bid_increments, float* max_increments, int* unass_idx,
                                   int* unass_cnt, int* unass_cnt_sum, int* cnt_tmp, int* max_idx,
                                   float eps, int iters, dfb200_stream_t stream) {
-  (void)unass_cnt_sum; (void)cnt_tmp;  // reference scratch the persistent kernel does not need
   // Same input contract as the reference (emd_cuda.cu:236-249), reported as a status.
   DFB_REQUIRE(b >= 0 && n >= 0, DFB200_ERR_INVALID_ARG, "emd_forward: negative size");
   DFB_REQUIRE(b <= 512, DFB200_ERR_INVALID_ARG, "emd_forward: the batch size should be less than 512");
   DFB_REQUIRE(n % 1024 == 0, DFB200_ERR_INVALID_ARG, "emd_forward: the size of the point clouds should be a multiple of 1024");
   DFB_REQUIRE(iters >= 1, DFB200_ERR_INVALID_ARG, "emd_forward: iters must be >= 1");
   if (b == 0 || n == 0) return DFB200_OK;
+  DFB_REQUIRE(n <= 65535, DFB200_ERR_UNSUPPORTED, "emd_forward: n=%d exceeds 65535", n);
   const size_t smem = sizeof(float) * 4 * (size_t)n + sizeof(float4) * EMD_TILE;
   DFB_REQUIRE(smem <= 200 * 1024, DFB200_ERR_UNSUPPORTED, "emd_forward: n=%d exceeds the shared-memory resident limit (10240)", n);
   DFB_CUDA(cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  emd_auction_kernel<<<b, EMD_THREADS, smem, as_stream(stream)>>>(n, xyz1, xyz2, dist, assignment, price, assignment_inv, bid,
-                                                                  bid_increments, max_increments, unass_idx, unass_cnt, max_idx, eps, iters);
-  DFB_LAUNCH_CHECK();
+  // cluster size: as many CTAs per cloud pair as keeps batch x C within one wave of the SMs (1 CTA per SM), at most 8
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    DFB_CUDA(cudaGetDevice(&dev));
+    DFB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int C = 1;
+  while (C < 8 && b * C * 2 <= n_sm && n / (C * 2) >= EMD_SOLO) C *= 2;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(b * C); cfg.blockDim = dim3(EMD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  DFB_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel, n, xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments,
+                              max_increments, unass_idx, unass_cnt, unass_cnt_sum, cnt_tmp, max_idx, eps, iters));
+  count_launch();
   return DFB200_OK;
 }
 

@@ -34,11 +34,14 @@ class emdFunction(Function):
         unass_idx = torch.empty(batchsize * n, **i32)
         max_idx = torch.empty(batchsize * m, **i32)
         unass_cnt = torch.zeros(512, **i32)
+        rounds = torch.zeros(512, **i32)      # diagnostics: auction rounds executed per pair ...
+        solo_from = torch.zeros(512, **i32)   # ... and the round from which one CTA finished alone
         with torch.cuda.device(dev):
             check(_lib.load().dfb200_emd_forward(batchsize, n, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(assignment), ptr(price),
                                                  ptr(assignment_inv), ptr(bid), ptr(bid_increments), ptr(max_increments),
-                                                 ptr(unass_idx), ptr(unass_cnt), None, None, ptr(max_idx), float(eps),
+                                                 ptr(unass_idx), ptr(unass_cnt), ptr(rounds), ptr(solo_from), ptr(max_idx), float(eps),
                                                  int(iters), stream()))
+        emdFunction.last_stats = (rounds[:batchsize], solo_from[:batchsize], unass_cnt[:batchsize])
         ctx.save_for_backward(xyz1, xyz2, assignment)
         return dist, assignment
 
