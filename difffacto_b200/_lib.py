@@ -50,6 +50,8 @@ SIGNATURES = {
     "dfb200_denoiser_forward": (c_int, [_CFG, P, c_int, c_int, c_int] + [P] * 8 + [P, c_size_t, P]),
     "dfb200_ddpm_step": (c_int, [c_int] * 3 + [P] * 10),
     "dfb200_q_sample": (c_int, [c_int] * 3 + [P] * 8),
+    "dfb200_ddim_step": (c_int, [c_int] * 3 + [P] * 9 + [c_float, P, P, P]),
+    "dfb200_guidance_mix": (c_int, [c_size_t, c_float, P, P, P, P]),
     "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),
     "dfb200_bench_umma": (c_int, [c_int, c_int, c_int, c_int, P, P]),
     "dfb200_bench_umma2": (c_int, [c_int, c_int, c_int, c_int, P, P]),

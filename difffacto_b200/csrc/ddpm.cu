@@ -109,6 +109,40 @@ philox_normal_kernel(float* __restrict__ out, size_t count, uint64_t seed, uint6
   }
 }
 
+// DDIM variant of the reverse step (anchored_diffusion.py:368-374 xt_dir, :480-481 sample), evaluated in the reference's
+// op order:  sample = (((x0 - a) * sqrt(acp_t) + a) + (L * dir_t) * eps) + ((eta * nonzero) * sqrt(pv_t * var)) * z
+// acp = float32(alphas_cumprod_prev), dir = float32(sqrt(1 - ac - eta^2 * posterior_variance)), both indexed by the
+// FULL-schedule timestep t (the reference does not re-derive them for the strided DDIM step list).
+__global__ void __launch_bounds__(256)
+ddim_step_kernel(long long total, int per_sample, int T, const float* __restrict__ sched, const int* __restrict__ t,
+                 const float* __restrict__ x_t, const float* __restrict__ eps, const float* __restrict__ anchors,
+                 const float* __restrict__ variance, const float* __restrict__ noise, const float* __restrict__ acp,
+                 const float* __restrict__ dir_coeff, float eta, float* __restrict__ x_prev, float* __restrict__ pred_xstart) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int b = (int)(q / per_sample);
+  const int tt = __ldg(t + b);
+  const StepCoef c = load_step_coef(sched, T, tt);
+  const float x = __ldg(x_t + q), a = __ldg(anchors + q), v = __ldg(variance + q), e = __ldg(eps + q);
+  const float x0 = ddpm_xstart(c, x, a, v, e);
+  const float L = __fsqrt_rn(v);
+  const float lhs = __fadd_rn(__fmul_rn(__fsub_rn(x0, a), __fsqrt_rn(__ldg(acp + tt))), a);
+  const float xt_dir = __fmul_rn(__fmul_rn(L, __ldg(dir_coeff + tt)), e);
+  const float sd = __fsqrt_rn(__fmul_rn(c.post_var, v));
+  const float nz = __fmul_rn(__fmul_rn(__fmul_rn(eta, c.nonzero), sd), noise != nullptr ? __ldg(noise + q) : 0.f);
+  x_prev[q] = __fadd_rn(__fadd_rn(lhs, xt_dir), nz);
+  if (pred_xstart != nullptr) pred_xstart[q] = x0;
+}
+
+// classifier-free guidance mix (anchored_diffusion.py:263-266): out = (1 - w) * uncond + w * cond
+__global__ void __launch_bounds__(256)
+guidance_mix_kernel(long long total, float one_minus_w, float w, const float* __restrict__ uncond, const float* __restrict__ cond,
+                    float* __restrict__ out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  out[q] = __fadd_rn(__fmul_rn(one_minus_w, __ldg(uncond + q)), __fmul_rn(w, __ldg(cond + q)));
+}
+
 int launch_ddpm_step(int B, int N, int T, const float* sched, const int* t, const float* x_t,
                      const float* eps, const float* anchors, const float* variance, const float* noise,
                      bool philox, uint64_t seed, uint64_t offset, float* x_prev, float* pred_xstart,
@@ -170,6 +204,28 @@ extern "C" int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uin
                                     dfb200_stream_t stream) {
   if (count == 0) return DFB200_OK;
   philox_normal_kernel<<<cdiv((long long)((count + 3) / 4), 256), 256, 0, as_stream(stream)>>>(out, count, seed, offset);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_ddim_step(int B, int N, int T, const float* sched, const int* t, const float* x_t, const float* eps,
+                                const float* anchors, const float* variance, const float* noise,
+                                const float* alphas_cumprod_prev, const float* xt_dir_coeff, float eta, float* x_prev,
+                                float* pred_xstart, dfb200_stream_t stream) {
+  DFB_REQUIRE(B >= 0 && N >= 0 && T > 0, DFB200_ERR_INVALID_ARG, "ddim_step: bad sizes B=%d N=%d T=%d", B, N, T);
+  const long long total = (long long)B * 3 * N;
+  if (total == 0) return DFB200_OK;
+  ddim_step_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(total, 3 * N, T, sched, t, x_t, eps, anchors, variance, noise,
+                                                                    alphas_cumprod_prev, xt_dir_coeff, eta, x_prev, pred_xstart);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_guidance_mix(size_t count, float classifier_weight, const float* eps_uncond, const float* eps_cond,
+                                   float* eps_out, dfb200_stream_t stream) {
+  if (count == 0) return DFB200_OK;
+  guidance_mix_kernel<<<cdiv((long long)count, 256), 256, 0, as_stream(stream)>>>((long long)count, 1.f - classifier_weight,
+                                                                                  classifier_weight, eps_uncond, eps_cond, eps_out);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

@@ -197,6 +197,17 @@ int dfb200_ddpm_step(int B, int N, int T, const float* sched, const int* t, cons
                      const float* eps, const float* anchors, const float* variance,
                      const float* noise, float* x_prev, float* pred_xstart,
                      dfb200_stream_t stream);
+/* DDIM variant of the reverse step (ddim_sampling=True; anchored_diffusion.py:114-126, :368-374, :480-481):
+ *   x_prev = (x0 - a)*sqrt(alphas_cumprod_prev[t]) + a + sqrt(var)*xt_dir_coeff[t]*eps + eta*[t!=0]*sqrt(post_var[t]*var)*noise
+ * alphas_cumprod_prev / xt_dir_coeff: device float32[T] tables (float32 of the reference's float64 numpy tables);
+ * noise may be NULL (treated as 0).  pred_xstart optional. */
+int dfb200_ddim_step(int B, int N, int T, const float* sched, const int* t, const float* x_t, const float* eps,
+                     const float* anchors, const float* variance, const float* noise,
+                     const float* alphas_cumprod_prev, const float* xt_dir_coeff, float eta, float* x_prev,
+                     float* pred_xstart, dfb200_stream_t stream);
+/* Classifier-free guidance mix, eps_out = (1 - w) * eps_uncond + w * eps_cond (anchored_diffusion.py:263-266). */
+int dfb200_guidance_mix(size_t count, float classifier_weight, const float* eps_uncond, const float* eps_cond,
+                        float* eps_out, dfb200_stream_t stream);
 /* x_t = sqrt_ac[t]*(x0-a)+a + sqrt_1mac[t]*sqrt(var)*noise.  Replaces q_sample, :148-173. */
 int dfb200_q_sample(int B, int N, int T, const float* sched, const int* t, const float* x_start,
                     const float* anchors, const float* variance, const float* noise, float* x_t,

@@ -225,9 +225,38 @@ def ddpm_step(s, x, t, eps, anchors, variance, noise):
     return sample, pred_xstart
 
 
+def ddim_steps(T, nsteps=10, discretize="uniform"):  # anchored_diffusion.py:117-126
+    if discretize == "uniform":
+        return list(range(0, T, T // nsteps))
+    return ((np.linspace(0., math.sqrt(T * 0.8), nsteps) ** 2).astype(np.int32)).tolist()
+
+
+def ddim_step(s, x, t, eps, anchors, variance, noise, eta):
+    """DDIM variant: anchored_diffusion.py:114-116 (xt_dir_coeff), :368-374 (xt_dir), :480-481 (sample)."""
+    betas = s["betas"]
+    ac = np.cumprod(1.0 - betas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    xt_dir_coeff = np.sqrt(1. - ac - eta * eta * s["posterior_variance"])
+    L = torch.sqrt(variance)
+    model_variance = _extract(s["posterior_variance"], t, x.shape) * variance
+    pred_xstart = (_extract(s["sqrt_recip_alphas_cumprod"], t, x.shape) * (x - anchors) + anchors
+                   - _extract(s["sqrt_recipm1_alphas_cumprod"], t, x.shape) * L * eps)
+    xt_dir = L * _extract(xt_dir_coeff, t, x.shape) * eps
+    nonzero_mask = (t != 0).float().view(-1, 1, 1)
+    sample = ((pred_xstart - anchors) * torch.sqrt(_extract(ac_prev, t, x.shape)) + anchors + xt_dir
+              + eta * nonzero_mask * torch.sqrt(model_variance) * noise)
+    return sample, pred_xstart
+
+
 @torch.no_grad()
-def p_sample(sd, s, x, t, ctx_list, anchors, variance, assign, valid, noise, depth=5):
+def p_sample(sd, s, x, t, ctx_list, anchors, variance, assign, valid, noise, depth=5, guidance_weight=None, ddim_eta=None):
+    """anchored_diffusion.py:450-484; guidance_weight: classifier-free guidance (:263-266); ddim_eta: DDIM step."""
     eps = denoiser_forward(sd, x, t, ctx_list, anchors, variance, valid, assign, depth=depth)
+    if guidance_weight is not None:
+        unc = denoiser_forward(sd, x, t, [torch.zeros_like(r) for r in ctx_list], anchors, variance, valid, assign, depth=depth)
+        eps = (1. - guidance_weight) * unc + guidance_weight * eps
+    if ddim_eta is not None:
+        return ddim_step(s, x, t, eps, anchors, variance, noise, ddim_eta) + (eps,)
     return ddpm_step(s, x, t, eps, anchors, variance, noise) + (eps,)
 
 

@@ -33,3 +33,10 @@ def ref_ext():
             spec.loader.exec_module(mod)
             out[name] = mod
     return out
+
+
+@pytest.fixture(scope="session")
+def variants_golden():
+    """DDIM / guidance outputs of the real reference (tests/golden/make_golden.py)."""
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "variants_golden.npz"))

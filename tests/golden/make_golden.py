@@ -129,6 +129,39 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in out.items()})
 
+    # ---- sampling variants of the same class: DDIM steps and classifier-free guidance (variants_golden.npz) ----
+    var = {}
+    inp = R.synthetic_inputs(12, 2, 128, True)
+    ctx = [inp["code"], inp["params"]]
+    for name, kw in {"ddim_eta1": dict(ddim_sampling=True, ddim_nsteps=10, ddim_eta=1.0, ddim_discretize="uniform"),
+                     "ddim_eta05_quad": dict(ddim_sampling=True, ddim_nsteps=8, ddim_eta=0.5, ddim_discretize="quad"),
+                     "guidance_w2": dict(guidance=True, classifier_weight=2.0)}.items():
+        cfg = gen_chair_diffusion_cfg()
+        cfg.update(kw)
+        d = build_from_cfg(cfg, DIFFUSIONS, num_timesteps=T).eval()
+        d.model.load_state_dict(sd, strict=True)
+        var[f"{name}_steps"] = np.array(d.steps)
+        with torch.no_grad(), FixedNoise([inp["noise"]]):
+            ps = d.p_sample(inp["x"], inp["t"], inp["anchors"], ctx=ctx, variance=inp["variance"],
+                            anchor_assignment=inp["assign"], valid_id=inp["valid"])
+        var[f"{name}_sample"] = ps["sample"].numpy()
+        var[f"{name}_pred_xstart"] = ps["pred_xstart"].numpy()
+    # a full DDIM loop (10 of 100 steps), noise supplied
+    cfg = gen_chair_diffusion_cfg()
+    cfg.update(ddim_sampling=True, ddim_nsteps=10, ddim_eta=1.0, ddim_discretize="uniform")
+    d = build_from_cfg(cfg, DIFFUSIONS, num_timesteps=T).eval()
+    d.model.load_state_dict(sd, strict=True)
+    rng = np.random.default_rng(77)
+    noises = [torch.from_numpy(rng.standard_normal((2, 3, 128)).astype(np.float32)) for _ in range(len(d.steps) + 1)]
+    with FixedNoise(list(noises)), contextlib.redirect_stdout(io.StringIO()):
+        x0 = d.p_sample_loop([2, 3, 128], inp["anchors"], ctx=ctx, variance=inp["variance"], anchor_assignment=inp["assign"],
+                             valid_id=inp["valid"], device="cpu")
+    var["ddim_loop_noises"] = np.stack([n.numpy() for n in noises])
+    var["ddim_loop_x0"] = x0.numpy()
+    path = os.path.join(HERE, "variants_golden.npz")
+    np.savez_compressed(path, **var)
+    print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in var.items()})
+
 
 if __name__ == "__main__":
     main()

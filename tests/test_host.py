@@ -101,9 +101,12 @@ def test_module_contract_against_golden(golden):
 def test_unsupported_settings_fail_loudly():
     c = Config(os.path.join(ROOT, "configs", "gen_chair.py"))
     bad = c.model.diffusion.dump()
-    bad["ddim_sampling"] = True
-    with pytest.raises(NotImplementedError, match="ddim_sampling"):
+    bad["include_anchors"] = True
+    with pytest.raises(NotImplementedError, match="include_anchors"):
         D.build_from_cfg(bad, D.DIFFUSIONS, num_timesteps=10)
+    ddim = c.model.diffusion.dump()
+    ddim.update(ddim_sampling=True, ddim_nsteps=5, ddim_discretize="uniform")
+    assert D.build_from_cfg(ddim, D.DIFFUSIONS, num_timesteps=100).steps == [0, 20, 40, 60, 80]  # reference :117-119
     net = c.model.diffusion.net.dump()
     net["context_proj"] = True
     with pytest.raises(NotImplementedError, match="context_proj"):

@@ -153,3 +153,39 @@ def test_emd_is_a_permutation_and_close_to_optimal():
     opt = cost[r, c].mean()
     got = np.sqrt(dist[0]).mean()
     assert opt <= got <= opt * 1.05 + 0.002
+
+
+VARIANTS = {"ddim_eta1": dict(ddim_eta=1.0), "ddim_eta05_quad": dict(ddim_eta=0.5), "guidance_w2": dict(guidance_weight=2.0)}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_ddim_and_guidance_port_matches_reference(variants_golden, name):
+    """DDIM step / classifier-free guidance of the oracle port against the real reference's p_sample."""
+    g = variants_golden
+    sd = R.synthetic_state_dict(1234)
+    inp = R.synthetic_inputs(12, 2, 128, True)
+    s = R.schedule(100)
+    smp, x0, _ = R.p_sample(sd, s, inp["x"], inp["t"], [inp["code"], inp["params"]], inp["anchors"], inp["variance"], inp["assign"],
+                            inp["valid"], inp["noise"], **VARIANTS[name])
+    assert np.abs(smp.numpy() - g[name + "_sample"]).max() < 2e-5
+    assert np.abs(x0.numpy() - g[name + "_pred_xstart"]).max() < 2e-5
+
+
+def test_ddim_step_lists_match_reference(variants_golden):
+    assert R.ddim_steps(100, 10, "uniform") == list(variants_golden["ddim_eta1_steps"])
+    assert R.ddim_steps(100, 8, "quad") == list(variants_golden["ddim_eta05_quad_steps"])
+    assert list(variants_golden["guidance_w2_steps"]) == list(range(100))
+
+
+def test_ddim_loop_port_matches_reference(variants_golden):
+    g = variants_golden
+    sd = R.synthetic_state_dict(1234)
+    inp = R.synthetic_inputs(12, 2, 128, True)
+    s = R.schedule(100)
+    noises = [torch.from_numpy(n) for n in g["ddim_loop_noises"]]
+    x = torch.sqrt(inp["variance"]) * noises[0] + inp["anchors"]
+    for k, i in enumerate(R.ddim_steps(100, 10)[::-1]):
+        t = torch.tensor([i] * 2)
+        x, _, _ = R.p_sample(sd, s, x, t, [inp["code"], inp["params"]], inp["anchors"], inp["variance"], inp["assign"], inp["valid"],
+                             noises[k + 1], ddim_eta=1.0)
+    assert np.abs(x.numpy() - g["ddim_loop_x0"]).max() < 5e-5
