@@ -163,5 +163,61 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in var.items()})
 
 
+def import_reference_eval():
+    """python/difffacto/datasets/evaluation_utils.py with its compiled-extension imports stubbed (only the pure-torch
+    functions knn / lgan_mmd_cov / lgan_mmd_cov_match are called)."""
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    for name, sub in [("difffacto", ""), ("difffacto.datasets", "/datasets"), ("difffacto.metrics", "/metrics"),
+                      ("difffacto.metrics.emd", "/metrics/emd"), ("difffacto.utils", "/utils")]:
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [REF + sub]
+            sys.modules[name] = m
+    stub("difffacto.metrics.chamfer_dist", ChamferDistanceL2_split=object)
+    stub("difffacto.metrics.emd.emd_module", EMD=object)
+    stub("difffacto.utils.misc", fps=None)
+    return importlib.import_module("difffacto.datasets.evaluation_utils")
+
+
+def eval_golden():
+    """knn / lgan_mmd_cov / lgan_mmd_cov_match of the reference on seeded distance matrices -> eval_golden.npz"""
+    import contextlib, io
+    E = import_reference_eval()
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    for tag, (S, Rn) in {"sq": (12, 12), "rect": (9, 14)}.items():
+        Mrs = torch.rand(Rn, S, generator=g) + 0.05
+        Mrr = torch.rand(Rn, Rn, generator=g); Mrr = (Mrr + Mrr.t()) / 2
+        Mss = torch.rand(S, S, generator=g); Mss = (Mss + Mss.t()) / 2
+        if tag == "rect":
+            Mrs[3] += 2000.0  # a reference shape farther than the outlier threshold from every sample
+        with contextlib.redirect_stdout(io.StringIO()):
+            nn = E.knn(Mrr, Mrs, Mss, 1, sqrt=False)
+            nn1 = E.knn(Mrr, Mrs, Mss, 1, sqrt=True, one_way=True)
+            mc = E.lgan_mmd_cov(Mrs.t())
+            mm, midx = E.lgan_mmd_cov_match(Mrs.t())
+        out[f"{tag}_Mrs"], out[f"{tag}_Mrr"], out[f"{tag}_Mss"] = Mrs.numpy(), Mrr.numpy(), Mss.numpy()
+        for k, v in nn.items():
+            out[f"{tag}_knn_{k}"] = np.asarray(float(v))
+        for k, v in nn1.items():
+            out[f"{tag}_knn1way_{k}"] = np.asarray(float(v))
+        for k, v in mc.items():
+            out[f"{tag}_mmdcov_{k}"] = np.asarray(float(v))
+        for k, v in mm.items():
+            out[f"{tag}_match_{k}"] = np.asarray(float(v))
+        out[f"{tag}_match_idx"] = midx.numpy()
+    path = os.path.join(HERE, "eval_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":
+        eval_golden()
+    else:
+        main()
+        eval_golden()
