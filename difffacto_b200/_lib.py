@@ -50,6 +50,17 @@ SIGNATURES = {
     "dfb200_denoiser_forward": (c_int, [_CFG, P, c_int, c_int, c_int] + [P] * 8 + [P, c_size_t, P]),
     "dfb200_ddpm_step": (c_int, [c_int] * 3 + [P] * 10),
     "dfb200_q_sample": (c_int, [c_int] * 3 + [P] * 8),
+    "dfb200_sgemm": (c_int, [c_int] * 5 + [P, c_int, P, c_int, P, c_int, P, c_int, c_int, P]),
+    "dfb200_colsum_accumulate": (c_int, [ctypes.c_longlong, c_int, P, c_int, P, P]),
+    "dfb200_layernorm128_forward": (c_int, [ctypes.c_longlong] + [P] * 7),
+    "dfb200_layernorm128_backward": (c_int, [ctypes.c_longlong] + [P] * 9),
+    "dfb200_geglu_forward": (c_int, [ctypes.c_longlong, c_int, P, P, P]),
+    "dfb200_geglu_backward": (c_int, [ctypes.c_longlong, c_int, P, P, P, P]),
+    "dfb200_part_attention_forward": (c_int, [c_int, c_int] + [P] * 7),
+    "dfb200_part_attention_backward": (c_int, [c_int, c_int] + [P] * 10),
+    "dfb200_timestep_embedding": (c_int, [c_int, P, P, P, P]),
+    "dfb200_dropout": (c_int, [c_size_t, c_float, c_u64, c_u64, P, P, P, P]),
+    "dfb200_q_sample_backward": (c_int, [c_int] * 3 + [P] * 9),
     "dfb200_ddim_step": (c_int, [c_int] * 3 + [P] * 9 + [c_float, P, P, P]),
     "dfb200_guidance_mix": (c_int, [c_size_t, c_float, P, P, P, P]),
     "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),

@@ -1,0 +1,476 @@
+// Training-side primitives of the cross-diffusion denoiser (fp32, CUDA cores): the differentiable building blocks that
+// difffacto_b200/train_ops.py composes - through torch.autograd.Function wrappers - into the training forward/backward of
+// TransformerNet (reference: python/difffacto/models/diffusions/nets/attention.py:50-57 GEGLU, :77-94 FeedForward,
+// :161-204 CrossAttention, :259-306 BasicTransformerBlock, :385-440 TransformerNet; loss: anchored_diffusion.py:760-852).
+// The sampling path never touches this file; it exists so that `training_losses(...).backward()` runs on this repo's own
+// kernels.  One strided SGEMM serves every Linear (forward, dgrad, wgrad with split-K).
+#include <float.h>
+#include <math.h>
+
+#include "denoiser.cuh"
+#include "philox.cuh"
+
+namespace dfb200 {
+
+// ---------------------------------------------------------------------------------------------
+// C[M,N] = (beta ? C : 0) + bias[j] + sum_k A(i,k) B(k,j)
+//   A_KC:  A(i,k) = A[i*lda + k]  (k contiguous)      else A(i,k) = A[k*lda + i]  (i contiguous)
+//   B_KC:  B(k,j) = B[j*ldb + k]  (k contiguous)      else B(k,j) = B[k*ldb + j]  (j contiguous)
+// 64x64 tile, 16-deep k slices, 256 threads x (4x4).  gridDim.z > 1 = split-K (atomicAdd epilogue; C must hold its
+// initial value, bias is added by split 0 only).
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_T = 64, SG_K = 16, SG_LD = SG_T + 4;
+
+template <bool KC>
+__device__ __forceinline__ void sg_load(float (*S)[SG_LD], const float* __restrict__ P, int ld, int r0, int rows, int k0, int kend) {
+  const int tid = threadIdx.x;
+  if (KC) {
+    const int r = tid >> 2, k4 = (tid & 3) * 4;
+    const int gr = r0 + r, gk = k0 + k4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gr < rows) {
+      const float* p = P + (size_t)gr * ld + gk;
+      if (gk + 3 < kend && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (gk + e < kend) v[e] = __ldg(p + e);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) S[k4 + e][r] = v[e];
+  } else {
+    const int k = tid >> 4, r4 = (tid & 15) * 4;
+    const int gk = k0 + k, gr = r0 + r4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gk < kend) {
+      const float* p = P + (size_t)gk * ld + gr;
+      if (gr + 3 < rows && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        t = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        if (gr < rows) t.x = __ldg(p);
+        if (gr + 1 < rows) t.y = __ldg(p + 1);
+        if (gr + 2 < rows) t.z = __ldg(p + 2);
+        if (gr + 3 < rows) t.w = __ldg(p + 3);
+      }
+    }
+    *reinterpret_cast<float4*>(&S[k][r4]) = t;
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+             float* __restrict__ C, int ldc, const float* __restrict__ bias, int beta, int k_per_split) {
+  __shared__ __align__(16) float As[SG_K][SG_LD];
+  __shared__ __align__(16) float Bs[SG_K][SG_LD];
+  const int i0 = blockIdx.y * SG_T, j0 = blockIdx.x * SG_T;
+  const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += SG_K) {
+    sg_load<A_KC>(As, A, lda, i0, M, k0, kend);
+    sg_load<B_KC>(Bs, B, ldb, j0, N, k0, kend);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_K; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r;
+    if (i >= M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + tx * 4 + c;
+      if (j >= N) continue;
+      float v = acc[r][c];
+      if (bias != nullptr && blockIdx.z == 0) v += __ldg(bias + j);
+      float* o = C + (size_t)i * ldc + j;
+      if (split) atomicAdd(o, v);
+      else *o = beta ? *o + v : v;
+    }
+  }
+}
+
+// out[j] += sum_i X[i*ld + j]   (bias gradients)
+__global__ void __launch_bounds__(256)
+colsum_kernel(long long M, int N, const float* __restrict__ X, int ld, float* __restrict__ out, int rows_per_block) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (j < N)
+    for (long long r = r0 + w; r < r1; r += 8) s += __ldg(X + r * ld + j);
+  __shared__ float part[8][33];
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && j < N) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+    atomicAdd(out + j, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over 128 features (nn.LayerNorm(128), eps 1e-5): warp per row, lane = 4 features
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(long long M, const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+              float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * D_MODEL) + lane);
+  float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+  const float mean = s * (1.f / D_MODEL);
+  const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+  float q = dx * dx + dy * dy + dz * dz + dw * dw;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, d);
+  const float rstd = rsqrtf(q * (1.f / D_MODEL) + LN_EPS);
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane), bb = __ldg(reinterpret_cast<const float4*>(b) + lane);
+  reinterpret_cast<float4*>(y + row * D_MODEL)[lane] =
+      make_float4(dx * rstd * gg.x + bb.x, dy * rstd * gg.y + bb.y, dz * rstd * gg.z + bb.z, dw * rstd * gg.w + bb.w);
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dx = rstd * (g.dy - mean(g.dy) - xhat * mean(g.dy.xhat));  dgamma += dy.xhat;  dbeta += dy   (atomics per CTA)
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(long long M, const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean_in,
+              const float* __restrict__ rstd_in, const float* __restrict__ dy, float* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp) {
+  __shared__ float red[2][D_MODEL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < D_MODEL) { red[0][threadIdx.x] = 0.f; red[1][threadIdx.x] = 0.f; }
+  __syncthreads();
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  const long long r0 = ((long long)blockIdx.x * 8 + warp) * rows_per_warp;
+  for (long long row = r0; row < min(M, r0 + rows_per_warp); ++row) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * D_MODEL) + lane);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + row * D_MODEL) + lane);
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+    const float4 gd = make_float4(gg.x * d.x, gg.y * d.y, gg.z * d.z, gg.w * d.w);
+    float m1 = gd.x + gd.y + gd.z + gd.w;
+    float m2 = gd.x * xh.x + gd.y * xh.y + gd.z * xh.z + gd.w * xh.w;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) { m1 += __shfl_xor_sync(0xFFFFFFFFu, m1, s); m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, s); }
+    m1 *= (1.f / D_MODEL); m2 *= (1.f / D_MODEL);
+    reinterpret_cast<float4*>(dx + row * D_MODEL)[lane] =
+        make_float4(rstd * (gd.x - m1 - xh.x * m2), rstd * (gd.y - m1 - xh.y * m2), rstd * (gd.z - m1 - xh.z * m2),
+                    rstd * (gd.w - m1 - xh.w * m2));
+    ag.x += d.x * xh.x; ag.y += d.y * xh.y; ag.z += d.z * xh.z; ag.w += d.w * xh.w;
+    ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+  }
+  atomicAdd(&red[0][lane * 4], ag.x); atomicAdd(&red[0][lane * 4 + 1], ag.y); atomicAdd(&red[0][lane * 4 + 2], ag.z); atomicAdd(&red[0][lane * 4 + 3], ag.w);
+  atomicAdd(&red[1][lane * 4], ab.x); atomicAdd(&red[1][lane * 4 + 1], ab.y); atomicAdd(&red[1][lane * 4 + 2], ab.z); atomicAdd(&red[1][lane * 4 + 3], ab.w);
+  __syncthreads();
+  if (threadIdx.x < D_MODEL) { atomicAdd(dgamma + threadIdx.x, red[0][threadIdx.x]); atomicAdd(dbeta + threadIdx.x, red[1][threadIdx.x]); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEGLU (attention.py:50-57): h = [a | g] (2*H wide), u = a * gelu(g) with the exact erf GELU (F.gelu default)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+geglu_fwd_kernel(long long total, int H, const float* __restrict__ h, float* __restrict__ u) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const long long row = q / H;
+  const int c = (int)(q - row * H);
+  const float a = __ldg(h + row * 2 * H + c), g = __ldg(h + row * 2 * H + H + c);
+  u[q] = a * (0.5f * g * (1.f + erff(g * 0.70710678118654752440f)));
+}
+__global__ void __launch_bounds__(256)
+geglu_bwd_kernel(long long total, int H, const float* __restrict__ h, const float* __restrict__ du, float* __restrict__ dh) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const long long row = q / H;
+  const int c = (int)(q - row * H);
+  const float a = __ldg(h + row * 2 * H + c), g = __ldg(h + row * 2 * H + H + c), d = __ldg(du + q);
+  const float cdf = 0.5f * (1.f + erff(g * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * g * g);
+  dh[row * 2 * H + c] = d * g * cdf;
+  dh[row * 2 * H + H + c] = d * a * (cdf + g * pdf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-attention core over the 4 part tokens (attention.py:183-203): 8 heads x 16, masked softmax over 4 keys.
+// Warp per token, lane = 4 of the 128 dims (head = lane / 4).  q/o (B*N,128), k/v (B,4,128), probs (B*N,8,4).
+// ---------------------------------------------------------------------------------------------
+constexpr int PA_TOK = 256;  // tokens per CTA (all of one sample: N % PA_TOK is handled by clamping)
+__global__ void __launch_bounds__(256)
+part_attn_fwd_kernel(int N, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                     const float* __restrict__ valid, float* __restrict__ o, float* __restrict__ probs) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4* kb = reinterpret_cast<const float4*>(k + (size_t)b * MAX_TOKENS * D_MODEL);
+  const float4* vb = reinterpret_cast<const float4*>(v + (size_t)b * MAX_TOKENS * D_MODEL);
+  float4 k4[MAX_TOKENS], v4[MAX_TOKENS];
+  bool ok[MAX_TOKENS];
+#pragma unroll
+  for (int j = 0; j < MAX_TOKENS; ++j) {
+    k4[j] = __ldg(kb + j * 32 + lane); v4[j] = __ldg(vb + j * 32 + lane);
+    ok[j] = valid == nullptr || __ldg(valid + b * MAX_TOKENS + j) != 0.f;
+  }
+  const int p0 = blockIdx.x * PA_TOK;
+  for (int p = p0 + warp; p < min(N, p0 + PA_TOK); p += 8) {
+    const size_t tok = (size_t)b * N + p;
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(q + tok * D_MODEL) + lane);
+    float s[MAX_TOKENS];
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) {
+      float d = q4.x * k4[j].x + q4.y * k4[j].y + q4.z * k4[j].z + q4.w * k4[j].w;
+      d += __shfl_xor_sync(0xFFFFFFFFu, d, 1);
+      d += __shfl_xor_sync(0xFFFFFFFFu, d, 2);
+      s[j] = ok[j] ? d * 0.25f : -FLT_MAX;  // dim_head ** -0.5; masked_fill(~mask, -finfo.max)
+    }
+    const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+    float e[MAX_TOKENS], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) { e[j] = expf(s[j] - mx); sum += e[j]; }
+    const float inv = 1.f / sum;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) {
+      const float pj = e[j] * inv;
+      acc.x = fmaf(pj, v4[j].x, acc.x); acc.y = fmaf(pj, v4[j].y, acc.y); acc.z = fmaf(pj, v4[j].z, acc.z); acc.w = fmaf(pj, v4[j].w, acc.w);
+      e[j] = pj;
+    }
+    reinterpret_cast<float4*>(o + tok * D_MODEL)[lane] = acc;
+    if ((lane & 3) == 0) reinterpret_cast<float4*>(probs + tok * 32)[lane >> 2] = make_float4(e[0], e[1], e[2], e[3]);
+  }
+}
+
+// dq per token; dk/dv accumulated over the tokens of the sample (registers -> shared -> one atomicAdd per CTA and element)
+__global__ void __launch_bounds__(256)
+part_attn_bwd_kernel(int N, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                     const float* __restrict__ valid, const float* __restrict__ probs, const float* __restrict__ d_o,
+                     float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv) {
+  __shared__ float red[2][MAX_TOKENS][D_MODEL];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 2 * MAX_TOKENS * D_MODEL; i += 256) (&red[0][0][0])[i] = 0.f;
+  __syncthreads();
+  const float4* kb = reinterpret_cast<const float4*>(k + (size_t)b * MAX_TOKENS * D_MODEL);
+  const float4* vb = reinterpret_cast<const float4*>(v + (size_t)b * MAX_TOKENS * D_MODEL);
+  float4 k4[MAX_TOKENS], v4[MAX_TOKENS], ak[MAX_TOKENS], av[MAX_TOKENS];
+  bool ok[MAX_TOKENS];
+#pragma unroll
+  for (int j = 0; j < MAX_TOKENS; ++j) {
+    k4[j] = __ldg(kb + j * 32 + lane); v4[j] = __ldg(vb + j * 32 + lane);
+    ak[j] = make_float4(0.f, 0.f, 0.f, 0.f); av[j] = ak[j];
+    ok[j] = valid == nullptr || __ldg(valid + b * MAX_TOKENS + j) != 0.f;
+  }
+  const int p0 = blockIdx.x * PA_TOK;
+  for (int p = p0 + warp; p < min(N, p0 + PA_TOK); p += 8) {
+    const size_t tok = (size_t)b * N + p;
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(q + tok * D_MODEL) + lane);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(d_o + tok * D_MODEL) + lane);
+    const float4 pr = __ldg(reinterpret_cast<const float4*>(probs + tok * 32) + (lane >> 2));
+    const float pj[MAX_TOKENS] = {pr.x, pr.y, pr.z, pr.w};
+    float dp[MAX_TOKENS], dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) {
+      float d = g4.x * v4[j].x + g4.y * v4[j].y + g4.z * v4[j].z + g4.w * v4[j].w;
+      d += __shfl_xor_sync(0xFFFFFFFFu, d, 1);
+      d += __shfl_xor_sync(0xFFFFFFFFu, d, 2);
+      dp[j] = d;
+      dot = fmaf(pj[j], d, dot);
+    }
+    float4 dq4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < MAX_TOKENS; ++j) {
+      // softmax backward; masked logits receive no gradient (masked_fill), and sim = 0.25 * q.k
+      const float ds = ok[j] ? 0.25f * pj[j] * (dp[j] - dot) : 0.f;
+      dq4.x = fmaf(ds, k4[j].x, dq4.x); dq4.y = fmaf(ds, k4[j].y, dq4.y); dq4.z = fmaf(ds, k4[j].z, dq4.z); dq4.w = fmaf(ds, k4[j].w, dq4.w);
+      ak[j].x = fmaf(ds, q4.x, ak[j].x); ak[j].y = fmaf(ds, q4.y, ak[j].y); ak[j].z = fmaf(ds, q4.z, ak[j].z); ak[j].w = fmaf(ds, q4.w, ak[j].w);
+      av[j].x = fmaf(pj[j], g4.x, av[j].x); av[j].y = fmaf(pj[j], g4.y, av[j].y); av[j].z = fmaf(pj[j], g4.z, av[j].z); av[j].w = fmaf(pj[j], g4.w, av[j].w);
+    }
+    reinterpret_cast<float4*>(dq + tok * D_MODEL)[lane] = dq4;
+  }
+#pragma unroll
+  for (int j = 0; j < MAX_TOKENS; ++j) {
+    float* rk = &red[0][j][lane * 4];
+    float* rv = &red[1][j][lane * 4];
+    atomicAdd(rk, ak[j].x); atomicAdd(rk + 1, ak[j].y); atomicAdd(rk + 2, ak[j].z); atomicAdd(rk + 3, ak[j].w);
+    atomicAdd(rv, av[j].x); atomicAdd(rv + 1, av[j].y); atomicAdd(rv + 2, av[j].z); atomicAdd(rv + 3, av[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MAX_TOKENS * D_MODEL; i += 256) {
+    atomicAdd(dk + (size_t)b * MAX_TOKENS * D_MODEL + i, (&red[0][0][0])[i]);
+    atomicAdd(dv + (size_t)b * MAX_TOKENS * D_MODEL + i, (&red[1][0][0])[i]);
+  }
+}
+
+// timestep_embedding (nets/utils.py:7-24): out[b] = [cos(t_b f_0..f_127) | sin(t_b f_0..f_127)]
+__global__ void __launch_bounds__(128)
+timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out) {
+  const int b = blockIdx.x, i = threadIdx.x;
+  const float a = __ldg(t + b) * __ldg(freqs + i);
+  out[(size_t)b * 256 + i] = cosf(a);
+  out[(size_t)b * 256 + 128 + i] = sinf(a);
+}
+
+// Inverted dropout with a counter-based mask (Philox, one draw per 4 elements): y = (keep ? x / (1 - p) : 0) (+ residual).  The backward
+// pass calls the same kernel on the incoming gradient with the same (seed, offset).
+__global__ void __launch_bounds__(256)
+dropout_kernel(long long total, float p, float scale, uint64_t seed, uint64_t offset, const float* __restrict__ x,
+               const float* __restrict__ residual, float* __restrict__ y) {
+  const long long q4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = q4 * 4;
+  if (e >= total) return;
+  uint32_t r[4];
+  philox4x32_10((uint64_t)q4, offset, seed, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (e + i < total) {
+      const float u = (float)(r[i] >> 8) * 5.9604644775390625e-8f;  // [0, 1)
+      const float r = residual != nullptr ? __ldg(residual + e + i) : 0.f;
+      y[e + i] = (u >= p ? __ldg(x + e + i) * scale : 0.f) + r;
+    }
+  }
+}
+
+// q_sample backward (anchored_diffusion.py:169-173): x_t = sa (x0 - a) + a + sb sqrt(var) noise
+//   d x0 = sa g;   d a = (1 - sa) g;   d var = sb noise g / (2 sqrt(var))
+__global__ void __launch_bounds__(256)
+q_sample_bwd_kernel(long long total, int per_sample, int T, const float* __restrict__ sched, const int* __restrict__ t,
+                    const float* __restrict__ variance, const float* __restrict__ noise, const float* __restrict__ g,
+                    float* __restrict__ dx0, float* __restrict__ da, float* __restrict__ dvar) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int tt = __ldg(t + (int)(q / per_sample));
+  const float sa = __ldg(sched + DFB200_SCHED_SQRT_ALPHAS_CUMPROD * T + tt);
+  const float sb = __ldg(sched + DFB200_SCHED_SQRT_ONE_MINUS_ALPHAS_CUMPROD * T + tt);
+  const float gg = __ldg(g + q);
+  if (dx0 != nullptr) dx0[q] = sa * gg;
+  if (da != nullptr) da[q] = (1.f - sa) * gg;
+  if (dvar != nullptr) dvar[q] = sb * __ldg(noise + q) * gg * 0.5f * rsqrtf(__ldg(variance + q));
+}
+
+}  // namespace dfb200
+
+using namespace dfb200;
+
+extern "C" int dfb200_sgemm(int a_k_contiguous, int b_k_contiguous, int M, int N, int K, const float* A, int lda, const float* B,
+                            int ldb, float* C, int ldc, const float* bias, int beta, int split_k, dfb200_stream_t stream) {
+  DFB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && split_k >= 1, DFB200_ERR_INVALID_ARG, "sgemm: bad sizes M=%d N=%d K=%d split=%d", M, N, K, split_k);
+  if (M == 0 || N == 0) return DFB200_OK;
+  int kps = cdiv(cdiv(K, split_k), SG_K) * SG_K;
+  if (kps == 0) kps = SG_K;
+  const int splits = K == 0 ? 1 : cdiv(K, kps);
+  dim3 grid(cdiv(N, SG_T), cdiv(M, SG_T), splits);
+  DFB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DFB200_ERR_INVALID_ARG, "sgemm: grid too large");
+  cudaStream_t st = as_stream(stream);
+#define SG_LAUNCH(AK, BK) sgemm_kernel<AK, BK><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta, kps)
+  if (a_k_contiguous && b_k_contiguous) SG_LAUNCH(true, true);
+  else if (a_k_contiguous) SG_LAUNCH(true, false);
+  else if (b_k_contiguous) SG_LAUNCH(false, true);
+  else SG_LAUNCH(false, false);
+#undef SG_LAUNCH
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_colsum_accumulate(long long M, int N, const float* X, int ld, float* out, dfb200_stream_t stream) {
+  if (M <= 0 || N <= 0) return DFB200_OK;
+  const int rpb = 512;
+  colsum_kernel<<<dim3(cdiv(N, 32), (unsigned)cdiv(M, (long long)rpb)), 256, 0, as_stream(stream)>>>(M, N, X, ld, out, rpb);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_layernorm128_forward(long long M, const float* x, const float* gamma, const float* beta, float* y,
+                                           float* mean, float* rstd, dfb200_stream_t stream) {
+  if (M <= 0) return DFB200_OK;
+  ln_fwd_kernel<<<(unsigned)cdiv(M, 8LL), 256, 0, as_stream(stream)>>>(M, x, gamma, beta, y, mean, rstd);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_layernorm128_backward(long long M, const float* x, const float* gamma, const float* mean, const float* rstd,
+                                            const float* dy, float* dx, float* dgamma_accum, float* dbeta_accum,
+                                            dfb200_stream_t stream) {
+  if (M <= 0) return DFB200_OK;
+  const int rpw = 16;
+  ln_bwd_kernel<<<(unsigned)cdiv(M, (long long)(8 * rpw)), 256, 0, as_stream(stream)>>>(M, x, gamma, mean, rstd, dy, dx, dgamma_accum,
+                                                                                        dbeta_accum, rpw);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_geglu_forward(long long M, int H, const float* h, float* u, dfb200_stream_t stream) {
+  const long long total = M * H;
+  if (total <= 0) return DFB200_OK;
+  geglu_fwd_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, as_stream(stream)>>>(total, H, h, u);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_geglu_backward(long long M, int H, const float* h, const float* du, float* dh, dfb200_stream_t stream) {
+  const long long total = M * H;
+  if (total <= 0) return DFB200_OK;
+  geglu_bwd_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, as_stream(stream)>>>(total, H, h, du, dh);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_part_attention_forward(int B, int N, const float* q, const float* k, const float* v, const float* valid_id,
+                                             float* o, float* probs, dfb200_stream_t stream) {
+  DFB_REQUIRE(B >= 0 && N >= 0 && B <= 65535, DFB200_ERR_INVALID_ARG, "part_attention_forward: bad sizes B=%d N=%d", B, N);
+  if (B == 0 || N == 0) return DFB200_OK;
+  part_attn_fwd_kernel<<<dim3(cdiv(N, PA_TOK), B), 256, 0, as_stream(stream)>>>(N, q, k, v, valid_id, o, probs);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_part_attention_backward(int B, int N, const float* q, const float* k, const float* v, const float* valid_id,
+                                              const float* probs, const float* d_o, float* dq, float* dk_accum, float* dv_accum,
+                                              dfb200_stream_t stream) {
+  DFB_REQUIRE(B >= 0 && N >= 0 && B <= 65535, DFB200_ERR_INVALID_ARG, "part_attention_backward: bad sizes B=%d N=%d", B, N);
+  if (B == 0 || N == 0) return DFB200_OK;
+  part_attn_bwd_kernel<<<dim3(cdiv(N, PA_TOK), B), 256, 0, as_stream(stream)>>>(N, q, k, v, valid_id, probs, d_o, dq, dk_accum, dv_accum);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_timestep_embedding(int B, const float* t, const float* freqs128, float* out, dfb200_stream_t stream) {
+  if (B <= 0) return DFB200_OK;
+  timestep_embedding_kernel<<<B, 128, 0, as_stream(stream)>>>(t, freqs128, out);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_dropout(size_t count, float p, uint64_t seed, uint64_t offset, const float* x, const float* residual, float* y,
+                              dfb200_stream_t stream) {
+  DFB_REQUIRE(p >= 0.f && p < 1.f, DFB200_ERR_INVALID_ARG, "dropout: p must be in [0, 1)");
+  if (count == 0) return DFB200_OK;
+  dropout_kernel<<<(unsigned)cdiv((long long)((count + 3) / 4), 256LL), 256, 0, as_stream(stream)>>>((long long)count, p, 1.f / (1.f - p), seed,
+                                                                                                     offset, x, residual, y);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_q_sample_backward(int B, int N, int T, const float* sched, const int* t, const float* variance,
+                                        const float* noise, const float* grad_x_t, float* grad_x_start, float* grad_anchors,
+                                        float* grad_variance, dfb200_stream_t stream) {
+  DFB_REQUIRE(B >= 0 && N >= 0 && T > 0, DFB200_ERR_INVALID_ARG, "q_sample_backward: bad sizes B=%d N=%d T=%d", B, N, T);
+  const long long total = (long long)B * 3 * N;
+  if (total == 0) return DFB200_OK;
+  q_sample_bwd_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, as_stream(stream)>>>(total, 3 * N, T, sched, t, variance, noise, grad_x_t,
+                                                                                   grad_x_start, grad_anchors, grad_variance);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}

@@ -136,8 +136,11 @@ class AnchoredDiffusion(Module):
         assert noise.shape == x_start.shape
         x_start, anchors, variance, noise = self._prep(x_start, anchors, variance, noise)
         B, C, N = x_start.shape
-        out = torch.empty_like(x_start)
         ti = t.to(torch.int32).contiguous()
+        if torch.is_grad_enabled() and any(v.requires_grad for v in (x_start, anchors, variance)):
+            from ... import train_ops
+            return train_ops.QSampleFn.apply(x_start, anchors, variance, noise, ti, self._sched(x_start.device), self.num_timesteps)
+        out = torch.empty_like(x_start)
         with torch.cuda.device(x_start.device):
             check(_lib.load().dfb200_q_sample(B, N, self.num_timesteps, ptr(self._sched(x_start.device)), ptr(ti),
                                               ptr(x_start), ptr(anchors), ptr(variance), ptr(noise), ptr(out), stream()))
@@ -286,7 +289,7 @@ class AnchoredDiffusion(Module):
                                               stream()))
         return (x, traj) if traj_interval else x
 
-    # ---- training objective (value only; backward kernels are not part of this build) --------
+    # ---- training objective: differentiable through difffacto_b200/train_ops.py (fp32 kernels) --------
     def training_losses(self, x_start, t, anchors=None, variance=None, ctx=None, reduce=True, anchor_assignment=None,
                         valid_id=None, flags=None, noise=None):
         """{'mse_loss'} of the epsilon objective (reference :760-852)."""

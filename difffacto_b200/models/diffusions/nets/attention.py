@@ -6,6 +6,10 @@ its pretrained checkpoints), same `forward(x, t, ctx, anchors=, variances=, vali
 anchor_assignment=)` contract.  The modules below only HOLD parameters; the forward pass is the
 hand-written CUDA of difffacto_b200/csrc/denoiser_*.cu reached through the C ABI
 (dfb200_denoiser_forward).  There is no PyTorch fallback: CPU tensors raise.
+
+When a gradient is required (training: `training_losses(...).backward()`), the forward runs as a
+composition of the differentiable fp32 primitives of difffacto_b200/train_ops.py (each a
+torch.autograd.Function over this repo's CUDA kernels), op for op like the reference modules.
 """
 import math
 import os
@@ -14,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from .... import _lib
+from .... import train_ops as T
 from ...._lib import DenoiserCfg, check, ptr, stream
 from ....utils.registry import NETS
 
@@ -162,11 +167,11 @@ class TransformerNet(nn.Module):
         """x (B,3,N); t (B,); ctx list of (B,C,4) or a (B,262,4) tensor; anchors/variances (B,N,3)
         (the reference passes `.transpose(1,2)` views of (B,3,N) tensors); valid_id (B,4);
         anchor_assignment (B,N) int32.  Returns eps (B,3,N).  Reference attention.py:385-440."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("difffacto_b200.TransformerNet: backward kernels are not part of this build; "
-                                      "call under torch.no_grad() / eval()")
         if isinstance(ctx, (list, tuple)):
             ctx = torch.cat(list(ctx), dim=1)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                        any(torch.is_tensor(a) and a.requires_grad for a in (x, ctx, anchors, variances))):
+            return self._forward_train(x, t, ctx, anchors, variances, valid_id, anchor_assignment)
         _lib.require_cuda(x, ctx, anchors, variances, anchor_assignment, valid_id)
         B, C, N = x.shape
         assert C == self.raw_in_channels
@@ -194,3 +199,49 @@ class TransformerNet(nn.Module):
             check(lib.dfb200_denoiser_forward(cfg, ptr(packed), mode, B, N, ptr(x), ptr(tf), ptr(ctx), ptr(anchors_cm),
                                               ptr(variances_cm), ptr(assign), ptr(valid), ptr(eps), ptr(ws), nws, stream()))
         return eps
+
+    # ---- training forward (differentiable) ----------------------------------------------------
+    def _ff(self, ff, x, residual=None):
+        """FeedForward (glu=True): Linear -> GEGLU -> Dropout -> Linear (reference attention.py:77-94)."""
+        h = T.linear(x, ff.net[0].proj.weight, ff.net[0].proj.bias)
+        u = T.dropout(T.geglu(h), self.dropout, self.training)
+        return T.linear(u, ff.net[2].weight, ff.net[2].bias, residual)
+
+    def _forward_train(self, x, t, ctx, anchors, variances, valid_id, anchor_assignment):
+        """Reference attention.py:385-440 (+ :296-306, :179-204) on the differentiable primitives; fp32."""
+        _lib.require_cuda(x, ctx, anchors, variances, anchor_assignment, valid_id)
+        if self.include_std:
+            raise NotImplementedError("difffacto_b200.TransformerNet: include_std is not supported on the training path")
+        B, C, N = x.shape
+        f32 = torch.float32
+        dev = x.device
+        # context (B,4,522) = [part code | mean, var | one-hot class | t_embed]  (:389-398)
+        ctx = ctx.to(f32).transpose(1, 2)
+        class_embed = torch.eye(self.n_class, device=dev, dtype=f32).unsqueeze(0).expand(B, -1, -1)
+        freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=128, dtype=f32) / 128).to(dev)
+        t_embed = self._ff(self.time_embed, T.timestep_embedding(t, freqs))
+        ctx = torch.cat([ctx, class_embed, t_embed.unsqueeze(1).expand(-1, self.n_class, -1)], dim=-1).contiguous()
+        ctx2d = ctx.reshape(B * self.n_class, self.context_dim)
+        # point features (B*N,13) = [x | anchors | variances | one-hot part]  (:400-407)
+        onehot = torch.nn.functional.one_hot(anchor_assignment.long(), num_classes=self.n_class).to(f32)
+        feat = torch.cat([x.to(f32).transpose(1, 2), anchors.to(f32), variances.to(f32), onehot], dim=-1).reshape(B * N, self.in_channels)
+        valid = None
+        if self.mask_out_unreferenced_code and valid_id is not None:
+            valid = valid_id.to(f32).contiguous()
+        h = T.linear(feat.contiguous(), self.proj_in.weight, self.proj_in.bias)
+        h = T.layernorm128(h, self.pre_norm.weight, self.pre_norm.bias)
+        for blk in self.transformer_blocks:
+            a = T.layernorm128(h, blk.norm2.weight, blk.norm2.bias)
+            q = T.linear(a, blk.attn2.to_q.weight)
+            k = T.linear(ctx2d, blk.attn2.to_k.weight).view(B, self.n_class, self.inner_dim)
+            v = T.linear(ctx2d, blk.attn2.to_v.weight).view(B, self.n_class, self.inner_dim)
+            o = T.part_attention(q, k, v, valid, B, N)
+            if self.training and self.dropout > 0:  # to_out = [Linear, Dropout], then the residual add (:203, :303)
+                h = T.dropout(T.linear(o, blk.attn2.to_out[0].weight, blk.attn2.to_out[0].bias), self.dropout, True, residual=h)
+            else:
+                h = T.linear(o, blk.attn2.to_out[0].weight, blk.attn2.to_out[0].bias, h)
+            f = T.layernorm128(h, blk.norm3.weight, blk.norm3.bias)
+            h = self._ff(blk.ff, f, residual=h)
+        h = T.layernorm128(h, self.post_norm.weight, self.post_norm.bias)
+        out = T.linear(h, self.proj_out.weight, self.proj_out.bias)
+        return out.view(B, N, self.out_channels).transpose(1, 2).contiguous()

@@ -1,0 +1,231 @@
+"""Differentiable building blocks of the denoiser's TRAINING path: torch.autograd.Function wrappers around the fp32
+CUDA primitives of difffacto_b200/csrc/train_ops.cu (C ABI: dfb200_sgemm, dfb200_layernorm128_*, dfb200_geglu_*,
+dfb200_part_attention_*, dfb200_dropout, dfb200_timestep_embedding, dfb200_q_sample_backward).
+
+torch supplies the autograd graph, memory and pure data movement (cat / transpose / one_hot); every multiply-add of the
+forward AND backward pass runs in this repo's kernels.  Composed by TransformerNet._forward_train
+(models/diffusions/nets/attention.py), which follows the reference's module structure op for op
+(python/difffacto/models/diffusions/nets/attention.py:50-57, 77-94, 161-204, 259-306, 385-440).
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+
+def _c(t):
+    return t.contiguous() if not t.is_contiguous() else t
+
+
+def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split_k=1):
+    with torch.cuda.device(C.device):
+        check(_lib.load().dfb200_sgemm(int(a_kc), int(b_kc), M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), int(beta),
+                                       int(split_k), stream()))
+
+
+class LinearFn(Function):
+    """y = x W^T (+ b) (+ residual);  x (M,K), W (N,K) as in nn.Linear.  Backward: dx = dy W, dW = dy^T x (split-K over the
+    M rows), db = column sums of dy; the residual receives dy unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        x, weight = _c(x), _c(weight)
+        M, K = x.shape
+        N = weight.shape[0]
+        if residual is not None:
+            y = residual.contiguous().clone()
+        else:
+            y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        _sgemm(True, True, M, N, K, x, K, weight, K, y, N, bias=bias, beta=residual is not None)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        M, K = x.shape
+        N = weight.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
+            _sgemm(True, False, M, K, N, dy, N, weight, K, dx, K)            # dx(i,k) = sum_n dy(i,n) W(n,k)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(N, K, device=x.device, dtype=torch.float32)
+            tiles = ((N + 63) // 64) * ((K + 63) // 64)
+            split = max(1, min((M + 255) // 256, (148 * 4 + tiles - 1) // tiles))
+            _sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=split)  # dW(n,k) = sum_m dy(m,n) x(m,k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(N, device=x.device, dtype=torch.float32)
+            with torch.cuda.device(x.device):
+                check(_lib.load().dfb200_colsum_accumulate(M, N, ptr(dy), N, ptr(db), stream()))
+        return dx, dw, db, (dy if ctx.has_res and ctx.needs_input_grad[3] else None)
+
+
+def linear(x, weight, bias=None, residual=None):
+    return LinearFn.apply(x, weight, bias, residual)
+
+
+class LayerNorm128Fn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        x = _c(x)
+        M = x.shape[0]
+        assert x.shape[1] == 128
+        y = torch.empty_like(x)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            check(_lib.load().dfb200_layernorm128_forward(M, ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), ptr(mean), ptr(rstd), stream()))
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        dg = torch.zeros(128, device=x.device, dtype=torch.float32)
+        db = torch.zeros(128, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            check(_lib.load().dfb200_layernorm128_backward(x.shape[0], ptr(x), ptr(_c(gamma)), ptr(mean), ptr(rstd), ptr(dy), ptr(dx),
+                                                           ptr(dg), ptr(db), stream()))
+        return dx, dg, db
+
+
+def layernorm128(x, gamma, beta):
+    return LayerNorm128Fn.apply(x, gamma, beta)
+
+
+class GegluFn(Function):
+    @staticmethod
+    def forward(ctx, h):
+        h = _c(h)
+        M, H2 = h.shape
+        u = torch.empty(M, H2 // 2, device=h.device, dtype=torch.float32)
+        with torch.cuda.device(h.device):
+            check(_lib.load().dfb200_geglu_forward(M, H2 // 2, ptr(h), ptr(u), stream()))
+        ctx.save_for_backward(h)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        (h,) = ctx.saved_tensors
+        dh = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            check(_lib.load().dfb200_geglu_backward(h.shape[0], h.shape[1] // 2, ptr(h), ptr(_c(du)), ptr(dh), stream()))
+        return dh
+
+
+def geglu(h):
+    return GegluFn.apply(h)
+
+
+class PartAttentionFn(Function):
+    """softmax(q k^T / 4, masked) v over the 4 part tokens; q (B*N,128), k/v (B,4,128), valid (B,4) float or None."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, valid, B, N):
+        q, k, v = _c(q), _c(k), _c(v)
+        o = torch.empty_like(q)
+        probs = torch.empty(B * N, 32, device=q.device, dtype=torch.float32)
+        with torch.cuda.device(q.device):
+            check(_lib.load().dfb200_part_attention_forward(B, N, ptr(q), ptr(k), ptr(v), ptr(valid), ptr(o), ptr(probs), stream()))
+        ctx.save_for_backward(q, k, v, probs)
+        ctx.valid, ctx.B, ctx.N = valid, B, N
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, probs = ctx.saved_tensors
+        dq = torch.empty_like(q)
+        dk = torch.zeros_like(k)
+        dv = torch.zeros_like(v)
+        with torch.cuda.device(q.device):
+            check(_lib.load().dfb200_part_attention_backward(ctx.B, ctx.N, ptr(q), ptr(k), ptr(v), ptr(ctx.valid), ptr(probs), ptr(_c(d_o)),
+                                                             ptr(dq), ptr(dk), ptr(dv), stream()))
+        return dq, dk, dv, None, None, None
+
+
+def part_attention(q, k, v, valid, B, N):
+    return PartAttentionFn.apply(q, k, v, valid, B, N)
+
+
+_dropout_calls = 0
+
+
+class DropoutFn(Function):
+    """y = dropout(x) (+ residual): inverted dropout with a Philox mask keyed by (seed, offset)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, offset, residual):
+        x = _c(x)
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(_lib.load().dfb200_dropout(x.numel(), float(p), int(seed), int(offset), ptr(x), ptr(None if residual is None else _c(residual)),
+                                             ptr(y), stream()))
+        ctx.args = (float(p), int(seed), int(offset))
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        p, seed, offset = ctx.args
+        with torch.cuda.device(dy.device):
+            check(_lib.load().dfb200_dropout(dy.numel(), p, seed, offset, ptr(dy), None, ptr(dx), stream()))
+        return dx, None, None, None, (dy if ctx.has_res else None)
+
+
+def dropout(x, p, training, residual=None):
+    """nn.Dropout (optionally fused with the residual add that follows it): identity in eval mode or for p == 0; the mask
+    seed comes from torch's CPU generator (so torch.manual_seed makes a run reproducible), the offset counts the dropout
+    calls of the process."""
+    global _dropout_calls
+    if not training or p == 0.0:
+        return x if residual is None else x + residual
+    _dropout_calls += 1
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return DropoutFn.apply(x, p, seed, _dropout_calls, residual)
+
+
+def timestep_embedding(t, freqs):
+    """(B,) float timesteps -> (B,256) sinusoid (no parameters, no gradient)."""
+    t = _c(t.to(torch.float32))
+    out = torch.empty(t.shape[0], 256, device=t.device, dtype=torch.float32)
+    with torch.cuda.device(t.device):
+        check(_lib.load().dfb200_timestep_embedding(t.shape[0], ptr(t), ptr(freqs), ptr(out), stream()))
+    return out
+
+
+class QSampleFn(Function):
+    """x_t = sqrt_ac (x0 - a) + a + sqrt_1mac sqrt(var) noise with gradients to x0, anchors and variance."""
+
+    @staticmethod
+    def forward(ctx, x_start, anchors, variance, noise, t_i32, sched, T):
+        x_start, anchors, variance, noise = _c(x_start), _c(anchors), _c(variance), _c(noise)
+        B, C, N = x_start.shape
+        out = torch.empty_like(x_start)
+        with torch.cuda.device(x_start.device):
+            check(_lib.load().dfb200_q_sample(B, N, T, ptr(sched), ptr(t_i32), ptr(x_start), ptr(anchors), ptr(variance), ptr(noise),
+                                              ptr(out), stream()))
+        ctx.save_for_backward(variance, noise, t_i32, sched)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        variance, noise, t_i32, sched = ctx.saved_tensors
+        g = _c(g)
+        B, C, N = g.shape
+        need = ctx.needs_input_grad
+        dx0 = torch.empty_like(g) if need[0] else None
+        da = torch.empty_like(g) if need[1] else None
+        dv = torch.empty_like(g) if need[2] else None
+        with torch.cuda.device(g.device):
+            check(_lib.load().dfb200_q_sample_backward(B, N, ctx.T, ptr(sched), ptr(t_i32), ptr(variance), ptr(noise), ptr(g), ptr(dx0),
+                                                       ptr(da), ptr(dv), stream()))
+        return dx0, da, dv, None, None, None, None

@@ -217,6 +217,44 @@ int dfb200_q_sample(int B, int N, int T, const float* sched, const int* t, const
 int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uint64_t offset,
                          dfb200_stream_t stream);
 
+/* ---- training-side primitives (fp32), composed by difffacto_b200/train_ops.py into the differentiable training
+ * forward/backward of TransformerNet (reference nets/attention.py:50-57, 77-94, 161-204, 259-306, 385-440 run under
+ * torch autograd; anchored_diffusion.py:760-852 training_losses).  All pointers are device pointers, row-major. ---- */
+/* C[M,N] = (beta ? C : 0) + bias[j] + sum_k A(i,k) B(k,j).  a_k_contiguous: A(i,k) = A[i*lda + k], else A[k*lda + i];
+ * b_k_contiguous: B(k,j) = B[j*ldb + k] (an nn.Linear weight), else B[k*ldb + j].  split_k > 1 reduces K in `split_k`
+ * slices with atomicAdd (C must hold its initial value).  bias may be NULL. */
+int dfb200_sgemm(int a_k_contiguous, int b_k_contiguous, int M, int N, int K, const float* A, int lda, const float* B,
+                 int ldb, float* C, int ldc, const float* bias, int beta, int split_k, dfb200_stream_t stream);
+/* out[j] += sum_i X[i*ld + j] (bias gradients; `out` accumulates). */
+int dfb200_colsum_accumulate(long long M, int N, const float* X, int ld, float* out, dfb200_stream_t stream);
+/* nn.LayerNorm(128, eps=1e-5) over M rows; mean/rstd (M) saved for the backward.  backward: dx written, dgamma/dbeta
+ * accumulated (atomicAdd) into caller-zeroed (or running) buffers. */
+int dfb200_layernorm128_forward(long long M, const float* x, const float* gamma, const float* beta, float* y,
+                                float* mean, float* rstd, dfb200_stream_t stream);
+int dfb200_layernorm128_backward(long long M, const float* x, const float* gamma, const float* mean, const float* rstd,
+                                 const float* dy, float* dx, float* dgamma_accum, float* dbeta_accum,
+                                 dfb200_stream_t stream);
+/* GEGLU (attention.py:50-57): h (M, 2H) = [a | g] -> u (M, H) = a * gelu_erf(g); backward dh (M, 2H). */
+int dfb200_geglu_forward(long long M, int H, const float* h, float* u, dfb200_stream_t stream);
+int dfb200_geglu_backward(long long M, int H, const float* h, const float* du, float* dh, dfb200_stream_t stream);
+/* Cross-attention core over the 4 part tokens (attention.py:183-203): q/o (B*N,128) in 8 heads x 16, k/v (B,4,128),
+ * valid_id (B,4) or NULL, probs (B*N,8,4) saved for the backward.  backward: dq written, dk/dv (B,4,128) accumulated. */
+int dfb200_part_attention_forward(int B, int N, const float* q, const float* k, const float* v, const float* valid_id,
+                                  float* o, float* probs, dfb200_stream_t stream);
+int dfb200_part_attention_backward(int B, int N, const float* q, const float* k, const float* v, const float* valid_id,
+                                   const float* probs, const float* d_o, float* dq, float* dk_accum, float* dv_accum,
+                                   dfb200_stream_t stream);
+/* timestep_embedding (nets/utils.py:7-24): out (B,256) = [cos(t f) | sin(t f)], f = the 128 frequencies. */
+int dfb200_timestep_embedding(int B, const float* t, const float* freqs128, float* out, dfb200_stream_t stream);
+/* Inverted dropout with a Philox mask keyed by (seed, offset): y = (keep ? x/(1-p) : 0) + residual (residual may be
+ * NULL).  The backward pass applies the same call (without residual) to the incoming gradient. */
+int dfb200_dropout(size_t count, float p, uint64_t seed, uint64_t offset, const float* x, const float* residual, float* y,
+                   dfb200_stream_t stream);
+/* Backward of dfb200_q_sample: any of the three outputs may be NULL. */
+int dfb200_q_sample_backward(int B, int N, int T, const float* sched, const int* t, const float* variance,
+                             const float* noise, const float* grad_x_t, float* grad_x_start, float* grad_anchors,
+                             float* grad_variance, dfb200_stream_t stream);
+
 /* Library self-test of the tcgen05 building blocks the bf16 denoiser is made of (canonical K-major
  * UMMA shared-memory tiles, cp.async.bulk staging, TMEM alloc/store/load, accumulate onto pre-stored
  * TMEM, bias as an extra MMA against a ones tile): D[128,N] = Cin + A[128,K].W[N,K]^T + bias with bf16

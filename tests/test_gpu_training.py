@@ -1,0 +1,108 @@
+"""-m gpu: the differentiable training path (difffacto_b200/train_ops.py over csrc/train_ops.cu) against torch autograd
+run over the oracle's PyTorch port of the reference on the CPU.
+
+Tolerances: forward eps 1e-4 abs; gradients 2e-3 relative to the largest entry of each tensor (fp32 accumulation order;
+weight gradients are reductions over B*N tokens with split-K atomics)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser_ref as R
+
+pytestmark = pytest.mark.gpu
+from test_gpu_denoiser import DIFF_CFG  # noqa: E402
+
+
+def _build(T=100, dropout=None):
+    import difffacto_b200 as D
+    cfg = dict(DIFF_CFG)
+    if dropout is not None:
+        cfg["net"] = dict(cfg["net"], dropout=dropout)
+    d = D.build_from_cfg(cfg, D.DIFFUSIONS, num_timesteps=T)
+    d.model.load_state_dict(R.synthetic_state_dict(1234), strict=True)
+    return d.cuda()
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+@pytest.mark.parametrize("case", [(11, 3, 64, False), (12, 2, 256, True)])
+def test_training_loss_and_gradients_match_autograd_of_the_port(case):
+    seed, B, N, av = case
+    d = _build().eval()  # eval(): dropout off (the reference's dropout consumes torch's RNG and cannot be reproduced)
+    inp = R.synthetic_inputs(seed, B, N, av)
+    s = R.schedule(100)
+    # ---- reference side: torch autograd over the CPU port ----
+    sd = {k: v.clone().requires_grad_(True) for k, v in R.synthetic_state_dict(1234).items()}
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("x", "anchors", "variance", "code", "params")}
+    x_t = R.q_sample(s, leaves["x"], inp["t"], leaves["anchors"], leaves["variance"], inp["noise"])
+    eps = R.denoiser_forward(sd, x_t, inp["t"], [leaves["code"], leaves["params"]], leaves["anchors"], leaves["variance"], inp["valid"],
+                             inp["assign"])
+    flags = torch.ones(B, 1, N)
+    loss_ref = (((inp["noise"] - eps) ** 2) * flags).mean(1).sum() / flags.sum()
+    loss_ref.backward()
+    # ---- ours ----
+    g = {k: inp[k].cuda().requires_grad_(True) for k in ("x", "anchors", "variance", "code", "params")}
+    out = d.training_losses(g["x"], inp["t"].cuda(), anchors=g["anchors"], variance=g["variance"], ctx=[g["code"], g["params"]],
+                            anchor_assignment=inp["assign"].cuda(), valid_id=inp["valid"].cuda(), flags=flags.cuda(),
+                            noise=inp["noise"].cuda())
+    loss = out["mse_loss"]
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    loss.backward()
+    for k in g:
+        assert g[k].grad is not None, k
+        assert _rel(g[k].grad.cpu(), leaves[k].grad) < 2e-3, (k, _rel(g[k].grad.cpu(), leaves[k].grad))
+    ours = dict(d.model.named_parameters())
+    assert set(ours) == set(sd)
+    worst = max((_rel(ours[k].grad.cpu(), sd[k].grad), k) for k in sd)
+    assert worst[0] < 2e-3, worst
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in d.model.parameters())
+
+
+def test_training_forward_equals_inference_kernels():
+    d = _build().eval()
+    i = {k: v.cuda() for k, v in R.synthetic_inputs(12, 2, 256, True).items()}
+    kw = dict(anchors=i["anchors"].transpose(1, 2), anchor_assignment=i["assign"], variances=i["variance"].transpose(1, 2), valid_id=i["valid"])
+    d.model.precision = "fp32"
+    with torch.no_grad():
+        ref = d.model(i["x"], i["t"], [i["code"], i["params"]], **kw)
+    tr = d.model(i["x"], i["t"], [i["code"], i["params"]], **kw)  # grad enabled -> composed differentiable path
+    assert tr.requires_grad and (tr - ref).abs().max().item() < 1e-4
+
+
+def test_sgemm_layouts_and_split_k():
+    from difffacto_b200 import train_ops as T
+    torch.manual_seed(0)
+    for (M, N, K) in [(70, 13, 131), (300, 128, 522), (1000, 3, 128), (257, 1024, 128)]:
+        x = torch.randn(M, K, device="cuda", requires_grad=True)
+        w = torch.randn(N, K, device="cuda", requires_grad=True)
+        b = torch.randn(N, device="cuda", requires_grad=True)
+        r = torch.randn(M, N, device="cuda", requires_grad=True)
+        y = T.linear(x, w, b, r)
+        yr = torch.nn.functional.linear(x.double(), w.double(), b.double()) + r.double()
+        assert (y.double() - yr).abs().max().item() < 1e-3
+        go = torch.randn(M, N, device="cuda")
+        y.backward(go)
+        gx, gw, gb = torch.autograd.grad(yr, (x, w, b), go.double())
+        assert _rel(x.grad.double(), gx) < 1e-5 and _rel(w.grad.double(), gw) < 1e-5 and _rel(b.grad.double(), gb) < 1e-5
+        assert torch.equal(r.grad, go)
+
+
+def test_dropout_mask_statistics_and_backward():
+    from difffacto_b200 import train_ops as T
+    torch.manual_seed(3)
+    x = torch.ones(1 << 20, device="cuda", requires_grad=True)
+    y = T.dropout(x, 0.2, True)
+    kept = (y != 0).float().mean().item()
+    assert abs(kept - 0.8) < 5e-3 and torch.allclose(y[y != 0], torch.tensor(1.25, device="cuda"))
+    y.sum().backward()
+    assert torch.equal(x.grad != 0, y.detach() != 0)         # the backward pass regenerates the same mask
+    assert T.dropout(x, 0.2, False) is x and T.dropout(x, 0.0, True) is x
+    d = _build(dropout=0.2).train()
+    i = {k: v.cuda() for k, v in R.synthetic_inputs(12, 2, 256, True).items()}
+    torch.manual_seed(7)
+    a = d.training_losses(i["x"], i["t"], anchors=i["anchors"], variance=i["variance"], ctx=[i["code"], i["params"]],
+                          anchor_assignment=i["assign"], valid_id=i["valid"], flags=torch.ones(2, 1, 256, device="cuda"), noise=i["noise"])
+    a["mse_loss"].backward()
+    assert torch.isfinite(a["mse_loss"]) and all(torch.isfinite(p.grad).all() for p in d.model.parameters())
