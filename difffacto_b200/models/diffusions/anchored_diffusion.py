@@ -289,6 +289,10 @@ class AnchoredDiffusion(Module):
                                               stream()))
         return (x, traj) if traj_interval else x
 
+    def forward(self, x_start, t, **kw):
+        """nn.Module entry (used under DistributedDataParallel): the training loss dict."""
+        return self.training_losses(x_start, t, **kw)
+
     # ---- training objective: differentiable through difffacto_b200/train_ops.py (fp32 kernels) --------
     def training_losses(self, x_start, t, anchors=None, variance=None, ctx=None, reduce=True, anchor_assignment=None,
                         valid_id=None, flags=None, noise=None):

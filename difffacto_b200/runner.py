@@ -1,11 +1,14 @@
-"""Runner for the sampling entry point (`tools/run_net.py --task val`), B200 path.
+"""Runner for the entry point (`tools/run_net.py --task val|train`), B200 path.
 
 Counterpart of the slice of the reference Runner that the generation configs exercise
 (python/difffacto/runner/runner.py:18-133 build/resume, :351-379 val): build the model pieces from the config
 through the registries, restore `diffusion.model.*` weights from a reference checkpoint if one is given, sample
 every conditioning batch with the fused reverse process, gather across ranks and save `results.npz` under
-work_dir.  Only the sampling path is built: the encoder/stylizer that produces the conditioning is out of scope
-(DESIGN.md section 6), so conditioning batches come from the registered dataset."""
+work_dir.  `--task train` (reference :135-230 train loop, :470-489 save) trains the cross-diffusion denoiser on the
+differentiable path (difffacto_b200/train_ops.py): optimizer / max_norm / intervals from the config, one process per GPU
+with DistributedDataParallel gradient all-reduce over NCCL, checkpoints in the reference's layout.  The encoder /
+stylizer that produces the conditioning is out of scope, so conditioning batches - and, for
+training, the target clouds - come from the registered dataset."""
 import os
 import time
 
@@ -82,5 +85,71 @@ class Runner:
             print(f"[Runner] sampled {n} shapes x {results[0]['pred'].shape[1]} points, T={self.num_timesteps} in {time.time() - t0:.2f}s -> {path}")
         return results
 
-    def run(self):
-        raise NotImplementedError("training is outside the B200 sampling build (DESIGN.md section 6)")
+    # ---- training of the diffusion denoiser -----------------------------------------------------------
+    def save(self, epoch, it, optimizer):
+        """Checkpoint in the reference's layout (runner.py:470-489): 'model' holds `diffusion.*` keys, 'decoder' the
+        diffusion state_dict, plus meta / optimizer."""
+        sd = self.diffusion.state_dict()
+        data = {"meta": {"epoch": epoch, "iter": it, "config": self.cfg.dump()},
+                "model": {f"diffusion.{k}": v for k, v in sd.items()}, "decoder": sd, "optimizer": optimizer.state_dict()}
+        path = os.path.join(self.work_dir, "checkpoints", f"ckpt_{epoch}.pth")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save(data, path)
+        return path
+
+    def run(self, max_iters=None):
+        """Epsilon-objective training of `diffusion.model` (anchored_diffusion.py:760-852) on the dataset's batches:
+        x_0 ~ per-part Gaussians N(mean_p, diag(var_p)) around the conditioning, uniform t."""
+        cfg = self.cfg
+        ds = build_from_cfg(cfg.dataset.train, DATASETS) if cfg.dataset and cfg.dataset.train else self.val_dataset
+        assert ds is not None, "config has no dataset.train"
+        self.diffusion.train()
+        model = self.diffusion
+        if self.world > 1:  # DDP all-reduces the gradients the autograd Functions hand to the parameters
+            model = torch.nn.parallel.DistributedDataParallel(self.diffusion, device_ids=[self.device.index])
+        ocfg = dict(cfg.optimizer.dump()) if cfg.optimizer else dict(type="Adam", lr=2e-3, weight_decay=0.)
+        opt = getattr(torch.optim, ocfg.pop("type"))(self.diffusion.parameters(), **ocfg)
+        max_epoch = int(cfg.max_epoch or 1)
+        max_norm, log_interval, ckpt_interval = cfg.max_norm, int(cfg.log_interval or 50), int(cfg.checkpoint_interval or 500)
+        torch.manual_seed(self.seed + self.rank)  # reference: seed + local_rank (runner.py:39)
+        it, losses = 0, []
+        for epoch in range(max_epoch):
+            for bi in range(len(ds)):
+                B = ds.batch_size
+                lo, hi = shard_range(B, self.rank, self.world)
+                b = {k: v.to(self.device) for k, v in ds.batch(bi + epoch * len(ds), lo, hi).items()}
+                x0 = torch.sqrt(b["variance"]) * torch.randn_like(b["anchors"]) + b["anchors"]
+                t = torch.randint(0, self.num_timesteps, (hi - lo,), device=self.device)
+                flags = torch.ones(hi - lo, 1, x0.shape[2], device=self.device)
+                opt.zero_grad(set_to_none=True)
+                # DDP hooks fire on the wrapped module's forward: route the loss through it
+                loss = _LossModule.forward_through(model, self.diffusion, x0, t, b, flags)
+                loss.backward()
+                if max_norm:
+                    torch.nn.utils.clip_grad_norm_(self.diffusion.parameters(), max_norm)
+                opt.step()
+                it += 1
+                losses.append(loss.detach())
+                if it % log_interval == 0 and self.rank == 0:
+                    print(f"[Runner] epoch {epoch} iter {it} mse_loss {torch.stack(losses[-log_interval:]).mean().item():.5f}")
+                if max_iters is not None and it >= max_iters:
+                    break
+            if ((epoch + 1) % ckpt_interval == 0 or epoch + 1 == max_epoch or (max_iters is not None and it >= max_iters)) and self.rank == 0:
+                self.save(epoch + 1, it, opt)
+            if max_iters is not None and it >= max_iters:
+                break
+        self.diffusion.eval()
+        return torch.stack(losses).cpu()
+
+
+class _LossModule:
+    """DistributedDataParallel synchronises gradients for the autograd graph built by ITS forward(); AnchoredDiffusion's
+    forward is the training loss (as AnchorDiffAE.forward calls diffusion.training_losses, anchor_gen.py:1020-1037)."""
+
+    @staticmethod
+    def forward_through(wrapped, diffusion, x0, t, b, flags):
+        kw = dict(anchors=b["anchors"], variance=b["variance"], ctx=[b["code"], b["params"]], anchor_assignment=b["assign"],
+                  valid_id=b["valid"], flags=flags)
+        if wrapped is diffusion:
+            return diffusion.training_losses(x0, t, **kw)["mse_loss"]
+        return wrapped(x0, t, **kw)["mse_loss"]

@@ -1,0 +1,83 @@
+"""-m gpu: the tools/run_net.py tasks through the Runner on a small synthetic config: `val` (sampling, results file) and
+`train` (denoiser training on the differentiable path, reference checkpoint layout)."""
+import os
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def small_cfg(tmp_path):
+    from difffacto_b200.config import init_cfg
+    p = tmp_path / "small.py"
+    p.write_text(textwrap.dedent(f"""
+        _base_ = '{ROOT}/configs/train_chair_stage1.py'
+        model = dict(num_timesteps=8, npoints=256)
+        dataset = dict(train=dict(type="SyntheticPartSeg", batch_size=4, npoints=256, n_parts=4, num_batches=3, seed=1),
+                       val=dict(type="SyntheticPartSeg", batch_size=4, npoints=256, n_parts=4, num_batches=1, seed=0))
+        max_epoch = 2
+        checkpoint_interval = 1
+        log_interval = 2
+        work_dir = '{tmp_path}/work'
+    """))
+    init_cfg(str(p))
+    return tmp_path
+
+
+def test_train_task_updates_weights_and_writes_reference_layout_checkpoint(small_cfg):
+    import difffacto_b200  # noqa: F401
+    import difffacto_b200.datasets  # noqa: F401
+    from difffacto_b200.runner import Runner
+    r = Runner("cuda:0", None)
+    before = {k: v.clone() for k, v in r.diffusion.state_dict().items()}
+    losses = r.run()
+    assert losses.numel() == 6 and torch.isfinite(losses).all()
+    after = r.diffusion.state_dict()
+    changed = sum(not torch.equal(before[k], after[k]) for k in before)
+    assert changed == len(before) == 77
+    ck = torch.load(os.path.join(str(small_cfg), "work", "checkpoints", "ckpt_2.pth"), map_location="cpu")
+    assert set(ck) >= {"meta", "model", "decoder", "optimizer"} and ck["meta"]["iter"] == 6
+    assert all(k.startswith("diffusion.model.") for k in ck["model"])
+    # the checkpoint restores through the key-tolerant loader (as a reference checkpoint would)
+    r2 = Runner("cuda:0", None)
+    r2.load(os.path.join(str(small_cfg), "work", "checkpoints", "ckpt_2.pth"))
+    assert all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(r2.diffusion.state_dict().values(), after.values()))
+
+
+def test_training_reduces_the_loss_on_a_fixed_batch():
+    """40 Adam steps on one batch: the epsilon loss keeps falling (end-to-end check of the gradient path)."""
+    import difffacto_b200 as D
+    from difffacto_b200.config import Config
+    from difffacto_b200.datasets import SyntheticPartSeg
+    cfg = Config(os.path.join(ROOT, "configs", "gen_chair.py"))
+    d = D.build_from_cfg(cfg.model.diffusion, D.DIFFUSIONS, num_timesteps=50).cuda().eval()
+    b = {k: v.cuda() for k, v in SyntheticPartSeg(batch_size=4, npoints=256).batch(0).items()}
+    torch.manual_seed(0)
+    x0 = torch.sqrt(b["variance"]) * torch.randn_like(b["anchors"]) + b["anchors"]
+    noise, t = torch.randn_like(x0), torch.randint(0, 50, (4,), device="cuda")
+    opt = torch.optim.Adam(d.parameters(), lr=1e-3)
+    hist = []
+    for _ in range(40):
+        opt.zero_grad()
+        loss = d.training_losses(x0, t, anchors=b["anchors"], variance=b["variance"], ctx=[b["code"], b["params"]],
+                                 anchor_assignment=b["assign"], valid_id=b["valid"], flags=torch.ones(4, 1, 256, device="cuda"),
+                                 noise=noise)["mse_loss"]
+        loss.backward()
+        opt.step()
+        hist.append(loss.item())
+    assert hist[-1] < 0.65 * hist[0] and hist[-1] < hist[20] < hist[5], hist[::8]
+
+
+def test_val_task_writes_results(small_cfg):
+    import difffacto_b200  # noqa: F401
+    import difffacto_b200.datasets  # noqa: F401
+    from difffacto_b200.runner import Runner
+    r = Runner("cuda:0", None)
+    res = r.val()
+    assert res[0]["pred"].shape == (4, 256, 3) and np.isfinite(res[0]["pred"]).all()
+    assert os.path.exists(os.path.join(str(small_cfg), "work", "results.npz"))

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Entry point with the reference's CLI (tools/run_net.py:8-124): --config-file, --task, --prefix, --launcher, --seed ...
-`--task val` runs reverse-diffusion sampling on the B200 path; the other tasks of the reference are outside this build."""
+`--task val` runs reverse-diffusion sampling on the B200 path, `--task train` trains the diffusion denoiser; the other tasks of
+the reference are outside this build."""
 import argparse
 import os
 import sys
@@ -11,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser(description="DiffFacto sampling on B200")
     ap.add_argument("--config-file", default="", metavar="FILE", type=str)
-    ap.add_argument("--task", default="val", type=str, help="train,val,val_gen,interpolation (only val is built here)")
+    ap.add_argument("--task", default="val", type=str, help="train,val,val_gen,interpolation (val and train are built here)")
     ap.add_argument("--prefix", default="", type=str)
     ap.add_argument("--launcher", choices=["none", "pytorch"], default="none")
     ap.add_argument("--local_rank", type=int, default=0)
@@ -45,8 +46,10 @@ def main():
     runner = Runner(f"cuda:{local}", args)
     if args.task == "val":
         runner.val()
+    elif args.task == "train":
+        runner.run()
     else:
-        raise SystemExit(f"--task {args.task} is outside the B200 sampling build (only val)")
+        raise SystemExit(f"--task {args.task} is outside the B200 build (val: sampling, train: denoiser training)")
     if distributed:
         dist.destroy_process_group()
 
