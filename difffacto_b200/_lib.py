@@ -61,6 +61,12 @@ SIGNATURES = {
     "dfb200_timestep_embedding": (c_int, [c_int, P, P, P, P]),
     "dfb200_dropout": (c_int, [c_size_t, c_float, c_u64, c_u64, P, P, P, P]),
     "dfb200_q_sample_backward": (c_int, [c_int] * 3 + [P] * 9),
+    "dfb200_layernorm_forward": (c_int, [ctypes.c_longlong, c_int, P, P, P, P, P]),
+    "dfb200_relu": (c_int, [c_size_t, P, P]),
+    "dfb200_scale": (c_int, [c_size_t, c_float, P, P, P]),
+    "dfb200_exp_shift": (c_int, [c_size_t, c_float, P, P, P]),
+    "dfb200_coupling_reverse": (c_int, [c_int, c_int, P, P, c_int, P]),
+    "dfb200_token_attention": (c_int, [c_int] * 4 + [P] * 6),
     "dfb200_ddim_step": (c_int, [c_int] * 3 + [P] * 9 + [c_float, P, P, P]),
     "dfb200_guidance_mix": (c_int, [c_size_t, c_float, P, P, P, P]),
     "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),

@@ -1,0 +1,1 @@
+from .part_encoders import PartAlignerTransformer, PartEncoderForTransformerDecoder, build_latent_flow  # noqa: F401

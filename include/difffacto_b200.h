@@ -255,6 +255,22 @@ int dfb200_q_sample_backward(int B, int N, int T, const float* sched, const int*
                              const float* noise, const float* grad_x_t, float* grad_x_start, float* grad_anchors,
                              float* grad_variance, dfb200_stream_t stream);
 
+/* ---- encoder side of sampling (PartEncoder.sample_latents, part_encoders.py:1052-1110): forward-only helpers used with
+ * dfb200_sgemm / dfb200_geglu_forward / dfb200_gather_points by difffacto_b200/models/encoders/part_encoders.py ---- */
+/* nn.LayerNorm(D, eps 1e-5) over M rows, any D. */
+int dfb200_layernorm_forward(long long M, int D, const float* x, const float* gamma, const float* beta, float* y,
+                             dfb200_stream_t stream);
+int dfb200_relu(size_t count, float* x_inplace, dfb200_stream_t stream);
+int dfb200_scale(size_t count, float alpha, const float* x, float* y, dfb200_stream_t stream);        /* y = alpha x */
+int dfb200_exp_shift(size_t count, float shift, const float* x, float* y, dfb200_stream_t stream);    /* y = exp(x + shift) */
+/* CouplingLayer reverse (encoders/flow.py:24-45): target[:, :d] (leading dimension ld, in place) =
+ * (target - s_t[:, d:]) / sigmoid(s_t[:, :d] + 2);  s_t (B, 2d). */
+int dfb200_coupling_reverse(int B, int d, const float* s_t, float* target, int ld, dfb200_stream_t stream);
+/* Multi-head self-attention among n_tok <= 8 tokens (attention.py:179-204 with context = x): q/k/v/out
+ * (Bt, n_tok, heads*d_head), valid (Bt, n_tok) masks keys, may be NULL. */
+int dfb200_token_attention(int Bt, int n_tok, int heads, int d_head, const float* q, const float* k, const float* v,
+                           const float* valid, float* out, dfb200_stream_t stream);
+
 /* Library self-test of the tcgen05 building blocks the bf16 denoiser is made of (canonical K-major
  * UMMA shared-memory tiles, cp.async.bulk staging, TMEM alloc/store/load, accumulate onto pre-stored
  * TMEM, bias as an extra MMA against a ones tile): D[128,N] = Cin + A[128,K].W[N,K]^T + bias with bf16

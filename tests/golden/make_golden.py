@@ -215,8 +215,47 @@ def eval_golden():
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
 
+def latents_golden():
+    """PartEncoderForTransformerDecoder.sample_latents of the REAL reference (configs/gen_chair.py encoder block, weights
+    from oracle.latents_ref.synthetic_encoder_state_dict) -> latents_golden.npz (outputs only)."""
+    import contextlib, io
+    from oracle import latents_ref as L
+    import_reference()
+    m = types.ModuleType("difffacto.models.encoders")
+    m.__path__ = [REF + "/models/encoders"]
+    sys.modules["difffacto.models.encoders"] = m
+    pe = importlib.import_module("difffacto.models.encoders.part_encoders")
+    from difffacto.utils.registry import ENCODERS, build_from_cfg
+    sys.path.insert(0, "/root/reference/configs")
+    cfg = dict(importlib.import_module("gen_chair").model["encoder"])
+    sys.path.pop(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = build_from_cfg(cfg, ENCODERS).eval()
+    sd = L.synthetic_encoder_state_dict(77)
+    res = enc.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("encoder.") for k in res.missing_keys), res
+    out = {"param_names": np.array(sorted(sd))}
+    g = torch.Generator().manual_seed(5)
+    for tag, (B, K, npts, fixed) in {"a": (3, 2, 256, [0, 0, 0, 0]), "b": (2, 3, 128, [0, 1, 0, 0])}.items():
+        prior = torch.randn(B, 256, 4, generator=g)
+        noise = torch.randn(B * K, 32, generator=g)
+        valid = torch.tensor([[1, 1, 1, 1], [1, 0, 1, 1], [0, 1, 1, 0]][:B], dtype=torch.float32)
+        with FixedNoise([prior, noise]), contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+            ctx, mpp, lpp, seg, vid, extra = enc.sample_latents(B, npts, "cpu", fixed_id=torch.tensor(fixed, dtype=torch.float32),
+                                                                valid_id=valid.clone(), K=K)
+        out.update({f"{tag}_prior": prior.numpy(), f"{tag}_noise": noise.numpy(), f"{tag}_valid_in": valid.numpy(),
+                    f"{tag}_ctx0": ctx[0].numpy(), f"{tag}_ctx1": ctx[1].numpy(), f"{tag}_mean_pp": mpp.numpy(),
+                    f"{tag}_logvar_pp": lpp.numpy(), f"{tag}_seg": seg.numpy(), f"{tag}_valid": vid.numpy(),
+                    f"{tag}_mean": extra[1].numpy(), f"{tag}_logvar": extra[2].numpy()})
+    path = os.path.join(HERE, "latents_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "eval":
+    if len(sys.argv) > 1 and sys.argv[1] == "latents":
+        latents_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "eval":
         eval_golden()
     else:
         main()
