@@ -1,6 +1,6 @@
 # Chair generation, B200 build.  Same keys / values as the sampling-relevant part of the reference's
-# configs/gen_chair.py (model.diffusion block :48-85, num_timesteps / npoints :88-89); the encoder and the
-# ShapeNet dataset are outside the hot path, so synthetic part-segmented clouds stand in for them.
+# configs/gen_chair.py (model.encoder :6-46 - generation path only -, model.diffusion :48-85, num_timesteps / npoints
+# :88-89); the ShapeNet dataset is outside this build, so synthetic part-segmented clouds stand in for it (--task val).
 # The reference's own configs (/root/reference/configs/*.py) load unmodified through difffacto_b200.config.
 denoiser = dict(
     type='TransformerNet',
@@ -15,6 +15,17 @@ denoiser = dict(
 
 model = dict(
     type='AnchorDiffAE',
+    encoder=dict(                 # reference configs/gen_chair.py:6-46; only its generation path (sample_latents) is built here
+        type='PartEncoderForTransformerDecoder',
+        encoder=dict(type='PointNetV2', zdim=256, point_dim=3, per_part_mlp=True),
+        part_aligner=dict(
+            type="PartAlignerTransformer", in_channels=256, out_channels=6, n_class=4, d_head=32, depth=5, n_heads=8, dropout=0.,
+            use_checkpoint=False, use_linear=True, class_cond=True, single_attn=True, add_class_cond=True, cimle=True,
+            noise_scale=100, cond_noise_type=0),
+        n_class=4, kl_weight=0, fit_loss_type=4, fit_loss_weight=1.0, use_flow=True, latent_flow_depth=14,
+        latent_flow_hidden_dim=256, include_z=False, include_part_code=True, include_params=True, use_gt_params=False,
+        kl_weight_annealing=False, gen=True, prior_var=1.0,
+    ),
     diffusion=dict(
         type='AnchoredDiffusion',
         net=denoiser,

@@ -18,7 +18,12 @@ import torch.distributed as dist
 
 from .config import get_cfg
 from .parallel import gather_shapes, rank_seed, shard_range
-from .utils.registry import DATASETS, DIFFUSIONS, build_from_cfg
+from .utils.registry import DATASETS, DIFFUSIONS, ENCODERS, build_from_cfg
+
+# part-presence distribution of ShapeNet chairs (reference datasets/dataset_utils.py:170-179)
+shapenet_chair_part_distribution = {
+    '1110': 0.7209302325581395, '1111': 0.2630199803471995, '1101': 0.009498853586636095, '1001': 0.00032754667540124465,
+    '1100': 0.002947920078611202, '0111': 0.0013101867016049786, '0110': 0.0016377333770062235, '1011': 0.00032754667540124465}
 
 
 class Runner:
@@ -36,6 +41,9 @@ class Runner:
         if cfg.precision:
             self.diffusion.model.precision = cfg.precision
         self.diffusion = self.diffusion.to(self.device).eval()
+        self.encoder = None
+        if m.encoder and m.encoder.type in ENCODERS:  # generation from the prior (`--task val_gen`): latent flows + part aligner
+            self.encoder = build_from_cfg(m.encoder, ENCODERS).to(self.device).eval()
         self.val_dataset = build_from_cfg(cfg.dataset.val, DATASETS) if cfg.dataset and cfg.dataset.val else None
         self.work_dir = cfg.work_dir
         if cfg.resume_path and os.path.exists(cfg.resume_path):
@@ -55,6 +63,16 @@ class Runner:
                 picked[k] = v
         missing = sorted(set(own) - set(picked))
         self.diffusion.load_state_dict(picked, strict=False)
+        if self.encoder is not None:  # `encoder.part_aligner.*`, `encoder.flow.*` of the same checkpoint
+            eown = self.encoder.state_dict()
+            epick = {}
+            for k, v in sd.items():
+                k = k[len("module."):] if k.startswith("module.") else k
+                k = k[len("encoder."):] if k.startswith("encoder.") else k
+                if k in eown and tuple(eown[k].shape) == tuple(v.shape):
+                    epick[k] = v
+            self.encoder.load_state_dict(epick, strict=False)
+            print(f"[Runner] restored {len(epick)}/{len(eown)} encoder tensors")
         print(f"[Runner] restored {len(picked)}/{len(own)} tensors from {path}" + (f"; missing {missing[:4]}..." if missing else ""))
 
     @torch.no_grad()
@@ -83,6 +101,37 @@ class Runner:
             np.savez_compressed(path, **{f"batch{i}_{k}": v for i, r in enumerate(results) for k, v in r.items()})
             n = sum(r["pred"].shape[0] for r in results)
             print(f"[Runner] sampled {n} shapes x {results[0]['pred'].shape[1]} points, T={self.num_timesteps} in {time.time() - t0:.2f}s -> {path}")
+        return results
+
+    @torch.no_grad()
+    def generate_samples(self, num_gen, param_sample_num=1, batch_size=None, rng="philox"):
+        """`--task val_gen` (reference runner.py:399-438): part-presence masks drawn from the ShapeNet-chair distribution,
+        latents from the prior through the encoder's flows and part aligner (`sample_latents`, K = param_sample_num
+        parameter draws per latent), then the fused reverse process.  Returns / saves {'pred', 'seg_mask_ref'}."""
+        assert self.encoder is not None, "config has no model.encoder this build can construct"
+        B = batch_size or (self.val_dataset.batch_size if self.val_dataset is not None else 32)
+        keys = list(shapenet_chair_part_distribution)
+        valid_ids = torch.tensor([[float(c) for c in k] for k in keys], device=self.device)
+        probs = torch.tensor([shapenet_chair_part_distribution[k] for k in keys])
+        torch.manual_seed(self.seed + self.rank)
+        results = dict(pred=[], seg_mask_ref=[])
+        npoints = int(self.cfg.model.npoints or 2048)
+        for bi in range(max(1, num_gen // B)):
+            valid_id = valid_ids[torch.multinomial(probs, B, replacement=True).to(self.device)]
+            ctx, mean_pp, logvar_pp, seg, vid, _ = self.encoder.sample_latents(B, npoints, self.device, fixed_id=torch.zeros(4, device=self.device),
+                                                                              valid_id=valid_id, K=param_sample_num)
+            from .models.encoders.part_encoders import _exp_shift
+            variance = _exp_shift(logvar_pp)
+            x0 = self.diffusion.p_sample_loop(list(mean_pp.shape), mean_pp, ctx=ctx, variance=variance, anchor_assignment=seg, valid_id=vid,
+                                              rng=rng, seed=rank_seed(self.seed * 7919 + bi, self.rank))
+            results["pred"].append(x0.transpose(1, 2).contiguous().cpu().numpy())
+            results["seg_mask_ref"].append(seg.cpu().numpy())
+        results = {k: np.concatenate(v, axis=0) for k, v in results.items()}
+        if self.rank == 0:
+            os.makedirs(os.path.join(self.work_dir, "val"), exist_ok=True)
+            path = os.path.join(self.work_dir, "val", "gen_fixed0000.npz")
+            np.savez_compressed(path, **results)
+            print(f"[Runner] generated {results['pred'].shape[0]} shapes -> {path}")
         return results
 
     # ---- training of the diffusion denoiser -----------------------------------------------------------

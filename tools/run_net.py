@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--no_cuda", action="store_true")
     ap.add_argument("--sync_bn", action="store_true")
     ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--gen_num", type=int, default=32)
+    ap.add_argument("--param_sample_num", type=int, default=1)
     ap.add_argument("--num_timesteps", type=int, default=None, help="override model.num_timesteps (e.g. 1000)")
     args = ap.parse_args()
     if args.no_cuda:
@@ -48,8 +50,10 @@ def main():
         runner.val()
     elif args.task == "train":
         runner.run()
+    elif args.task == "val_gen":
+        runner.generate_samples(args.gen_num, args.param_sample_num)
     else:
-        raise SystemExit(f"--task {args.task} is outside the B200 build (val: sampling, train: denoiser training)")
+        raise SystemExit(f"--task {args.task} is outside the B200 build (val: sampling, val_gen: generation from the prior, train: denoiser training)")
     if distributed:
         dist.destroy_process_group()
 
