@@ -460,6 +460,57 @@ three_interpolate_kernel(int c, int m, int n, int c_per_block, const float* __re
   }
 }
 
+// Shared-memory staged variant (same idea as group_points_c4_kernel): per quad of channels the m source columns are staged
+// interleaved in shared memory (one float4 = 4 channels per source point), so each of the 3 neighbours costs ONE random
+// LDS.128 for 4 channels and the gathers never leave the SM; a thread owns TI_PPT query points (idx / weights in registers
+// for the whole channel tile) and the 4 output rows are written with coalesced streaming stores.  (A variant with 4
+// consecutive points per thread and STG.128 stores measured slower: its idx/weight loads are 48-byte strided.)
+constexpr int TI_THREADS = 256, TI_PPT = 4;
+__global__ void __launch_bounds__(TI_THREADS)
+three_interpolate_c4_kernel(int c, int m, int n, int quads_per_block, const float* __restrict__ points,
+                            const int* __restrict__ idx, const float* __restrict__ weight, float* __restrict__ out) {
+  extern __shared__ float4 ti_tile[];  // [m]
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int nquad = (c + 3) >> 2;
+  const int q0 = blockIdx.y * quads_per_block, q1 = min(nquad, q0 + quads_per_block);
+  const float* pts = points + (size_t)b * c * m;
+  float* o = out + (size_t)b * c * n;
+  int i1[TI_PPT], i2[TI_PPT], i3[TI_PPT];
+  float w1[TI_PPT], w2[TI_PPT], w3[TI_PPT];
+  bool ok[TI_PPT];
+#pragma unroll
+  for (int u = 0; u < TI_PPT; ++u) {
+    const int j = (blockIdx.x * TI_PPT + u) * TI_THREADS + tid;  // consecutive threads -> consecutive points (coalesced stores)
+    ok[u] = j < n;
+    const int* ii = idx + ((size_t)b * n + (ok[u] ? j : 0)) * 3;
+    const float* ww = weight + ((size_t)b * n + (ok[u] ? j : 0)) * 3;
+    i1[u] = __ldg(ii); i2[u] = __ldg(ii + 1); i3[u] = __ldg(ii + 2);
+    w1[u] = __ldg(ww); w2[u] = __ldg(ww + 1); w3[u] = __ldg(ww + 2);
+  }
+  for (int q = q0; q < q1; ++q) {
+    const int l0 = q * 4, nl = min(4, c - l0);
+    const float* r0 = pts + (size_t)l0 * m;
+    const float* r1 = r0 + (nl > 1 ? m : 0);
+    const float* r2 = r0 + (nl > 2 ? 2 * (size_t)m : 0);
+    const float* r3 = r0 + (nl > 3 ? 3 * (size_t)m : 0);
+    __syncthreads();
+    for (int i = tid; i < m; i += TI_THREADS) ti_tile[i] = make_float4(__ldg(r0 + i), __ldg(r1 + i), __ldg(r2 + i), __ldg(r3 + i));
+    __syncthreads();
+    float* o0 = o + (size_t)l0 * n;
+#pragma unroll
+    for (int u = 0; u < TI_PPT; ++u) {
+      if (!ok[u]) continue;
+      const int j = (blockIdx.x * TI_PPT + u) * TI_THREADS + tid;
+      const float4 a = ti_tile[i1[u]], bq = ti_tile[i2[u]], cq = ti_tile[i3[u]];
+      // fma(p3,w3, fma(p1,w1, mul(p2,w2))) per channel, as in the plain kernel
+      __stcs(o0 + j, __fmaf_rn(cq.x, w3[u], __fmaf_rn(a.x, w1[u], __fmul_rn(bq.x, w2[u]))));
+      if (nl > 1) __stcs(o0 + (size_t)n + j, __fmaf_rn(cq.y, w3[u], __fmaf_rn(a.y, w1[u], __fmul_rn(bq.y, w2[u]))));
+      if (nl > 2) __stcs(o0 + 2 * (size_t)n + j, __fmaf_rn(cq.z, w3[u], __fmaf_rn(a.z, w1[u], __fmul_rn(bq.z, w2[u]))));
+      if (nl > 3) __stcs(o0 + 3 * (size_t)n + j, __fmaf_rn(cq.w, w3[u], __fmaf_rn(a.w, w1[u], __fmul_rn(bq.w, w2[u]))));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 three_interpolate_grad_kernel(int c, int n, int m, int c_per_block,
                               const float* __restrict__ grad_out, const int* __restrict__ idx,
@@ -591,6 +642,22 @@ extern "C" int dfb200_three_interpolate(int b, int c, int m, int n, const float*
   DFB_REQUIRE(b >= 0 && c >= 0 && n >= 0 && m >= 0, DFB200_ERR_INVALID_ARG, "three_interpolate: negative size");
   if (b == 0 || c == 0 || n == 0) return DFB200_OK;
   DFB_REQUIRE(m > 0, DFB200_ERR_INVALID_ARG, "three_interpolate: empty source cloud");
+  {
+    // staged path: the interleaved source tile fits in shared memory and is reused by enough outputs
+    const size_t smem = sizeof(float4) * (size_t)m;
+    if (smem <= 48 * 1024 && n >= 4 * m && c >= 4 && b <= 65535) {
+      const int gx4 = cdiv(n, TI_THREADS * TI_PPT);
+      const int nquad = (c + 3) / 4;
+      int qpb = nquad;
+      while (qpb > 1 && (long long)gx4 * b * cdiv(nquad, qpb) < 148 * 8) qpb = (qpb + 1) / 2;
+      dim3 grid4(gx4, cdiv(nquad, qpb), b);
+      if (grid4.y <= 65535) {
+        three_interpolate_c4_kernel<<<grid4, TI_THREADS, smem, as_stream(stream)>>>(c, m, n, qpb, points, idx, weight, out);
+        DFB_LAUNCH_CHECK();
+        return DFB200_OK;
+      }
+    }
+  }
   const int gx = cdiv(n, 256);
   const int cpb = channel_tile(c, (long long)gx * b);
   dim3 grid(gx, cdiv(c, cpb), b);
