@@ -51,6 +51,7 @@ SIGNATURES = {
     "dfb200_ddpm_step": (c_int, [c_int] * 3 + [P] * 10),
     "dfb200_q_sample": (c_int, [c_int] * 3 + [P] * 8),
     "dfb200_sgemm": (c_int, [c_int] * 5 + [P, c_int, P, c_int, P, c_int, P, c_int, c_int, P]),
+    "dfb200_gemm_bf16": (c_int, [c_int] * 5 + [P, c_int, P, c_int, P, c_int, P, c_int, c_int, P]),
     "dfb200_colsum_accumulate": (c_int, [ctypes.c_longlong, c_int, P, c_int, P, P]),
     "dfb200_layernorm128_forward": (c_int, [ctypes.c_longlong] + [P] * 7),
     "dfb200_layernorm128_backward": (c_int, [ctypes.c_longlong] + [P] * 9),

@@ -21,7 +21,6 @@
 //     FF-out + next FF-in.
 // TMEM map (512 columns): X0 [0,128) X1 [128,256) ACC0 [256,384) ACC1 [384,512).
 #include <float.h>
-#include <stdlib.h>
 
 #include "ddpm.cuh"
 #include "denoiser.cuh"
@@ -982,8 +981,7 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   }
   // persistent: one CTA per SM walks the (step, unit) work list; dependencies between steps of a unit go through P.done
   const long long items = (long long)p.n_units * p.n_steps;
-  int grid = (int)(items < n_sm ? items : n_sm);
-  if (const char* g = getenv("DFB200_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }  // experiment knob
+  const int grid = (int)(items < n_sm ? items : n_sm);
   denoiser_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;

@@ -110,6 +110,8 @@ class TransformerNet(nn.Module):
 
         # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulation); "fp32": CUDA-core path
         self.precision = precision or os.environ.get("DFB200_PRECISION", "bf16")
+        # training path: "fp32" (CUDA-core GEMMs, bit-faithful gradients) or "bf16" (tcgen05 GEMMs, mixed precision)
+        self.train_precision = os.environ.get("DFB200_TRAIN_PRECISION", "fp32")
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -171,7 +173,10 @@ class TransformerNet(nn.Module):
             ctx = torch.cat(list(ctx), dim=1)
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
                                         any(torch.is_tensor(a) and a.requires_grad for a in (x, ctx, anchors, variances))):
-            return self._forward_train(x, t, ctx, anchors, variances, valid_id, anchor_assignment)
+            # precision "bf16": the large Linear layers run on the tensor cores (bf16 operands, fp32 accumulation); everything
+            # else (LayerNorm, attention core, GEGLU, small GEMMs) stays fp32
+            with T.gemm_precision(getattr(self, "train_precision", None) or "fp32"):
+                return self._forward_train(x, t, ctx, anchors, variances, valid_id, anchor_assignment)
         _lib.require_cuda(x, ctx, anchors, variances, anchor_assignment, valid_id)
         B, C, N = x.shape
         assert C == self.raw_in_channels

@@ -18,10 +18,33 @@ def _c(t):
     return t.contiguous() if not t.is_contiguous() else t
 
 
-def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split_k=1):
+def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split_k=1, bf16=False):
+    """fp32 CUDA-core GEMM, or - bf16=True and the problem is big enough for 128x128x64 tensor-core tiles - the tcgen05 GEMM
+    with bf16-rounded operands and fp32 accumulation (same layout contract)."""
+    fn = "dfb200_gemm_bf16" if (bf16 and M >= 128 and N >= 64 and K >= 64) else "dfb200_sgemm"
     with torch.cuda.device(C.device):
-        check(_lib.load().dfb200_sgemm(int(a_kc), int(b_kc), M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), int(beta),
+        check(getattr(_lib.load(), fn)(int(a_kc), int(b_kc), M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), int(beta),
                                        int(split_k), stream()))
+
+
+_GEMM_BF16 = False  # set by gemm_precision(): Linear layers built inside use the tensor cores (forward AND backward)
+
+
+class gemm_precision:
+    """with gemm_precision("bf16"): ... -> LinearFn created inside runs its GEMMs (fwd, dgrad, wgrad) on the tensor cores."""
+
+    def __init__(self, precision):
+        assert precision in ("fp32", "bf16")
+        self.bf16 = precision == "bf16"
+
+    def __enter__(self):
+        global _GEMM_BF16
+        self.prev, _GEMM_BF16 = _GEMM_BF16, self.bf16
+        return self
+
+    def __exit__(self, *a):
+        global _GEMM_BF16
+        _GEMM_BF16 = self.prev
 
 
 class LinearFn(Function):
@@ -37,7 +60,8 @@ class LinearFn(Function):
             y = residual.contiguous().clone()
         else:
             y = torch.empty(M, N, device=x.device, dtype=torch.float32)
-        _sgemm(True, True, M, N, K, x, K, weight, K, y, N, bias=bias, beta=residual is not None)
+        ctx.bf16 = _GEMM_BF16
+        _sgemm(True, True, M, N, K, x, K, weight, K, y, N, bias=bias, beta=residual is not None, bf16=ctx.bf16)
         ctx.save_for_backward(x, weight)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         return y
@@ -51,12 +75,14 @@ class LinearFn(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
-            _sgemm(True, False, M, K, N, dy, N, weight, K, dx, K)            # dx(i,k) = sum_n dy(i,n) W(n,k)
+            _sgemm(True, False, M, K, N, dy, N, weight, K, dx, K, bf16=ctx.bf16)  # dx(i,k) = sum_n dy(i,n) W(n,k)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros(N, K, device=x.device, dtype=torch.float32)
-            tiles = ((N + 63) // 64) * ((K + 63) // 64)
-            split = max(1, min((M + 255) // 256, (148 * 4 + tiles - 1) // tiles))
-            _sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=split)  # dW(n,k) = sum_m dy(m,n) x(m,k)
+            tc = ctx.bf16 and N >= 128 and K >= 64 and M >= 64
+            t = 128 if tc else 64
+            tiles = ((N + t - 1) // t) * ((K + t - 1) // t)
+            split = max(1, min((M + 255) // 256, (148 * (2 if tc else 4) + tiles - 1) // tiles))
+            _sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=split, bf16=ctx.bf16)  # dW(n,k) = sum_m dy(m,n) x(m,k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.zeros(N, device=x.device, dtype=torch.float32)
             with torch.cuda.device(x.device):

@@ -225,6 +225,10 @@ int dfb200_philox_normal(float* out, size_t count, uint64_t seed, uint64_t offse
  * slices with atomicAdd (C must hold its initial value).  bias may be NULL. */
 int dfb200_sgemm(int a_k_contiguous, int b_k_contiguous, int M, int N, int K, const float* A, int lda, const float* B,
                  int ldb, float* C, int ldc, const float* bias, int beta, int split_k, dfb200_stream_t stream);
+/* The same contract on the tensor cores: operands rounded to bf16 on the fly, fp32 accumulation in tensor memory
+ * (tcgen05, 128x128 tiles).  Used for the large Linear layers of the training path when precision = "bf16". */
+int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, int N, int K, const float* A, int lda, const float* B,
+                     int ldb, float* C, int ldc, const float* bias, int beta, int split_k, dfb200_stream_t stream);
 /* out[j] += sum_i X[i*ld + j] (bias gradients; `out` accumulates). */
 int dfb200_colsum_accumulate(long long M, int N, const float* X, int ld, float* out, dfb200_stream_t stream);
 /* nn.LayerNorm(128, eps=1e-5) over M rows; mean/rstd (M) saved for the backward.  backward: dx written, dgamma/dbeta

@@ -106,3 +106,48 @@ def test_dropout_mask_statistics_and_backward():
                           anchor_assignment=i["assign"], valid_id=i["valid"], flags=torch.ones(2, 1, 256, device="cuda"), noise=i["noise"])
     a["mse_loss"].backward()
     assert torch.isfinite(a["mse_loss"]) and all(torch.isfinite(p.grad).all() for p in d.model.parameters())
+
+
+def test_tensor_core_gemm_layouts_match_bf16_reference():
+    """dfb200_gemm_bf16 (tcgen05) in the four operand layouts, edge tiles, bias, accumulate and split-K against a bf16-operand,
+    fp64-accumulate reference."""
+    from difffacto_b200 import train_ops as T
+    torch.manual_seed(1)
+    bf = lambda t: t.bfloat16().double()  # noqa: E731
+    for (M, N, K) in [(128, 128, 64), (300, 200, 136), (1000, 128, 512), (257, 1024, 128)]:
+        x, w, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda"), torch.randn(N, device="cuda")
+        c0 = torch.randn(M, N, device="cuda")
+        y = c0.clone()
+        T._sgemm(True, True, M, N, K, x, K, w, K, y, N, bias=b, beta=1, bf16=True)
+        ref = c0.double() + bf(x) @ bf(w).t() + b.double()
+        assert (y.double() - ref).abs().max().item() < 2e-3 * K ** 0.5, (M, N, K)
+        dy = torch.randn(M, N, device="cuda")
+        dx = torch.empty(M, K, device="cuda")
+        T._sgemm(True, False, M, K, N, dy, N, w, K, dx, K, bf16=True)                 # dgrad layout
+        assert (dx.double() - bf(dy) @ bf(w)).abs().max().item() < 2e-3 * N ** 0.5
+        dw = torch.zeros(N, K, device="cuda")
+        T._sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=3, bf16=True)     # wgrad layout, split-K with atomics
+        assert (dw.double() - bf(dy).t() @ bf(x)).abs().max().item() < 2e-3 * M ** 0.5
+        xt = x.t().contiguous()
+        y2 = torch.empty(M, N, device="cuda")
+        T._sgemm(False, True, M, N, K, xt, M, w, K, y2, N, bf16=True)                 # A row-contiguous, B k-contiguous
+        assert (y2.double() - bf(x) @ bf(w).t()).abs().max().item() < 2e-3 * K ** 0.5
+
+
+def test_bf16_training_gradients_close_to_fp32():
+    """precision bf16 on the training path: loss within 2e-3, gradients within 5 % (relative to each tensor's largest entry) of
+    the fp32 path - the error of bf16 operand rounding, not of the kernels (layouts are checked exactly above)."""
+    d = _build().eval()
+    inp = {k: v.cuda() for k, v in R.synthetic_inputs(12, 2, 256, True).items()}
+    flags = torch.ones(2, 1, 256, device="cuda")
+    res = {}
+    for prec in ("fp32", "bf16"):
+        d.model.train_precision = prec
+        d.zero_grad(set_to_none=True)
+        loss = d.training_losses(inp["x"], inp["t"], anchors=inp["anchors"], variance=inp["variance"], ctx=[inp["code"], inp["params"]],
+                                 anchor_assignment=inp["assign"], valid_id=inp["valid"], flags=flags, noise=inp["noise"])["mse_loss"]
+        loss.backward()
+        res[prec] = (loss.item(), {k: p.grad.clone() for k, p in d.model.named_parameters()})
+    assert abs(res["bf16"][0] - res["fp32"][0]) < 2e-3 * max(1.0, abs(res["fp32"][0]))
+    worst = max((_rel(res["bf16"][1][k], res["fp32"][1][k]), k) for k in res["fp32"][1])
+    assert worst[0] < 5e-2, worst

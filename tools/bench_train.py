@@ -7,10 +7,9 @@ import torch
 import bench
 
 B, N, T = int(sys.argv[1]) if len(sys.argv) > 1 else 16, 2048, 200
+PREC = sys.argv[2] if len(sys.argv) > 2 else "fp32"   # GEMMs of the training path: fp32 CUDA cores or bf16 tcgen05
 d = bench.build_model(T, "fp32").cuda().train()
-for m in d.modules():
-    if isinstance(m, torch.nn.Dropout):
-        pass
+d.model.train_precision = PREC
 b = {k: v.cuda() for k, v in bench.synthetic_batch(0, B, N).items()}
 x0 = (torch.sqrt(b["variance"]) * torch.randn(B, 3, N, device="cuda") + b["anchors"])
 opt = torch.optim.Adam(d.parameters(), lr=1e-4)
@@ -31,5 +30,5 @@ for it in range(14):
         ts.append(e0.elapsed_time(e1))
 ms = float(np.median(ts))
 flop = 3 * B * N * bench.FLOP_PER_POINT_STEP
-print(json.dumps({"op": "training step (denoiser fwd+bwd+Adam, fp32 CUDA-core primitives)", "batch": B, "points": N, "ms": round(ms, 2),
-                  "shapes_per_s": round(B / ms * 1e3, 1), "algorithmic_TFLOPs": round(flop / ms / 1e9, 2), "loss": float(loss)}))
+print(json.dumps({"op": f"training step (denoiser fwd+bwd+Adam, {PREC} GEMMs)", "batch": B, "points": N, "ms": round(ms, 2),
+                  "shapes_per_s": round(B / ms * 1e3, 1), "algorithmic_TFLOPs": round(flop / ms / 1e9, 2), "loss": float(loss.detach())}))
