@@ -21,7 +21,17 @@ def _c(t):
 def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split_k=1, bf16=False):
     """fp32 CUDA-core GEMM, or - bf16=True and the problem is big enough for 128x128x64 tensor-core tiles - the tcgen05 GEMM
     with bf16-rounded operands and fp32 accumulation (same layout contract)."""
-    fn = "dfb200_gemm_bf16" if (bf16 and M >= 128 and N >= 64 and K >= 64) else "dfb200_sgemm"
+    tc = bf16 and M >= 128 and N >= 64 and K >= 64
+    fn = "dfb200_gemm_bf16" if tc else "dfb200_sgemm"
+    if split_k == 1 and K >= 256:
+        # few output tiles and a long reduction (e.g. the K/V projections of the 4 part tokens: M = 4B, K = 522): split K over
+        # more CTAs (atomic accumulation onto a zeroed / residual-initialised C)
+        t = 128 if tc else 64
+        tiles = ((M + t - 1) // t) * ((N + t - 1) // t)
+        if tiles * 4 <= 148:
+            split_k = max(1, min(K // 64, 148 // tiles))
+            if split_k > 1 and not beta:
+                C.zero_()
     with torch.cuda.device(C.device):
         check(getattr(_lib.load(), fn)(int(a_kc), int(b_kc), M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), int(beta),
                                        int(split_k), stream()))

@@ -298,3 +298,30 @@ def test_ddim_loop_matches_reference(variants_golden):
     b = d.p_sample_loop([2, 3, 128], i["anchors"], ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"],
                         valid_id=i["valid"])
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,N,T", [(5, 384, 6), (1, 128, 3), (40, 2048, 4)])
+def test_bf16_fused_loop_odd_shapes_track_the_stepwise_fp32_path(B, N, T):
+    """Persistent fused loop at shapes where 256-token units straddle samples (N = 384), where a unit is half empty (B*N = 128)
+    and where the work list is longer than the SM count (B = 40): same draws, fp32 step-wise path as the reference."""
+    from difffacto_b200 import _lib
+    lib = _lib.load()
+    d = build(T, "bf16")
+    i = dev(R.synthetic_inputs(50 + B, B, N, False))
+    seed = 7
+    draws = torch.empty(T + 1, B, 3, N, device="cuda")
+    for k in range(T + 1):
+        _lib.check(lib.dfb200_philox_normal(_lib.ptr(draws[k]), B * 3 * N, seed, k, _lib.stream()))
+    a, traj = d.p_sample_loop([B, 3, N], i["anchors"], ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"],
+                              valid_id=i["valid"], rng="philox", seed=seed, traj_interval=2)
+    d32 = build(T, "fp32")
+    x = torch.sqrt(i["variance"]) * draws[T] + i["anchors"]
+    kept = {}
+    for step in range(T - 1, -1, -1):
+        tt = torch.full((B,), step, dtype=torch.long, device="cuda")
+        x = d32.p_sample(x, tt, i["anchors"], ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"],
+                         valid_id=i["valid"], noise=draws[step])["sample"]
+        kept[step] = x
+    assert torch.isfinite(a).all() and (a - x).abs().max().item() < 5e-2
+    for s_ in range(traj.shape[0]):  # trajectory slot s holds x_t for t = (s+1)*interval
+        assert (traj[s_] - kept[(s_ + 1) * 2]).abs().max().item() < 5e-2
