@@ -23,12 +23,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "shapes/sec reverse DDPM (2048 pts, 4 parts, 1000 steps)"
 UNIT = "shapes/s"
-B_PER_GPU, NPTS, T_STEPS = 32, 2048, 1000
+B_PER_GPU, NPTS, T_STEPS = int(os.environ.get("DFB200_BENCH_BATCH", "32")), 2048, 1000  # BASELINE configs[1]: 32 per GPU
 FLOP_PER_POINT_STEP = 2308096  # proj_in + 5 x (Q, QK^T, PV, out, GEGLU-in, FF-out) + proj_out
 # dram__bytes_read.sum + dram__bytes_write.sum of one persistent denoiser launch (24 sampling steps of this workload) from the
 # committed `ncu --set full` capture profiles/ncu_denoiser_tc_r1_v7.csv: 69.73 MB + 1.89 MB, i.e. per sampling step:
 NCU_DRAM_BYTES_PER_STEP = (69.734912e6 + 1.889280e6) / 24
-WORKLOAD = "gen_chair full 1000-step reverse sampling, batch=32 per GPU, 2048 pts x 4 parts"
+WORKLOAD = f"gen_chair full 1000-step reverse sampling, batch={B_PER_GPU} per GPU, 2048 pts x 4 parts"
 
 
 def peaks():

@@ -68,6 +68,14 @@ SIGNATURES = {
     "dfb200_exp_shift": (c_int, [c_size_t, c_float, P, P, P]),
     "dfb200_coupling_reverse": (c_int, [c_int, c_int, P, P, c_int, P]),
     "dfb200_token_attention": (c_int, [c_int] * 4 + [P] * 6),
+    "dfb200_batchnorm_forward": (c_int, [ctypes.c_longlong, c_int, c_int] + [P] * 8 + [c_float, P, P]),
+    "dfb200_batchnorm_apply": (c_int, [ctypes.c_longlong, c_int, c_int] + [P] * 7),
+    "dfb200_batchnorm_backward": (c_int, [ctypes.c_longlong, c_int, c_int] + [P] * 10),
+    "dfb200_relu_backward": (c_int, [c_size_t, P, P, P, P]),
+    "dfb200_weighted_maxpool_forward": (c_int, [c_int] * 4 + [c_float, P, P, P, P, P]),
+    "dfb200_weighted_maxpool_backward": (c_int, [c_int] * 4 + [c_float, P, P, P, P, P]),
+    "dfb200_coupling_forward": (c_int, [c_int, c_int, P, P, c_int, P, c_int, P, P]),
+    "dfb200_coupling_backward": (c_int, [c_int, c_int, P, P, c_int, P, c_int, P, P, P, c_int, P]),
     "dfb200_ddim_step": (c_int, [c_int] * 3 + [P] * 9 + [c_float, P, P, P]),
     "dfb200_guidance_mix": (c_int, [c_size_t, c_float, P, P, P, P]),
     "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),

@@ -474,3 +474,252 @@ extern "C" int dfb200_q_sample_backward(int B, int N, int T, const float* sched,
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }
+
+// =============================================================================================
+// Training-side encoder primitives: PointNetV2 (reference models/encoders/pointnet.py:122-214)
+// = 1x1 convolutions (dfb200_sgemm / dfb200_gemm_bf16 over the B*N point rows) + BatchNorm1d + ReLU + the anchor-weighted
+// max-pool, and the forward direction of the latent coupling flows with their log-determinant (encoders/flow.py:24-45).
+// =============================================================================================
+namespace dfb200 {
+
+// Column sums over M rows of a row-major (M, C) matrix, optionally of TWO quantities at once:
+//   mode 0 (BatchNorm forward statistics):  s1 = sum x,            s2 = sum x^2
+//   mode 1 (BatchNorm backward):            s1 = sum g,            s2 = sum g * xhat,   g = dy * (y > 0 if relu)
+// One thread per column inside a 32-column x 8-row-slice tile; partial sums land with atomicAdd.
+__global__ void __launch_bounds__(256)
+bn_colstats_kernel(long long M, int C, int mode, int relu, const float* __restrict__ x, const float* __restrict__ dy,
+                   const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   float* __restrict__ s1, float* __restrict__ s2, int rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    const float mu = mode ? __ldg(mean + c) : 0.f, rs = mode ? __ldg(rstd + c) : 0.f;
+    for (long long r = r0 + w; r < r1; r += 8) {
+      const float xv = __ldg(x + r * C + c);
+      if (mode == 0) {
+        a += xv;
+        b = fmaf(xv, xv, b);
+      } else {
+        float g = __ldg(dy + r * C + c);
+        if (relu && __ldg(y + r * C + c) <= 0.f) g = 0.f;
+        a += g;
+        b = fmaf(g, (xv - mu) * rs, b);
+      }
+    }
+  }
+  __shared__ float pa[8][33], pb[8][33];
+  pa[w][threadIdx.x & 31] = a;
+  pb[w][threadIdx.x & 31] = b;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float ta = 0.f, tb = 0.f;
+    for (int k = 0; k < 8; ++k) { ta += pa[k][threadIdx.x & 31]; tb += pb[k][threadIdx.x & 31]; }
+    atomicAdd(s1 + c, ta);
+    atomicAdd(s2 + c, tb);
+  }
+}
+
+// mean / rstd from the column sums (biased variance, eps 1e-5) and the running-statistics update of nn.BatchNorm1d
+// (momentum 0.1, unbiased variance)
+__global__ void bn_finalize_kernel(long long M, int C, const float* __restrict__ s1, const float* __restrict__ s2, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = s1[c] / (float)M;
+  const float var = fmaxf(s2[c] / (float)M - mu * mu, 0.f);
+  mean[c] = mu;
+  rstd[c] = rsqrtf(var + 1e-5f);
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * ((float)M / (float)max(M - 1, 1LL));
+  }
+}
+
+// y = (x - mean) * rstd * gamma + beta (+ ReLU)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(long long total, int C, int relu, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int c = (int)(q % C);
+  float v = (__ldg(x + q) - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(gamma + c) + __ldg(beta + c);
+  if (relu) v = fmaxf(v, 0.f);
+  y[q] = v;
+}
+
+// dx = gamma * rstd * (g - sum_g / M - xhat * sum_gx / M),  g = dy * (y > 0 if relu)
+__global__ void __launch_bounds__(256)
+bn_dx_kernel(long long total, long long M, int C, int relu, const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+             const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ sum_g,
+             const float* __restrict__ sum_gx, float* __restrict__ dx) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int c = (int)(q % C);
+  float g = __ldg(dy + q);
+  if (relu && __ldg(y + q) <= 0.f) g = 0.f;
+  const float rs = __ldg(rstd + c);
+  const float xh = (__ldg(x + q) - __ldg(mean + c)) * rs;
+  const float invM = 1.f / (float)M;
+  dx[q] = __ldg(gamma + c) * rs * (g - __ldg(sum_g + c) * invM - xh * __ldg(sum_gx + c) * invM);
+}
+
+// ReLU backward: dx = dy * (y > 0)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(long long n, const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = __ldg(y + i) > 0.f ? __ldg(dy + i) : 0.f;
+}
+
+// Anchor-weighted max-pool of PointNetV2 (pointnet.py:194-198) WITHOUT the (B, C, N, A) intermediate:
+//   out[b, c, a] = max_n  x[b, n, c] * w[b, n, a] * scale        x (B, N, C) channel-last, w (B, N, A), A <= 4
+// thread = (channel, anchor); the point loop reads x coalesced over channels and w broadcast.  arg[b,c,a] = winning n.
+__global__ void __launch_bounds__(128)
+weighted_maxpool_fwd_kernel(int N, int C, int A, float scale, const float* __restrict__ x, const float* __restrict__ w,
+                            float* __restrict__ out, int* __restrict__ arg) {
+  const int b = blockIdx.y;
+  const int cl = threadIdx.x & 31, a = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (c >= C || a >= A) return;
+  const float* xb = x + (size_t)b * N * C + c;
+  const float* wb = w + (size_t)b * N * A + a;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int n = 0; n < N; ++n) {
+    const float v = __ldg(xb + (size_t)n * C) * __ldg(wb + (size_t)n * A) * scale;
+    if (v > best) { best = v; bi = n; }  // first maximum, as torch.max
+  }
+  out[((size_t)b * C + c) * A + a] = best;
+  arg[((size_t)b * C + c) * A + a] = bi;
+}
+// dx[b, arg, c] += w[b, arg, a] * scale * dout[b, c, a]      (dx zeroed by the caller)
+__global__ void __launch_bounds__(256)
+weighted_maxpool_bwd_kernel(long long total, int N, int C, int A, float scale, const float* __restrict__ w, const int* __restrict__ arg,
+                            const float* __restrict__ dout, float* __restrict__ dx) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int a = (int)(q % A);
+  const int c = (int)((q / A) % C);
+  const long long b = q / ((long long)A * C);
+  const int n = __ldg(arg + q);
+  atomicAdd(dx + ((size_t)b * N + n) * C + c, __ldg(w + ((size_t)b * N + n) * A + a) * scale * __ldg(dout + q));
+}
+
+// CouplingLayer forward (flow.py:33-37): scale = sigmoid(s + 2); y1 = x2 * scale + shift; logdet[r] = sum_c log(scale)
+// s_t (B, 2d) = [s | shift]; x2 / y1: d columns with leading dimension ld (y1 may alias x2).  One warp per row.
+__global__ void __launch_bounds__(256)
+coupling_fwd_kernel(int B, int d, const float* __restrict__ s_t, const float* __restrict__ x2, int ldx, float* __restrict__ y1, int ldy,
+                    float* __restrict__ logdet) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= B) return;
+  float ld = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float sc = 1.f / (1.f + expf(-(__ldg(s_t + (size_t)r * 2 * d + c) + 2.f)));
+    y1[(size_t)r * ldy + c] = x2[(size_t)r * ldx + c] * sc + __ldg(s_t + (size_t)r * 2 * d + d + c);
+    ld += logf(sc);
+  }
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) ld += __shfl_xor_sync(0xFFFFFFFFu, ld, k);
+  if (lane == 0) logdet[r] = ld;
+}
+// backward: given dy1 (B,d; ld ldy) and dlogdet (B): ds_t (B,2d) and dx2 (B,d; ld ldx)
+//   d scale = dy1 * x2 + dlogdet / scale;  ds = d scale * scale (1 - scale);  dshift = dy1;  dx2 = dy1 * scale
+__global__ void __launch_bounds__(256)
+coupling_bwd_kernel(int B, int d, const float* __restrict__ s_t, const float* __restrict__ x2, int ldx, const float* __restrict__ dy1, int ldy,
+                    const float* __restrict__ dlogdet, float* __restrict__ ds_t, float* __restrict__ dx2, int lddx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d) return;
+  const int r = i / d, c = i - r * d;
+  const float sc = 1.f / (1.f + expf(-(__ldg(s_t + (size_t)r * 2 * d + c) + 2.f)));
+  const float g = __ldg(dy1 + (size_t)r * ldy + c);
+  const float dsc = g * __ldg(x2 + (size_t)r * ldx + c) + __ldg(dlogdet + r) / sc;
+  ds_t[(size_t)r * 2 * d + c] = dsc * sc * (1.f - sc);
+  ds_t[(size_t)r * 2 * d + d + c] = g;
+  dx2[(size_t)r * lddx + c] = g * sc;
+}
+
+}  // namespace dfb200
+
+extern "C" int dfb200_batchnorm_forward(long long M, int C, int relu, const float* x, const float* gamma, const float* beta, float* y,
+                                        float* mean, float* rstd, float* running_mean, float* running_var, float momentum,
+                                        float* scratch2C, dfb200_stream_t stream) {
+  DFB_REQUIRE(M >= 1 && C >= 1, DFB200_ERR_INVALID_ARG, "batchnorm_forward: bad sizes M=%lld C=%d", M, C);
+  cudaStream_t st = as_stream(stream);
+  DFB_CUDA(cudaMemsetAsync(scratch2C, 0, sizeof(float) * 2 * (size_t)C, st));
+  const int rpb = 1024;
+  bn_colstats_kernel<<<dim3(cdiv(C, 32), (unsigned)cdiv(M, (long long)rpb)), 256, 0, st>>>(M, C, 0, 0, x, nullptr, nullptr, nullptr, nullptr,
+                                                                                          scratch2C, scratch2C + C, rpb);
+  DFB_LAUNCH_CHECK();
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(M, C, scratch2C, scratch2C + C, mean, rstd, running_mean, running_var, momentum);
+  DFB_LAUNCH_CHECK();
+  const long long total = M * C;
+  bn_apply_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, st>>>(total, C, relu, x, mean, rstd, gamma, beta, y);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+/* eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps) supplied by the caller */
+extern "C" int dfb200_batchnorm_apply(long long M, int C, int relu, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                      const float* beta, float* y, dfb200_stream_t stream) {
+  const long long total = M * C;
+  if (total <= 0) return DFB200_OK;
+  bn_apply_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, as_stream(stream)>>>(total, C, relu, x, mean, rstd, gamma, beta, y);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_batchnorm_backward(long long M, int C, int relu, const float* x, const float* y, const float* dy, const float* gamma,
+                                         const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta, dfb200_stream_t stream) {
+  DFB_REQUIRE(M >= 1 && C >= 1, DFB200_ERR_INVALID_ARG, "batchnorm_backward: bad sizes M=%lld C=%d", M, C);
+  cudaStream_t st = as_stream(stream);
+  DFB_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * (size_t)C, st));
+  DFB_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)C, st));
+  const int rpb = 1024;
+  bn_colstats_kernel<<<dim3(cdiv(C, 32), (unsigned)cdiv(M, (long long)rpb)), 256, 0, st>>>(M, C, 1, relu, x, dy, y, mean, rstd, dbeta, dgamma, rpb);
+  DFB_LAUNCH_CHECK();
+  const long long total = M * C;
+  bn_dx_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, st>>>(total, M, C, relu, x, dy, y, mean, rstd, gamma, dbeta, dgamma, dx);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_relu_backward(size_t count, const float* y, const float* dy, float* dx, dfb200_stream_t stream) {
+  if (count == 0) return DFB200_OK;
+  relu_bwd_kernel<<<(unsigned)cdiv((long long)count, 256LL), 256, 0, as_stream(stream)>>>((long long)count, y, dy, dx);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_weighted_maxpool_forward(int B, int N, int C, int A, float scale, const float* x, const float* w, float* out, int* arg,
+                                               dfb200_stream_t stream) {
+  DFB_REQUIRE(B >= 0 && N >= 1 && C >= 1 && A >= 1 && A <= 4 && B <= 65535, DFB200_ERR_INVALID_ARG, "weighted_maxpool_forward: bad sizes");
+  if (B == 0) return DFB200_OK;
+  weighted_maxpool_fwd_kernel<<<dim3(cdiv(C, 32), B), 128, 0, as_stream(stream)>>>(N, C, A, scale, x, w, out, arg);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_weighted_maxpool_backward(int B, int N, int C, int A, float scale, const float* w, const int* arg, const float* dout,
+                                                float* dx_zeroed, dfb200_stream_t stream) {
+  const long long total = (long long)B * C * A;
+  if (total <= 0) return DFB200_OK;
+  weighted_maxpool_bwd_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, as_stream(stream)>>>(total, N, C, A, scale, w, arg, dout, dx_zeroed);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_coupling_forward(int B, int d, const float* s_t, const float* x2, int ldx, float* y1, int ldy, float* logdet,
+                                       dfb200_stream_t stream) {
+  if (B <= 0 || d <= 0) return DFB200_OK;
+  coupling_fwd_kernel<<<cdiv(B, 8), 256, 0, as_stream(stream)>>>(B, d, s_t, x2, ldx, y1, ldy, logdet);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_coupling_backward(int B, int d, const float* s_t, const float* x2, int ldx, const float* dy1, int ldy,
+                                        const float* dlogdet, float* ds_t, float* dx2, int lddx, dfb200_stream_t stream) {
+  if (B <= 0 || d <= 0) return DFB200_OK;
+  coupling_bwd_kernel<<<cdiv(B * d, 256), 256, 0, as_stream(stream)>>>(B, d, s_t, x2, ldx, dy1, ldy, dlogdet, ds_t, dx2, lddx);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}

@@ -80,14 +80,33 @@ class CouplingLayer(nn.Module):  # reference encoders/flow.py:7-45
         return x
 
 
+    def forward_with_logdet(self, x, logpx):
+        """Forward direction (training prior loss), differentiable: reference flow.py:24-45 with reverse=False."""
+        d = self.d
+        if self.swap:
+            x = torch.cat([x[:, d:], x[:, :d]], 1)
+        cond, x2 = x[:, :d].contiguous(), x[:, d:].contiguous()
+        h = T.relu(T.linear(cond, self.net_s_t[0].weight, self.net_s_t[0].bias))
+        h = T.relu(T.linear(h, self.net_s_t[2].weight, self.net_s_t[2].bias))
+        s_t = T.linear(h, self.net_s_t[4].weight, self.net_s_t[4].bias)
+        y1, logdet = T.coupling_forward(s_t, x2)
+        y = torch.cat([cond, y1], 1) if not self.swap else torch.cat([y1, cond], 1)
+        return y, logpx - logdet.view(-1, 1)
+
+
 class SequentialFlow(nn.Module):  # reference encoders/flow.py:48-71
     def __init__(self, layers):
         super().__init__()
         self.chain = nn.ModuleList(layers)
 
     def forward(self, x, logpx=None, reverse=False, inds=None):
-        if not reverse or logpx is not None:
-            raise NotImplementedError("difffacto_b200: only the reverse (sampling) direction of the latent flow is built")
+        if not reverse:
+            assert logpx is not None
+            for i in (range(len(self.chain)) if inds is None else inds):
+                x, logpx = self.chain[i].forward_with_logdet(x, logpx)
+            return x, logpx
+        if logpx is not None:
+            raise NotImplementedError("difffacto_b200: the reverse direction of the latent flow is built without log-density tracking")
         x = x.to(torch.float32).contiguous().clone()
         for i in range(len(self.chain) - 1, -1, -1):
             self.chain[i].reverse_(x)
@@ -176,14 +195,18 @@ class PartEncoderForTransformerDecoder(nn.Module):
                  kl_weight=0.001, use_flow=False, latent_flow_depth=14, latent_flow_hidden_dim=256, gen=False, prior_var=1.0,
                  detach_params_in_ctx=False, selective_noise_sampling=False, selective_noise_sampling_global=False, **kwargs):
         super().__init__()
-        unsupported = dict(use_gt_params=use_gt_params, encode_ref=encode_ref, selective_noise_sampling=selective_noise_sampling,
+        unsupported = dict(encode_ref=encode_ref, selective_noise_sampling=selective_noise_sampling,
                            selective_noise_sampling_global=selective_noise_sampling_global, gen=not gen)
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError("difffacto_b200.PartEncoderForTransformerDecoder implements sample_latents of configs/gen_*.py; "
                                       f"unsupported setting(s): {bad}")
         self.zdim = int((encoder or {}).get("zdim", 256)) if isinstance(encoder, dict) else 256
-        self.encoder = None  # PointNetV2 (reconstruction / training only) is outside this build
+        self.encoder = build_from_cfg(encoder, ENCODERS, num_anchors=n_class) if encoder is not None and encoder.get("type") in ENCODERS else None
+        self.use_gt_params_cfg, self.origin_scale, self.kl_weight = use_gt_params, origin_scale, kl_weight
+        self.kl_weight_annealing = kwargs.get("kl_weight_annealing", False)
+        self.min_kl_weight = kwargs.get("min_kl_weight", 1e-7)
+        self.kl_weight_annealing_end_epoch = kwargs.get("kl_weight_annealing_end_epoch", 3000)
         self.part_aligner = build_from_cfg(part_aligner, ENCODERS)
         self.n_class, self.prior_var = n_class, prior_var
         self.include_part_code, self.include_params = include_part_code, include_params
@@ -192,9 +215,61 @@ class PartEncoderForTransformerDecoder(nn.Module):
         if use_flow:
             self.flow = nn.ModuleList([build_latent_flow(latent_flow_depth, latent_flow_hidden_dim, self.zdim) for _ in range(n_class)])
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("difffacto_b200: the point-cloud encoder (reconstruction / training) is outside this build; "
-                                  "use sample_latents")
+    # ---- training forward (stage 1: use_gt_params=True, no part aligner; reference :1185-1257) ----------------------------
+    def get_prior_loss(self, part_code, mean, logvar, valid_id, epoch=-1):
+        """reference :1143-1183.  The flows (Linear / ReLU / coupling with log-determinant) run on this repo's kernels; the
+        O(B * 256) Gaussian log-likelihood / entropy bookkeeping around them is host-side torch, as in the reference."""
+        B, C, M = part_code.shape
+        entropy = 0.5 * logvar.reshape(B * self.n_class, -1).sum(dim=1) + 0.5 * float(C) * (1. + math.log(math.pi * 2))  # gaussian_entropy
+        log_p_part = torch.zeros(B, self.n_class, device=part_code.device)
+        for i in range(self.n_class):
+            _id = valid_id[:, i] == 1
+            if _id.any():
+                pc = part_code[_id, :, i].contiguous()
+                b = pc.shape[0]
+                w, delta_log_pw = self.flow[i](pc, torch.zeros(b, 1, device=pc.device), reverse=False)
+                log_z = -0.5 * math.log(2 * math.pi) * w.shape[1]                      # (sic) gaussian_log_likelihood(dim=w.shape[1]) per element
+                log_pw = (-math.log(self.prior_var) + log_z - w.pow(2) / (2. * self.prior_var)).view(b, -1).sum(dim=1)
+                log_p_part = log_p_part.index_put((_id.nonzero(as_tuple=True)[0], torch.full((b,), i, device=pc.device)), log_pw - delta_log_pw.view(b))
+        entropy = entropy.view(B, self.n_class)
+        loss_prior = ((-log_p_part - entropy) * valid_id).sum(1) / valid_id.sum(1)
+        if self.kl_weight_annealing and self.kl_weight_annealing_end_epoch > epoch:
+            kl_weight = self.min_kl_weight + (self.kl_weight - self.min_kl_weight) * epoch / self.kl_weight_annealing_end_epoch
+        else:
+            kl_weight = self.kl_weight
+        out = {"prior_loss": kl_weight * loss_prior.mean(), "kl_weight": torch.ones(1, device=part_code.device) * kl_weight}
+        mlog_p, ment = (log_p_part * valid_id).sum(0) / valid_id.sum(0), (entropy * valid_id).sum(0) / valid_id.sum(0)
+        for i in range(self.n_class):
+            out[f"log_p_part_{i}"], out[f"entropy_{i}"] = mlog_p[i], ment[i]
+        return out
+
+    def forward(self, pcds, device, noise=None, epoch=-1, eps=None):
+        """Training forward of the stage-1 configuration (configs/train_chair_stage1.py: PointNetV2 encoder, latent flows as
+        the prior, ground-truth part parameters): returns (ctx, mean_per_point, logvar_per_point, flag_per_point, loss_dict,
+        [part_code, mean, logvar, noise]) like the reference (:1185-1257).  `eps` overrides the reparameterisation draw."""
+        if self.encoder is None or self.part_aligner is not None or not self.use_gt_params_cfg:
+            raise NotImplementedError("difffacto_b200: the training forward is built for the stage-1 configuration "
+                                      "(encoder=PointNetV2, part_aligner=None, use_gt_params=True)")
+        inp = pcds['input'].to(device)
+        valid_id = pcds['present'].to(device).float()
+        ref = pcds['ref'].to(device).transpose(1, 2)
+        seg_mask = pcds['ref_seg_mask'].to(device).to(torch.int32)
+        seg_flag = pcds['ref_attn_map'].to(device)
+        B = ref.shape[0]
+        gt_shift = pcds.get('part_shift', torch.zeros(B, 3, self.n_class)).to(device)
+        gt_var = pcds.get('part_scale', torch.ones(B, 3, self.n_class)).to(device)
+        if not self.origin_scale:
+            gt_var = gt_var ** 2
+        m, v = self.encoder(inp, seg_flag)                                            # (B, 4, 256) each
+        if eps is None:
+            eps = torch.randn(v.size()).to(m)
+        part_code = (m + torch.exp(0.5 * v) * eps).transpose(1, 2)                    # reparameterize_gaussian (:282-285), (B, 256, 4)
+        loss_dict = dict(self.get_prior_loss(part_code, m, v, valid_id, epoch=epoch))
+        mean, logvar = gt_shift, torch.log(gt_var)                                    # use_gt_params (:456-458)
+        mean_pp, logvar_pp, flag_pp = self.gather_all(seg_mask, anchors=mean, variances=logvar, valid_id=valid_id)
+        loss_dict['fit_loss'] = torch.zeros(1, device=ref.device)
+        ctx = self.prepare_ctx(part_code, mean, logvar, anchor_assignments=seg_mask)
+        return ctx, mean_pp, logvar_pp + self.log_scale_var, flag_pp, loss_dict, [part_code, mean, logvar, noise]
 
     def gather_all(self, anchor_assignments, anchors=None, variances=None, valid_id=None):  # reference :417-428
         B, N = anchor_assignments.shape

@@ -265,3 +265,136 @@ class QSampleFn(Function):
             check(_lib.load().dfb200_q_sample_backward(B, N, ctx.T, ptr(sched), ptr(t_i32), ptr(variance), ptr(noise), ptr(g), ptr(dx0),
                                                        ptr(da), ptr(dv), stream()))
         return dx0, da, dv, None, None, None, None
+
+
+# ---- training-side encoder primitives (row f3) ---------------------------------------------------------------------------
+class BatchNormFn(Function):
+    """nn.BatchNorm1d over the M rows of a (M, C) matrix (+ fused ReLU).  training=True: batch statistics + running-stat
+    update; else the running statistics.  Backward (training statistics only): dx, dgamma, dbeta."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, relu, momentum):
+        x = _c(x)
+        M, C = x.shape
+        y = torch.empty_like(x)
+        lib = _lib.load()
+        if training:
+            mean = torch.empty(C, device=x.device)
+            rstd = torch.empty(C, device=x.device)
+            scratch = torch.empty(2 * C, device=x.device)
+            with torch.cuda.device(x.device):
+                check(lib.dfb200_batchnorm_forward(M, C, int(relu), ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd),
+                                                   ptr(running_mean), ptr(running_var), float(momentum), ptr(scratch), stream()))
+        else:
+            mean = running_mean
+            rstd = torch.rsqrt(running_var + 1e-5)  # C numbers of statistics bookkeeping
+            with torch.cuda.device(x.device):
+                check(lib.dfb200_batchnorm_apply(M, C, int(relu), ptr(x), ptr(_c(mean)), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), stream()))
+        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.relu, ctx.training = relu, training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        if not ctx.training:
+            raise NotImplementedError("difffacto_b200: BatchNorm backward is implemented for training-mode statistics")
+        dy = _c(dy)
+        M, C = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty(C, device=x.device)
+        db = torch.empty(C, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.load().dfb200_batchnorm_backward(M, C, int(ctx.relu), ptr(x), ptr(y), ptr(dy), ptr(gamma), ptr(mean), ptr(rstd),
+                                                        ptr(dx), ptr(dg), ptr(db), stream()))
+        return dx, dg, db, None, None, None, None, None
+
+
+def batchnorm(x, bn, relu=False):
+    """x (M, C) through an nn.BatchNorm1d module `bn` (parameters + running statistics), optionally fused with ReLU."""
+    training = bn.training or bn.running_mean is None
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, relu, bn.momentum if bn.momentum is not None else 0.1)
+
+
+class ReluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = _c(x).clone()
+        with torch.cuda.device(y.device):
+            check(_lib.load().dfb200_relu(y.numel(), ptr(y), stream()))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            check(_lib.load().dfb200_relu_backward(y.numel(), ptr(y), ptr(_c(dy)), ptr(dx), stream()))
+        return dx
+
+
+def relu(x):
+    return ReluFn.apply(x)
+
+
+class WeightedMaxPoolFn(Function):
+    """out[b,c,a] = max_n x[b,n,c] * w[b,n,a] * scale (PointNetV2's anchor-weighted max-pool, no (B,C,N,A) intermediate)."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale):
+        x, w = _c(x), _c(w.to(torch.float32))
+        B, N, C = x.shape
+        A = w.shape[2]
+        out = torch.empty(B, C, A, device=x.device)
+        arg = torch.empty(B, C, A, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.load().dfb200_weighted_maxpool_forward(B, N, C, A, float(scale), ptr(x), ptr(w), ptr(out), ptr(arg), stream()))
+        ctx.save_for_backward(w, arg)
+        ctx.dims, ctx.scale = (B, N, C, A), float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, arg = ctx.saved_tensors
+        B, N, C, A = ctx.dims
+        dx = torch.zeros(B, N, C, device=dout.device)
+        with torch.cuda.device(dout.device):
+            check(_lib.load().dfb200_weighted_maxpool_backward(B, N, C, A, ctx.scale, ptr(w), ptr(arg), ptr(_c(dout)), ptr(dx), stream()))
+        return dx, None, None
+
+
+def weighted_maxpool(x, w, scale):
+    return WeightedMaxPoolFn.apply(x, w, scale)
+
+
+class CouplingForwardFn(Function):
+    """y1 = x2 * sigmoid(s + 2) + shift, logdet = sum log sigmoid(s + 2);  s_t (B, 2d) = [s | shift], x2 (B, d)."""
+
+    @staticmethod
+    def forward(ctx, s_t, x2):
+        s_t, x2 = _c(s_t), _c(x2)
+        B, d = x2.shape
+        y1 = torch.empty_like(x2)
+        logdet = torch.empty(B, device=x2.device)
+        with torch.cuda.device(x2.device):
+            check(_lib.load().dfb200_coupling_forward(B, d, ptr(s_t), ptr(x2), d, ptr(y1), d, ptr(logdet), stream()))
+        ctx.save_for_backward(s_t, x2)
+        return y1, logdet
+
+    @staticmethod
+    def backward(ctx, dy1, dlogdet):
+        s_t, x2 = ctx.saved_tensors
+        B, d = x2.shape
+        ds_t = torch.empty_like(s_t)
+        dx2 = torch.empty_like(x2)
+        with torch.cuda.device(x2.device):
+            check(_lib.load().dfb200_coupling_backward(B, d, ptr(s_t), ptr(x2), d, ptr(_c(dy1)), d, ptr(_c(dlogdet)), ptr(ds_t), ptr(dx2), d,
+                                                       stream()))
+        return ds_t, dx2
+
+
+def coupling_forward(s_t, x2):
+    return CouplingForwardFn.apply(s_t, x2)

@@ -259,6 +259,33 @@ int dfb200_q_sample_backward(int B, int N, int T, const float* sched, const int*
                              const float* noise, const float* grad_x_t, float* grad_x_start, float* grad_anchors,
                              float* grad_variance, dfb200_stream_t stream);
 
+/* ---- training-side encoder primitives (row f3): PointNetV2 (models/encoders/pointnet.py:122-214) and the forward direction
+ * of the latent flows (encoders/flow.py:24-45), composed by difffacto_b200/train_ops.py ---- */
+/* nn.BatchNorm1d in training mode over the M rows of a row-major (M, C) matrix (+ fused ReLU): batch statistics (saved in
+ * mean / rstd for the backward), running-statistics update (momentum; pointers may be NULL).  scratch2C: 2*C floats. */
+int dfb200_batchnorm_forward(long long M, int C, int relu, const float* x, const float* gamma, const float* beta, float* y,
+                             float* mean, float* rstd, float* running_mean, float* running_var, float momentum,
+                             float* scratch2C, dfb200_stream_t stream);
+/* y = (x - mean) * rstd * gamma + beta (+ ReLU) with caller-supplied statistics (eval mode). */
+int dfb200_batchnorm_apply(long long M, int C, int relu, const float* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, float* y, dfb200_stream_t stream);
+int dfb200_batchnorm_backward(long long M, int C, int relu, const float* x, const float* y, const float* dy, const float* gamma,
+                              const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta, dfb200_stream_t stream);
+int dfb200_relu_backward(size_t count, const float* y, const float* dy, float* dx, dfb200_stream_t stream);
+/* Anchor-weighted max-pool of PointNetV2 (pointnet.py:194-198) without the (B,C,N,A) intermediate:
+ * out[b,c,a] = max_n x[b,n,c] * w[b,n,a] * scale, arg = winning n.  x (B,N,C), w (B,N,A), A <= 4.  backward: dx (zeroed by the
+ * caller) += w * scale * dout at the winners. */
+int dfb200_weighted_maxpool_forward(int B, int N, int C, int A, float scale, const float* x, const float* w, float* out, int* arg,
+                                    dfb200_stream_t stream);
+int dfb200_weighted_maxpool_backward(int B, int N, int C, int A, float scale, const float* w, const int* arg, const float* dout,
+                                     float* dx_zeroed, dfb200_stream_t stream);
+/* CouplingLayer forward (flow.py:33-37): y1 = x2 * sigmoid(s + 2) + shift, logdet[r] = sum log sigmoid(s + 2); s_t (B, 2d);
+ * x2 / y1 are d columns with leading dimensions ldx / ldy.  backward: ds_t (B,2d), dx2 (ld lddx) from dy1 and dlogdet (B). */
+int dfb200_coupling_forward(int B, int d, const float* s_t, const float* x2, int ldx, float* y1, int ldy, float* logdet,
+                            dfb200_stream_t stream);
+int dfb200_coupling_backward(int B, int d, const float* s_t, const float* x2, int ldx, const float* dy1, int ldy,
+                             const float* dlogdet, float* ds_t, float* dx2, int lddx, dfb200_stream_t stream);
+
 /* ---- encoder side of sampling (PartEncoder.sample_latents, part_encoders.py:1052-1110): forward-only helpers used with
  * dfb200_sgemm / dfb200_geglu_forward / dfb200_gather_points by difffacto_b200/models/encoders/part_encoders.py ---- */
 /* nn.LayerNorm(D, eps 1e-5) over M rows, any D. */

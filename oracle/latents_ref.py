@@ -31,11 +31,45 @@ def encoder_param_shapes(depth=5, flow_depth=14, zdim=256, hidden=256, inner=256
     return s
 
 
-def synthetic_encoder_state_dict(seed=0, **kw):
+def pointnet_param_shapes(zdim=256, n_class=4, prefix="encoder."):
+    """PointNetV2(per_part_mlp=True) parameters and buffers (reference models/encoders/pointnet.py:122-181)."""
+    s = {}
+    for i, (ci, co) in enumerate([(3, 128), (128, 128), (128, 256), (256, 512)], 1):
+        s[f"{prefix}conv{i}.weight"], s[f"{prefix}conv{i}.bias"] = (co, ci, 1), (co,)
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            s[f"{prefix}bn{i}.{n}"] = (co,)
+        s[f"{prefix}bn{i}.num_batches_tracked"] = ()
+    g = n_class
+    for head in ("mlp_m", "mlp_v"):
+        for idx, (ci, co) in zip((0, 3, 6), [(512, 256), (256, 128), (128, zdim)]):
+            s[f"{prefix}{head}.{idx}.weight"], s[f"{prefix}{head}.{idx}.bias"] = (co * g, ci, 1), (co * g,)
+        for idx, c in zip((1, 4), (256, 128)):
+            for n in ("weight", "bias", "running_mean", "running_var"):
+                s[f"{prefix}{head}.{idx}.{n}"] = (c * g,)
+            s[f"{prefix}{head}.{idx}.num_batches_tracked"] = ()
+    return s
+
+
+def synthetic_encoder_state_dict(seed=0, with_pointnet=False, with_aligner=True, **kw):
     """Deterministic weights (name order, seeded generator): Linear ~ N(0, 1/fan_in), biases ~ 0.05 N, LayerNorm gain 1 + 0.1 N."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for name, shape in encoder_param_shapes(**kw).items():
+    shapes = {k: v for k, v in encoder_param_shapes(**kw).items() if with_aligner or not k.startswith("part_aligner.")}
+    if with_pointnet:
+        shapes.update(pointnet_param_shapes())
+    for name, shape in shapes.items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.zeros((), dtype=torch.long)
+            continue
+        if name.endswith("running_mean"):
+            sd[name] = 0.1 * torch.randn(shape, generator=g)
+            continue
+        if name.endswith("running_var"):
+            sd[name] = 0.5 + torch.rand(shape, generator=g)
+            continue
+        if ".bn" in name or (name.split(".")[-2] in ("1", "4") and ("mlp_m" in name or "mlp_v" in name)):
+            sd[name] = (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.05 * torch.randn(shape, generator=g)
+            continue
         if name.endswith("bias"):
             sd[name] = 0.05 * torch.randn(shape, generator=g)
         elif "norm" in name:

@@ -252,8 +252,72 @@ def latents_golden():
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
 
+def synthetic_pcds(seed, B, N):
+    """A training batch shaped like ShapeNetSegPart's (datasets/shapenet_seg.py): points, part labels, presence, part boxes."""
+    g = torch.Generator().manual_seed(seed)
+    seg = torch.randint(0, 4, (B, N), generator=g)
+    seg[1][seg[1] == 3] = 0                                     # shape 1 has no part 3
+    present = torch.stack([(seg == k).any(1) for k in range(4)], 1).float()
+    pts = 0.5 * torch.randn(B, N, 3, generator=g)
+    attn = torch.nn.functional.one_hot(seg, 4).float()
+    return {"input": pts, "ref": pts.clone(), "present": present, "ref_seg_mask": seg, "ref_attn_map": attn,
+            "part_shift": 0.3 * torch.randn(B, 3, 4, generator=g), "part_scale": 0.2 + 0.3 * torch.rand(B, 3, 4, generator=g),
+            "noise": torch.zeros(B, 32)}
+
+
+def encoder_train_golden():
+    """Training forward + backward of the REAL reference stage-1 encoder (configs/train_chair_stage1.py: PointNetV2 +
+    latent flows, ground-truth part parameters) -> encoder_train_golden.npz (outputs and a few gradients)."""
+    import contextlib, io
+    from oracle import latents_ref as L
+    import_reference()
+    m = types.ModuleType("difffacto.models.encoders")
+    m.__path__ = [REF + "/models/encoders"]
+    sys.modules["difffacto.models.encoders"] = m
+    importlib.import_module("difffacto.models.encoders.pointnet")
+    importlib.import_module("difffacto.models.encoders.part_encoders")
+    from difffacto.utils.registry import ENCODERS, build_from_cfg
+    sys.path.insert(0, "/root/reference/configs")
+    cfg = dict(importlib.import_module("train_chair_stage1").model["encoder"])
+    sys.path.pop(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = build_from_cfg(cfg, ENCODERS)
+    sd = L.synthetic_encoder_state_dict(31, with_pointnet=True, with_aligner=False)
+    enc.load_state_dict(sd, strict=True)
+    enc.train()
+    B, N = 8, 256
+    pcds = synthetic_pcds(8, B, N)
+    g = torch.Generator().manual_seed(123)
+    eps = torch.randn(B, 4, 256, generator=g)
+    R_ = torch.randn(B, 256, 4, generator=g)
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # the reference writes `torch.ones(1).cuda()` in its loss dict
+    try:
+        with FixedNoise([eps]):
+            ctx, mpp, lpp, flag, loss_dict, extra = enc(pcds, "cpu", epoch=10)
+    finally:
+        torch.Tensor.cuda = _cuda
+    total = loss_dict["prior_loss"] * 1000.0 + (ctx[0] * R_).sum()
+    total.backward()
+    out = {"eps": eps.numpy(), "R": R_.numpy(), "ctx0": ctx[0].detach().numpy(), "ctx1": ctx[1].detach().numpy(), "mean_pp": mpp.numpy(),
+           "logvar_pp": lpp.numpy(), "flag_pp": flag.numpy(), "prior_loss": loss_dict["prior_loss"].detach().numpy(),
+           "total": total.detach().numpy(), "bn4_running_mean": enc.encoder.bn4.running_mean.numpy(),
+           "bn4_running_var": enc.encoder.bn4.running_var.numpy(), "mlp_m1_running_var": enc.encoder.mlp_m[1].running_var.numpy()}
+    params = dict(enc.named_parameters())
+    for k in ("encoder.conv1.weight", "encoder.conv4.bias", "encoder.bn2.weight", "encoder.bn4.bias", "encoder.mlp_m.0.weight",
+              "encoder.mlp_v.6.weight", "encoder.mlp_m.4.weight", "flow.0.chain.0.net_s_t.0.weight", "flow.2.chain.13.net_s_t.4.bias",
+              "flow.3.chain.7.net_s_t.2.weight"):
+        out["grad:" + k] = params[k].grad.numpy()[:8]  # first 8 rows keep the fixture small; grad_norms covers every tensor
+    out["grad_norms"] = np.array([float(p.grad.norm()) if p.grad is not None else 0.0 for _, p in sorted(params.items())])
+    path = os.path.join(HERE, "encoder_train_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays; prior_loss", float(loss_dict["prior_loss"]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "latents":
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder_train":
+        encoder_train_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "latents":
         latents_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "eval":
         eval_golden()

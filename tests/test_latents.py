@@ -41,7 +41,8 @@ def test_port_matches_reference_sample_latents(lg, tag):
 def _build():
     import difffacto_b200 as D
     enc = D.build_from_cfg(ENC_CFG, D.ENCODERS)
-    res = enc.load_state_dict(L.synthetic_encoder_state_dict(77), strict=True)  # every reference parameter of the sampling path exists here
+    res = enc.load_state_dict(L.synthetic_encoder_state_dict(77), strict=False)  # sampling path: part_aligner.* and flow.*
+    assert not res.unexpected_keys and all(k.startswith("encoder.") for k in res.missing_keys)
     return enc.cuda().eval()
 
 
