@@ -41,6 +41,19 @@ class SyntheticPartSeg:
         hi = B if hi is None else hi
         return {k: v[lo:hi].contiguous() for k, v in out.items()}
 
+    def train_batch(self, index, lo=0, hi=None):
+        """A training batch in the layout of ShapeNetSegPart items (reference datasets/shapenet_seg.py; keys read by
+        PartEncoder.forward, part_encoders.py:1196-1204): clouds drawn from the per-part Gaussians of `batch(index)`."""
+        b = self.batch(index, lo, hi)
+        B, N = b["assign"].shape
+        g = torch.Generator().manual_seed(self.seed * 7907 + index + 17)
+        pts = (b["variance"].sqrt() * torch.randn(B, 3, N, generator=g) + b["anchors"]).transpose(1, 2).contiguous()
+        seg = b["assign"].long()
+        mean, var = b["params"][:, :3], b["params"][:, 3:]
+        return {"input": pts, "ref": pts.clone(), "present": b["valid"], "ref_seg_mask": seg,
+                "ref_attn_map": torch.nn.functional.one_hot(seg, self.n_parts).float(), "part_shift": mean.contiguous(),
+                "part_scale": var.sqrt().contiguous(), "noise": torch.zeros(B, 32)}
+
     def __iter__(self):
         for i in range(self.num_batches):
             yield self.batch(i)

@@ -139,8 +139,14 @@ class Runner:
         """Checkpoint in the reference's layout (runner.py:470-489): 'model' holds `diffusion.*` keys, 'decoder' the
         diffusion state_dict, plus meta / optimizer."""
         sd = self.diffusion.state_dict()
-        data = {"meta": {"epoch": epoch, "iter": it, "config": self.cfg.dump()},
-                "model": {f"diffusion.{k}": v for k, v in sd.items()}, "decoder": sd, "optimizer": optimizer.state_dict()}
+        model_sd = {f"diffusion.{k}": v for k, v in sd.items()}
+        data = {"meta": {"epoch": epoch, "iter": it, "config": self.cfg.dump()}, "decoder": sd, "optimizer": optimizer.state_dict()}
+        if self.encoder is not None:
+            esd = self.encoder.state_dict()
+            model_sd.update({f"encoder.{k}": v for k, v in esd.items()})
+            if getattr(self.encoder, "encoder", None) is not None:
+                data["encoder"] = self.encoder.encoder.state_dict()
+        data["model"] = model_sd
         path = os.path.join(self.work_dir, "checkpoints", f"ckpt_{epoch}.pth")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         torch.save(data, path)
@@ -156,8 +162,15 @@ class Runner:
         model = self.diffusion
         if self.world > 1:  # DDP all-reduces the gradients the autograd Functions hand to the parameters
             model = torch.nn.parallel.DistributedDataParallel(self.diffusion, device_ids=[self.device.index])
+        # stage-1 configuration (train_chair_stage1.py): the PointNetV2 encoder + latent-flow prior are trained jointly with the
+        # denoiser (AnchorDiffAE.forward, anchor_gen.py:995-1037); otherwise the conditioning comes from the dataset
+        joint = self.encoder is not None and getattr(self.encoder, "encoder", None) is not None and self.encoder.part_aligner is None \
+            and getattr(self.encoder, "use_gt_params_cfg", False)
+        params = list(self.diffusion.parameters()) + (list(self.encoder.parameters()) if joint else [])
+        if joint:
+            self.encoder.train()
         ocfg = dict(cfg.optimizer.dump()) if cfg.optimizer else dict(type="Adam", lr=2e-3, weight_decay=0.)
-        opt = getattr(torch.optim, ocfg.pop("type"))(self.diffusion.parameters(), **ocfg)
+        opt = getattr(torch.optim, ocfg.pop("type"))(params, **ocfg)
         max_epoch = int(cfg.max_epoch or 1)
         max_norm, log_interval, ckpt_interval = cfg.max_norm, int(cfg.log_interval or 50), int(cfg.checkpoint_interval or 500)
         torch.manual_seed(self.seed + self.rank)  # reference: seed + local_rank (runner.py:39)
@@ -166,27 +179,43 @@ class Runner:
             for bi in range(len(ds)):
                 B = ds.batch_size
                 lo, hi = shard_range(B, self.rank, self.world)
-                b = {k: v.to(self.device) for k, v in ds.batch(bi + epoch * len(ds), lo, hi).items()}
-                x0 = torch.sqrt(b["variance"]) * torch.randn_like(b["anchors"]) + b["anchors"]
                 t = torch.randint(0, self.num_timesteps, (hi - lo,), device=self.device)
-                flags = torch.ones(hi - lo, 1, x0.shape[2], device=self.device)
                 opt.zero_grad(set_to_none=True)
-                # DDP hooks fire on the wrapped module's forward: route the loss through it
-                loss = _LossModule.forward_through(model, self.diffusion, x0, t, b, flags)
+                if joint:
+                    pcds = ds.train_batch(bi + epoch * len(ds), lo, hi)
+                    ctx, mean_pp, logvar_pp, flag_pp, loss_dict, _ = self.encoder(pcds, self.device, epoch=epoch)
+                    from .models.encoders.part_encoders import _exp_shift
+                    x0 = pcds["ref"].to(self.device).transpose(1, 2).contiguous()
+                    b = dict(anchors=mean_pp, variance=_exp_shift(logvar_pp), code=ctx[0], params=ctx[1],
+                             assign=pcds["ref_seg_mask"].to(self.device).int(), valid=pcds["present"].to(self.device))
+                    loss = _LossModule.forward_through(model, self.diffusion, x0, t, b, flag_pp) + loss_dict["prior_loss"] + loss_dict["fit_loss"].sum()
+                else:
+                    b = {k: v.to(self.device) for k, v in ds.batch(bi + epoch * len(ds), lo, hi).items()}
+                    x0 = torch.sqrt(b["variance"]) * torch.randn_like(b["anchors"]) + b["anchors"]
+                    flags = torch.ones(hi - lo, 1, x0.shape[2], device=self.device)
+                    # DDP hooks fire on the wrapped module's forward: route the loss through it
+                    loss = _LossModule.forward_through(model, self.diffusion, x0, t, b, flags)
                 loss.backward()
+                if joint and self.world > 1:  # the encoder is not DDP-wrapped: average its gradients explicitly
+                    for p in self.encoder.parameters():
+                        if p.grad is not None:
+                            dist.all_reduce(p.grad)
+                            p.grad /= self.world
                 if max_norm:
-                    torch.nn.utils.clip_grad_norm_(self.diffusion.parameters(), max_norm)
+                    torch.nn.utils.clip_grad_norm_(params, max_norm)
                 opt.step()
                 it += 1
                 losses.append(loss.detach())
                 if it % log_interval == 0 and self.rank == 0:
-                    print(f"[Runner] epoch {epoch} iter {it} mse_loss {torch.stack(losses[-log_interval:]).mean().item():.5f}")
+                    print(f"[Runner] epoch {epoch} iter {it} loss {torch.stack(losses[-log_interval:]).mean().item():.5f}")
                 if max_iters is not None and it >= max_iters:
                     break
             if ((epoch + 1) % ckpt_interval == 0 or epoch + 1 == max_epoch or (max_iters is not None and it >= max_iters)) and self.rank == 0:
                 self.save(epoch + 1, it, opt)
             if max_iters is not None and it >= max_iters:
                 break
+        if joint:
+            self.encoder.eval()
         self.diffusion.eval()
         return torch.stack(losses).cpu()
 

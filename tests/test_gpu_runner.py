@@ -29,20 +29,37 @@ def small_cfg(tmp_path):
     return tmp_path
 
 
+@pytest.fixture()
+def small_gen_cfg(tmp_path):
+    from difffacto_b200.config import init_cfg
+    p = tmp_path / "small_gen.py"
+    p.write_text(textwrap.dedent(f"""
+        _base_ = '{ROOT}/configs/gen_chair.py'
+        model = dict(num_timesteps=8, npoints=256, ret_traj=False)
+        dataset = dict(val=dict(type="SyntheticPartSeg", batch_size=4, npoints=256, n_parts=4, num_batches=1, seed=0))
+        work_dir = '{tmp_path}/work'
+    """))
+    init_cfg(str(p))
+    return tmp_path
+
+
 def test_train_task_updates_weights_and_writes_reference_layout_checkpoint(small_cfg):
     import difffacto_b200  # noqa: F401
     import difffacto_b200.datasets  # noqa: F401
     from difffacto_b200.runner import Runner
     r = Runner("cuda:0", None)
     before = {k: v.clone() for k, v in r.diffusion.state_dict().items()}
+    assert r.encoder is not None and type(r.encoder.encoder).__name__ == "PointNetV2"   # stage 1: encoder + denoiser jointly
+    enc_before = {k: v.clone() for k, v in r.encoder.named_parameters()}
     losses = r.run()
     assert losses.numel() == 6 and torch.isfinite(losses).all()
     after = r.diffusion.state_dict()
     changed = sum(not torch.equal(before[k], after[k]) for k in before)
     assert changed == len(before) == 77
+    assert all(not torch.equal(enc_before[k], v) for k, v in r.encoder.named_parameters())
     ck = torch.load(os.path.join(str(small_cfg), "work", "checkpoints", "ckpt_2.pth"), map_location="cpu")
     assert set(ck) >= {"meta", "model", "decoder", "optimizer"} and ck["meta"]["iter"] == 6
-    assert all(k.startswith("diffusion.model.") for k in ck["model"])
+    assert all(k.startswith(("diffusion.model.", "encoder.")) for k in ck["model"]) and "encoder" in ck
     # the checkpoint restores through the key-tolerant loader (as a reference checkpoint would)
     r2 = Runner("cuda:0", None)
     r2.load(os.path.join(str(small_cfg), "work", "checkpoints", "ckpt_2.pth"))
@@ -84,7 +101,8 @@ def test_val_task_writes_results(small_cfg):
     assert os.path.exists(os.path.join(str(small_cfg), "work", "results.npz"))
 
 
-def test_val_gen_task_generates_from_the_prior(small_cfg):
+def test_val_gen_task_generates_from_the_prior(small_gen_cfg):
+    small_cfg = small_gen_cfg
     """--task val_gen: prior -> flows -> part aligner -> fused sampler (random-init weights: finite output, right shapes)."""
     import difffacto_b200  # noqa: F401
     import difffacto_b200.datasets  # noqa: F401
