@@ -179,6 +179,7 @@ class AnchoredDiffusion(Module):
                                                   ptr(cond.contiguous()), ptr(out), stream()))
         return out
 
+    @torch.no_grad()  # sampling never needs a graph (the reference wraps its loop in no_grad, :577); keeps the fused inference kernels
     def p_sample(self, x, t, anchors, ctx=None, variance=None, anchor_assignment=None, valid_id=None, noise=None):
         """One reverse step; returns {'sample', 'pred_xstart'} like the reference (:450-484).
         `noise` (optional) overrides the torch.randn_like draw."""
