@@ -53,16 +53,46 @@ chamfer_kernel(int n, int m, const float* __restrict__ xyz1, const float* __rest
       tile[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
     }
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < len; ++k) {
-      const float4 p = tile[k];
+    if (QPT % 2 == 0) {
+      // two query points per packed fp32x2 instruction (FADD2/FMUL2/FFMA2 round each half like the
+      // scalar ops; p - q == p + (-q) exactly): 3 FP issue slots per pair test instead of 6
+      float2 nx[(QPT + 1) / 2], ny[(QPT + 1) / 2], nz[(QPT + 1) / 2];
 #pragma unroll
-      for (int i = 0; i < QPT; ++i) {
-        // reference: x2 = buf - x1; dist = x2*x2 + y2*y2 + z2*z2 (same FMA contraction as sq3)
-        const float d = sq3(p.x - qx[i], p.y - qy[i], p.z - qz[i]);
-        if (d < best[i]) {
-          best[i] = d;
-          bi[i] = k0 + k;
+      for (int i = 0; i < QPT / 2; ++i) {
+        nx[i] = make_float2(-qx[2 * i], -qx[2 * i + 1]);
+        ny[i] = make_float2(-qy[2 * i], -qy[2 * i + 1]);
+        nz[i] = make_float2(-qz[2 * i], -qz[2 * i + 1]);
+      }
+#pragma unroll 4
+      for (int k = 0; k < len; ++k) {
+        const float4 p = tile[k];
+        const float2 px = make_float2(p.x, p.x), py = make_float2(p.y, p.y), pz = make_float2(p.z, p.z);
+#pragma unroll
+        for (int i = 0; i < QPT / 2; ++i) {
+          const float2 dx = __fadd2_rn(px, nx[i]), dy = __fadd2_rn(py, ny[i]), dz = __fadd2_rn(pz, nz[i]);
+          const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+          if (d.x < best[2 * i]) {
+            best[2 * i] = d.x;
+            bi[2 * i] = k0 + k;
+          }
+          if (d.y < best[2 * i + 1]) {
+            best[2 * i + 1] = d.y;
+            bi[2 * i + 1] = k0 + k;
+          }
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < len; ++k) {
+        const float4 p = tile[k];
+#pragma unroll
+        for (int i = 0; i < QPT; ++i) {
+          // reference: x2 = buf - x1; dist = x2*x2 + y2*y2 + z2*z2 (same FMA contraction as sq3)
+          const float d = sq3(p.x - qx[i], p.y - qy[i], p.z - qz[i]);
+          if (d < best[i]) {
+            best[i] = d;
+            bi[i] = k0 + k;
+          }
         }
       }
     }

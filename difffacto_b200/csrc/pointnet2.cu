@@ -10,6 +10,7 @@
 // over (cloud, centre/point tile, channel tile) so that a batch fills the 148 SMs, xyz tiles are
 // staged in shared memory, and idx/out traffic is coalesced and 128-bit vectorised.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -294,6 +295,110 @@ fps_kernel(int n, int m, int log2bs, int qbits, const float* __restrict__ datase
   }
 }
 
+// Fast path: THREADS == the reference's block size bs (>= 32).  Then point k = tid + i*bs has
+// rank (bitrev(tid) << qbits) | i, ascending in i inside a thread, so the in-thread arg-max needs
+// only the strict `>` of the reference (no rank compare per point) and the thread's rank is
+// `rbase | best_i`.  Skipped points (|p|^2 <= 1e-3) carry td = -1: fminf keeps them at -1 and
+// `-1 > best` never fires, so there is no per-point branch; pairs of points go through the packed
+// fp32x2 pipe (FADD2/FMUL2/FFMA2 round each half exactly like the scalar ops).  A round costs
+// ~7 issue slots per point pair instead of ~44.
+__device__ __forceinline__ float2 sq3x2(float2 dx, float2 dy, float2 dz) {
+  return __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+}
+
+template <int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+fps_fast_kernel(int n, int m, int log2bs, int qbits, const float* __restrict__ dataset,
+                float* __restrict__ temp, int* __restrict__ idxs) {
+  extern __shared__ float fps_smem[];  // xs[n], ys[n], zs[n]
+  constexpr int NW = THREADS / 32;
+  constexpr int NP = (PPT + 1) / 2;
+  __shared__ uint2 slot[2][NW];
+  float* xs = fps_smem;
+  float* ys = xs + n;
+  float* zs = ys + n;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* pts = dataset + (size_t)b * n * 3;
+  int* out = idxs + (size_t)b * m;
+
+  for (int i = tid; i < n * 3; i += THREADS) {
+    const float v = __ldg(pts + i);
+    const int k = i / 3, ch = i - k * 3;
+    (ch == 0 ? xs : ch == 1 ? ys : zs)[k] = v;
+  }
+  __syncthreads();
+
+  float2 px[NP], py[NP], pz[NP], td[NP];
+#pragma unroll
+  for (int i = 0; i < 2 * NP; ++i) {
+    const int k = tid + i * THREADS;
+    const bool in = (i < PPT) && (k < n);
+    const float x = in ? xs[k] : 0.f, y = in ? ys[k] : 0.f, z = in ? zs[k] : 0.f;
+    const float mag = sq3(x, y, z);
+    const bool ok = in && !((double)mag <= 1e-3);  // reference: fp32 mag, double compare
+    const float t0 = ok ? 1e10f : -1.f;
+    if (i & 1) { px[i >> 1].y = x; py[i >> 1].y = y; pz[i >> 1].y = z; td[i >> 1].y = t0; }
+    else       { px[i >> 1].x = x; py[i >> 1].x = y; pz[i >> 1].x = z; td[i >> 1].x = t0; }
+  }
+  const unsigned rbase = (__brev((unsigned)tid) >> (32 - log2bs)) << qbits;
+
+  int old = 0;
+  if (tid == 0 && m > 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float nx = -xs[old], ny = -ys[old], nz = -zs[old];  // x - x1 == x + (-x1) exactly
+    const float2 nx2 = make_float2(nx, nx), ny2 = make_float2(ny, ny), nz2 = make_float2(nz, nz);
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float2 d = sq3x2(__fadd2_rn(px[i], nx2), __fadd2_rn(py[i], ny2), __fadd2_rn(pz[i], nz2));
+      const float a = fminf(d.x, td[i].x), c = fminf(d.y, td[i].y);
+      td[i] = make_float2(a, c);
+      bool take = a > best;
+      best = take ? a : best;
+      besti = take ? 2 * i : besti;
+      take = c > best;
+      best = take ? c : best;
+      besti = take ? 2 * i + 1 : besti;
+    }
+    const unsigned key = best < 0.f ? 0u : (__float_as_uint(best) + 1u);
+    const unsigned brank = best < 0.f ? 0xFFFFFFFFu : (rbase | (unsigned)besti);
+    unsigned wkey = __reduce_max_sync(0xFFFFFFFFu, key);
+    unsigned wrank = __reduce_min_sync(0xFFFFFFFFu, key == wkey ? brank : 0xFFFFFFFFu);
+    if (NW > 1) {
+      if (lane == 0) slot[j & 1][warp] = make_uint2(wkey, wrank);
+      __syncthreads();
+      const uint2 s = lane < NW ? slot[j & 1][lane] : make_uint2(0u, 0xFFFFFFFFu);
+      wkey = __reduce_max_sync(0xFFFFFFFFu, s.x);
+      wrank = __reduce_min_sync(0xFFFFFFFFu, s.x == wkey ? s.y : 0xFFFFFFFFu);
+    }
+    old = (wkey == 0u) ? 0 : fps_unrank(wrank, log2bs, qbits);
+    if (tid == 0) out[j] = old;
+  }
+  if (temp != nullptr) {  // skipped points keep the caller's 1e10 initialisation
+    float* t = temp + (size_t)b * n;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = tid + i * THREADS;
+      const float v = (i & 1) ? td[i >> 1].y : td[i >> 1].x;
+      if (k < n) t[k] = v < 0.f ? 1e10f : v;
+    }
+  }
+}
+
+template <int PPT, int THREADS>
+static int launch_fps_fast(int b, int n, int m, int log2bs, int qbits, const float* dataset, float* temp,
+                           int* idxs, cudaStream_t st) {
+  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  if (smem + 1024 > 48 * 1024) {  // static slots count against the 48 KB default too
+    DFB_CUDA(cudaFuncSetAttribute(fps_fast_kernel<PPT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  fps_fast_kernel<PPT, THREADS><<<b, THREADS, smem, st>>>(n, m, log2bs, qbits, dataset, temp, idxs);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
 // reference cuda_utils.h:15-19 -- evaluated in double exactly as there (the quotient of logs can
 // land just below an integer, which changes the block size and therefore the tie rule).
 static int ref_opt_n_threads(int work_size) {
@@ -308,7 +413,7 @@ template <int PPT, int THREADS, bool REGPTS>
 static int launch_fps(int b, int n, int m, int log2bs, int qbits, const float* dataset, float* temp,
                       int* idxs, cudaStream_t st) {
   const size_t smem = sizeof(float) * 3 * (size_t)n;
-  if (smem > 48 * 1024) {
+  if (smem + 1024 > 48 * 1024) {  // static slots count against the 48 KB default too
     DFB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, THREADS, REGPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   fps_kernel<PPT, THREADS, REGPTS><<<b, THREADS, smem, st>>>(n, m, log2bs, qbits, dataset, temp, idxs);
@@ -323,14 +428,55 @@ static int launch_fps(int b, int n, int m, int log2bs, int qbits, const float* d
 // index order with ballot + prefix-popcount (keeps "first nsample in ascending k"), exact early
 // exit once nsample hits are found, coalesced idx writes.  The cloud tile is staged once per CTA
 // in shared memory (SoA) and reused by CENTRES_PER_WARP * 8 centres.
+// Ordered scan of one centre by one warp (brute force, exact early exit).
+template <bool SMEM>
+__device__ __forceinline__ void bq_warp_scan(int n, float radius2, int nsample, float cx, float cy, float cz,
+                                             const float* xs, const float* ys, const float* zs,
+                                             const float* __restrict__ pts, int* __restrict__ o, int lane) {
+  int cnt = 0, first = 0;
+  for (int k0 = 0; k0 < n && cnt < nsample; k0 += 128) {
+    unsigned mask[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 32 + lane;
+      bool hit = false;
+      if (k < n) {
+        float x, y, z;
+        if (SMEM) {
+          x = xs[k]; y = ys[k]; z = zs[k];
+        } else {
+          x = __ldg(pts + 3 * k); y = __ldg(pts + 3 * k + 1); z = __ldg(pts + 3 * k + 2);
+        }
+        const float d2 = sq3(cx - x, cy - y, cz - z);
+        hit = d2 < radius2;  // reference: `if (d2 < radius2)` (PTX setp.geu + branch)
+      }
+      mask[u] = __ballot_sync(0xFFFFFFFFu, hit);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (mask[u] != 0u && cnt < nsample) {
+        if (cnt == 0) first = k0 + u * 32 + __ffs(mask[u]) - 1;
+        const int pos = cnt + __popc(mask[u] & lanemask_lt());
+        if (((mask[u] >> lane) & 1u) && pos < nsample) o[pos] = k0 + u * 32 + lane;
+        cnt += __popc(mask[u]);
+      }
+    }
+  }
+  // slots never reached keep the first hit (or 0 for an empty ball)
+  for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) o[l] = first;
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(256)
-ball_query_kernel(int n, int m, float radius2, int nsample, int centres_per_warp,
+ball_query_kernel(int n, int m, float radius2, int nsample, int centres_per_warp, int only_marked,
                   const float* __restrict__ new_xyz, const float* __restrict__ xyz,
                   int* __restrict__ idx) {
   extern __shared__ float bq_smem[];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // second launch of the grid path: only the tiles the grid kernel handed over (sentinel -1 in the
+  // first output slot of the tile, which this CTA alone overwrites)
+  if (only_marked && idx[((size_t)b * m + (size_t)blockIdx.x * 8 * centres_per_warp) * nsample] != -1) return;
   const float* pts = xyz + (size_t)b * n * 3;
   float* xs = bq_smem;
   float* ys = xs + n;
@@ -349,39 +495,291 @@ ball_query_kernel(int n, int m, float radius2, int nsample, int centres_per_warp
     if (j >= m) break;
     const float* cq = new_xyz + ((size_t)b * m + j) * 3;
     const float cx = __ldg(cq), cy = __ldg(cq + 1), cz = __ldg(cq + 2);
-    int* o = idx + ((size_t)b * m + j) * nsample;
-    int cnt = 0, first = 0;
-    for (int k0 = 0; k0 < n && cnt < nsample; k0 += 128) {
-      unsigned mask[4];
+    bq_warp_scan<SMEM>(n, radius2, nsample, cx, cy, cz, xs, ys, zs, pts, idx + ((size_t)b * m + j) * nsample, lane);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Grid path (1024 <= n <= 8192): sparse balls (r = 0.1 / 0.2 on a unit-scale cloud hold 6 / 43 of
+// 2048 points on average, so 77-92 % of the centres scan ALL n points in the brute-force kernel).
+// Each CTA bins the cloud into a uniform grid of cell size >= 1.001 r (at most 16 cells per axis)
+// with a shared-memory counting sort, then a GROUP OF 8 LANES per centre walks the <= 9
+// x-contiguous runs of the centre's 3x3x3 cell neighbourhood (8.7x / 57x fewer pair tests at
+// r = 0.2 / 0.1; 8 lanes match the typical run length, a full warp would idle on short runs and a
+// single thread is latency- and divergence-bound -- measured).  The cells are visited out of index
+// order, so every hit sets a bit (shared-memory atomicOr) in a per-centre n-bit map; the group then
+// reads the map back in ascending index order (popcount prefix scan) to emit "the first nsample
+// hits in index order, padded with the first hit" -- bit-identical to the ordered scan.
+// Degenerate inputs (non-finite bounding box, r <= 0) and dense balls (few occupied cells: no
+// pruning, and the unordered walk cannot stop early) are handed over, per cloud, to the ordered-scan
+// kernel launched right after on the same stream: the grid kernel writes the sentinel -1 into the
+// first output slot of every scan tile it skips, and a scan CTA that does not find it exits at once.
+constexpr int BQG_G = 16;
+constexpr int BQG_CELLS = BQG_G * BQG_G * BQG_G;
+constexpr int BQG_MIN_OCCUPIED = 135;  // ~27 n / occupied candidates per centre; above ~n/5 the ordered scan with early exit wins (measured)
+constexpr int BQG_T = 256;            // threads per CTA
+constexpr int BQG_LPC = 8;            // lanes per centre
+constexpr int BQG_GPW = 32 / BQG_LPC; // centres per warp and pass
+__device__ __forceinline__ int bqg_phys(int c) { return c + (c >> 5); }  // de-conflicts the chunked scan
+// words of one bitmap, padded so that the 4 maps of a warp start 8 banks apart
+static __host__ __device__ inline int bqg_stride(int n) { return ((n + 1023) / 1024) * 32 + BQG_LPC; }
+
+static size_t bqg_smem_bytes(int n) {
+  const size_t bitmaps = 4 * (size_t)(BQG_T / BQG_LPC) * bqg_stride(n);
+  const size_t counters = 4 * (size_t)(BQG_CELLS + BQG_CELLS / 32 + 1);
+  const size_t u = bitmaps > counters ? bitmaps : counters;
+  return 16 * (size_t)n + (size_t)((2 * (BQG_CELLS + 1) + 15) / 16 * 16) + (u + 15) / 16 * 16;
+}
+
+__global__ void __launch_bounds__(BQG_T)
+ball_query_grid_kernel(int nb, int n, int m, float radius, float radius2, int nsample, int scan_tile,
+                       const float* __restrict__ new_xyz, const float* __restrict__ xyz,
+                       int* __restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char bqg_smem[];
+  constexpr int T = BQG_T, NW = T / 32, LPC = BQG_LPC, GPW = BQG_GPW;
+  constexpr int CHUNK = BQG_CELLS / T;
+  __shared__ float red[NW][6];
+  __shared__ unsigned wsum[NW];
+  __shared__ int s_occ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int words = (n + 31) >> 5;
+  float4* S = reinterpret_cast<float4*>(bqg_smem);                                    // sorted (x, y, z, index)
+  unsigned short* E = reinterpret_cast<unsigned short*>(bqg_smem + 16 * (size_t)n);    // E[c] = start of cell c
+  unsigned* U = reinterpret_cast<unsigned*>(bqg_smem + 16 * (size_t)n + (2 * (BQG_CELLS + 1) + 15) / 16 * 16);
+  // Balanced static partition: the work items are (cloud, pass of 32 centres), cloud-major; CTA i owns
+  // a contiguous slice, i.e. a few whole or partial clouds, and builds the grid once per cloud it touches.
+  const int ppc = (m + NW * GPW - 1) / (NW * GPW);
+  const long long items = (long long)nb * ppc;
+  const long long it_lo = items * blockIdx.x / gridDim.x, it_hi = items * (blockIdx.x + 1) / gridDim.x;
+  for (long long it0 = it_lo; it0 < it_hi;) {
+  const int b = (int)(it0 / ppc);
+  const long long it1 = min(it_hi, (long long)(b + 1) * ppc);
+  const int jlo = (int)(it0 - (long long)b * ppc) * (NW * GPW), jhi = min(m, (int)(it1 - (long long)b * ppc) * (NW * GPW));
+  it0 = it1;
+  const float* pts = xyz + (size_t)b * n * 3;
+
+  // ---- bounding box of the cloud -------------------------------------------------------------
+  float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+  bool fin = true;
+#pragma unroll 4
+  for (int k = tid; k < n; k += T) {
+    const float x = __ldg(pts + 3 * k), y = __ldg(pts + 3 * k + 1), z = __ldg(pts + 3 * k + 2);
+    fin = fin && isfinite(x) && isfinite(y) && isfinite(z);
+    lx = fminf(lx, x); ly = fminf(ly, y); lz = fminf(lz, z);
+    hx = fmaxf(hx, x); hy = fmaxf(hy, y); hz = fmaxf(hz, z);
+  }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + u * 32 + lane;
-        bool hit = false;
-        if (k < n) {
-          float x, y, z;
-          if (SMEM) {
-            x = xs[k]; y = ys[k]; z = zs[k];
-          } else {
-            x = __ldg(pts + 3 * k); y = __ldg(pts + 3 * k + 1); z = __ldg(pts + 3 * k + 2);
-          }
-          const float d2 = sq3(cx - x, cy - y, cz - z);
-          hit = d2 < radius2;  // reference: `if (d2 < radius2)` (PTX setp.geu + branch)
-        }
-        mask[u] = __ballot_sync(0xFFFFFFFFu, hit);
+  for (int d = 16; d > 0; d >>= 1) {
+    lx = fminf(lx, __shfl_xor_sync(0xFFFFFFFFu, lx, d)); ly = fminf(ly, __shfl_xor_sync(0xFFFFFFFFu, ly, d));
+    lz = fminf(lz, __shfl_xor_sync(0xFFFFFFFFu, lz, d)); hx = fmaxf(hx, __shfl_xor_sync(0xFFFFFFFFu, hx, d));
+    hy = fmaxf(hy, __shfl_xor_sync(0xFFFFFFFFu, hy, d)); hz = fmaxf(hz, __shfl_xor_sync(0xFFFFFFFFu, hz, d));
+  }
+  if (tid == 0) s_occ = 0;
+  if (lane == 0) { red[warp][0] = lx; red[warp][1] = ly; red[warp][2] = lz; red[warp][3] = hx; red[warp][4] = hy; red[warp][5] = hz; }
+  const int all_finite = __syncthreads_and(fin ? 1 : 0);
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    lx = fminf(lx, red[w][0]); ly = fminf(ly, red[w][1]); lz = fminf(lz, red[w][2]);
+    hx = fmaxf(hx, red[w][3]); hy = fmaxf(hy, red[w][4]); hz = fmaxf(hz, red[w][5]);
+  }
+  bool brute = !(all_finite && radius > 0.f && isfinite(radius));
+
+  // ---- grid: cell size >= 1.001 r, <= 16 cells per axis ----------------------------------------
+  // |p - c| < r implies the cell coordinates of p and c differ by < 1/1.001 + O(1e-5) on every axis,
+  // so all hits of a centre lie in its 3x3x3 neighbourhood, with margin for the fp32 rounding of
+  // the coordinates and of the d2 < r2 test.
+  const float cell = radius * 1.001f;
+  const float csx = fmaxf(cell, (hx - lx) * (1.0f / 15.99f)), csy = fmaxf(cell, (hy - ly) * (1.0f / 15.99f)),
+              csz = fmaxf(cell, (hz - lz) * (1.0f / 15.99f));
+  const float ivx = 1.0f / csx, ivy = 1.0f / csy, ivz = 1.0f / csz;
+  int gx = 1, gy = 1, gz = 1;
+  if (!brute) {
+    gx = min((int)((hx - lx) * ivx) + 1, BQG_G);
+    gy = min((int)((hy - ly) * ivy) + 1, BQG_G);
+    gz = min((int)((hz - lz) * ivz) + 1, BQG_G);
+  }
+  const int ncell = gx * gy * gz;
+  // coarse grids cannot have enough occupied cells: skip the build (r = 0.4 on a unit-scale cloud)
+  brute = brute || ncell < 2 * BQG_MIN_OCCUPIED;
+  auto cell_of = [&](float x, float y, float z) {
+    const int ix = min(max((int)floorf((x - lx) * ivx), 0), gx - 1);
+    const int iy = min(max((int)floorf((y - ly) * ivy), 0), gy - 1);
+    const int iz = min(max((int)floorf((z - lz) * ivz), 0), gz - 1);
+    return (iz * gy + iy) * gx + ix;
+  };
+
+  if (!brute) {
+    // ---- counting sort of the points by cell --------------------------------------------------
+    for (int i = tid; i < BQG_CELLS + BQG_CELLS / 32 + 1; i += T) U[i] = 0u;
+    __syncthreads();
+#pragma unroll 4
+    for (int k = tid; k < n; k += T) {
+      const float x = __ldg(pts + 3 * k), y = __ldg(pts + 3 * k + 1), z = __ldg(pts + 3 * k + 2);
+      atomicAdd(&U[bqg_phys(cell_of(x, y, z))], 1u);
+    }
+    __syncthreads();
+    unsigned local = 0u;
+    int occ = 0;
+#pragma unroll 4
+    for (int i = 0; i < CHUNK; ++i) {
+      const int c = tid * CHUNK + i;
+      const unsigned v = c < ncell ? U[bqg_phys(c)] : 0u;
+      local += v;
+      occ += v != 0u;
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    occ = __reduce_add_sync(0xFFFFFFFFu, occ);
+    if (lane == 31) wsum[warp] = incl;
+    if (lane == 0 && occ) atomicAdd(&s_occ, occ);
+    __syncthreads();
+    unsigned run = incl - local;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) run += w < warp ? wsum[w] : 0u;
+#pragma unroll 4
+    for (int i = 0; i < CHUNK; ++i) {
+      const int c = tid * CHUNK + i;
+      if (c < ncell) {
+        const unsigned v = U[bqg_phys(c)];
+        U[bqg_phys(c)] = run;  // start of cell c; the scatter below advances it to the end of c
+        run += v;
       }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = tid; k < n; k += T) {
+      const float x = __ldg(pts + 3 * k), y = __ldg(pts + 3 * k + 1), z = __ldg(pts + 3 * k + 2);
+      const unsigned pos = atomicAdd(&U[bqg_phys(cell_of(x, y, z))], 1u);
+      S[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+    __syncthreads();
+    if (tid == 0) E[0] = 0;
+    for (int c = tid; c < ncell; c += T) E[c + 1] = (unsigned short)U[bqg_phys(c)];
+    brute = s_occ < BQG_MIN_OCCUPIED;
+    __syncthreads();
+  }
+
+  if (brute) {  // hand this slice over to the ordered-scan kernel launched next on the same stream
+    for (int j = jlo + tid; j < jhi; j += T) {
+      if (j % scan_tile == 0) idx[((size_t)b * m + j) * nsample] = -1;
+    }
+    __syncthreads();  // the next cloud's build reuses shared memory
+    continue;
+  }
+
+  // ---- 8 lanes per centre: walk the neighbourhood, mark hits, read the map back in index order ----
+  // All loops below are WARP-uniform (the four groups of a warp run in lockstep, idle lanes are
+  // predicated): group-divergent control flow was measured 4x slower (the groups serialise).
+  const int stride = bqg_stride(n);
+  const int wpl = (stride - LPC) / LPC;  // map words per lane (a multiple of 4)
+  const int g = lane / LPC, gl = lane % LPC;
+  unsigned* BM = U + (size_t)(warp * GPW + g) * stride;
+  for (int i = gl; i < stride; i += LPC) BM[i] = 0u;
+  __syncwarp();
+  const int npass = (jhi - jlo + NW * GPW - 1) / (NW * GPW);
+  for (int pass = 0; pass < npass; ++pass) {
+    const int j = jlo + pass * NW * GPW + warp * GPW + g;
+    const bool valid = j < jhi;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (valid) {
+      const float* cq = new_xyz + ((size_t)b * m + j) * 3;
+      cx = __ldg(cq); cy = __ldg(cq + 1); cz = __ldg(cq + 2);
+    }
+    // cell of the centre, clamped to [-1, g] (centres may lie outside the cloud's box; NaN -> -1)
+    const int icx = (int)fminf(fmaxf(floorf((cx - lx) * ivx), -1.f), (float)gx);
+    const int icy = (int)fminf(fmaxf(floorf((cy - ly) * ivy), -1.f), (float)gy);
+    const int icz = (int)fminf(fmaxf(floorf((cz - lz) * ivz), -1.f), (float)gz);
+    const int x0 = max(icx - 1, 0), x1 = min(icx + 1, gx - 1);
+    // bounds of the 9 (dy, dz) runs (x-contiguous cells are one run): lane r of the group loads run r,
+    // lane 0 also run 8 -- one shared-memory latency for all of them
+    auto run_bounds = [&](int r, int& kb, int& e) {
+      const int dz = r / 3, dy = r - 3 * dz;
+      const int yy = icy - 1 + dy, zz = icz - 1 + dz;
+      kb = 0; e = 0;
+      if (valid && x0 <= x1 && yy >= 0 && yy < gy && zz >= 0 && zz < gz) {
+        const int row = (zz * gy + yy) * gx;
+        kb = E[row + x0];
+        e = E[row + x1 + 1];
+      }
+    };
+    int kbA, eA, kbB = 0, eB = 0;
+    run_bounds(gl, kbA, eA);
+    if (gl == 0) run_bounds(8, kbB, eB);
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+      const int src = g * LPC + (r & 7);
+      const int e = __shfl_sync(0xFFFFFFFFu, r < 8 ? eA : eB, src);
+      int k = __shfl_sync(0xFFFFFFFFu, r < 8 ? kbA : kbB, src) + gl;
+      while (__any_sync(0xFFFFFFFFu, k < e)) {
+        const int k1 = k + LPC;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (k < e) p0 = S[k];
+        if (k1 < e) p1 = S[k1];
+        const float d0 = sq3(cx - p0.x, cy - p0.y, cz - p0.z);
+        const float d1 = sq3(cx - p1.x, cy - p1.y, cz - p1.z);
+        if (k < e && d0 < radius2) {
+          const int q = __float_as_int(p0.w);
+          atomicOr(&BM[q >> 5], 1u << (q & 31));
+        }
+        if (k1 < e && d1 < radius2) {
+          const int q = __float_as_int(p1.w);
+          atomicOr(&BM[q >> 5], 1u << (q & 31));
+        }
+        k += 2 * LPC;
+      }
+    }
+    __syncwarp();
+
+    // read-back: lane gl owns the wpl consecutive words [gl*wpl, (gl+1)*wpl) of its group's map
+    // (ascending index order across the group), so ONE prefix scan over the 8 lane totals places
+    // every lane's hits; two 128-bit loads fetch a lane's words of a 2048-point cloud.
+    int* o = idx + ((size_t)b * m + (valid ? j : 0)) * nsample;
+    uint4* BM4 = reinterpret_cast<uint4*>(BM + gl * wpl);
+    int c = 0, myfirst = 0;
+    for (int i = 0; i < wpl / 4; ++i) {
+      const uint4 v = BM4[i];
+      const unsigned wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (mask[u] != 0u && cnt < nsample) {
-          if (cnt == 0) first = k0 + u * 32 + __ffs(mask[u]) - 1;
-          const int pos = cnt + __popc(mask[u] & lanemask_lt());
-          if (((mask[u] >> lane) & 1u) && pos < nsample) o[pos] = k0 + u * 32 + lane;
-          cnt += __popc(mask[u]);
+        if (c == 0 && wv[u] != 0u) myfirst = (gl * wpl + i * 4 + u) * 32 + __ffs(wv[u]) - 1;
+        c += __popc(wv[u]);
+      }
+    }
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < LPC; d <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d, LPC);
+      if (gl >= d) incl += v;
+    }
+    const int cnt = __shfl_sync(0xFFFFFFFFu, incl, LPC - 1, LPC);
+    const unsigned nz = (__ballot_sync(0xFFFFFFFFu, c != 0) >> (g * LPC)) & ((1u << LPC) - 1u);
+    const int ffirst = __shfl_sync(0xFFFFFFFFu, myfirst, (__ffs(nz) - 1) & (LPC - 1), LPC);  // all lanes: full-mask shuffle
+    const int first = cnt > 0 ? ffirst : 0;
+    int pos = incl - c;
+    for (int i = 0; i < wpl / 4; ++i) {
+      const uint4 v = BM4[i];
+      if (c != 0) BM4[i] = make_uint4(0u, 0u, 0u, 0u);  // ready for the group's next centre
+      unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int base = (gl * wpl + i * 4 + u) * 32;
+        while (wv[u] != 0u && pos < nsample) {
+          o[pos++] = base + __ffs(wv[u]) - 1;
+          wv[u] &= wv[u] - 1u;
         }
       }
     }
-    // slots never reached keep the first hit (or 0 for an empty ball)
-    for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) o[l] = first;
+    if (valid) {
+      for (int l = min(cnt, nsample) + gl; l < nsample; l += LPC) o[l] = first;
+    }
+    __syncwarp();
   }
+  __syncthreads();  // the next cloud's build overwrites the maps / sorted array
+  }  // clouds of this CTA
 }
 
 // ============================================================================================
@@ -587,6 +985,21 @@ extern "C" int dfb200_furthest_point_sampling(int b, int n, int m, const float* 
   const int q = cdiv(n, bs);
   int qbits = 0;
   while ((1 << qbits) < q) ++qbits;
+  // fast path: one thread block of exactly the reference's block size (see fps_fast_kernel)
+#define FPS_FAST(PPT, THREADS) return launch_fps_fast<PPT, THREADS>(b, n, m, log2bs, qbits, dataset, temp, idxs, st)
+  if (bs == 512) {
+    if (q <= 1) FPS_FAST(1, 512);
+    if (q <= 2) FPS_FAST(2, 512);
+    if (q <= 4) FPS_FAST(4, 512);
+    if (q <= 8) FPS_FAST(8, 512);
+    if (q <= 16) FPS_FAST(16, 512);
+  } else if (q <= 2) {
+    if (bs == 256) FPS_FAST(2, 256);
+    if (bs == 128) FPS_FAST(2, 128);
+    if (bs == 64) FPS_FAST(2, 64);
+    if (bs == 32) FPS_FAST(2, 32);
+  }
+#undef FPS_FAST
 #define FPS_CASE(PPT, THREADS, REG) return launch_fps<PPT, THREADS, REG>(b, n, m, log2bs, qbits, dataset, temp, idxs, st)
   if (n <= 32) FPS_CASE(1, 32, true);
   if (n <= 128) FPS_CASE(4, 32, true);
@@ -608,6 +1021,35 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
   DFB_REQUIRE(b <= 65535, DFB200_ERR_INVALID_ARG, "query_ball_point: b > 65535");
   cudaStream_t st = as_stream(stream);
   const float radius2 = radius * radius;  // one fp32 multiply, as in the reference
+  // sparse-ball path: uniform grid + one thread per centre (see ball_query_grid_kernel);
+  // DFB200_BALL_QUERY=scan forces the ordered brute-force scan (A/B measurements)
+  static const bool force_scan = [] { const char* e = getenv("DFB200_BALL_QUERY"); return e != nullptr && e[0] == 's'; }();
+  if (!force_scan && n >= 1024 && n <= 8192 && m >= 32) {
+    const size_t gsm = bqg_smem_bytes(n);
+    // persistent CTAs (as many as fit: shared memory or 8 x 256 threads per SM), balanced static partition
+    int per_sm = (int)((227 * 1024) / (gsm + 1024));
+    per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
+    const int ppc = cdiv(m, BQG_T / BQG_LPC);  // passes of 32 centres per cloud
+    const long long items = (long long)b * ppc, slots = 148LL * per_sm;
+    int ctas;
+    if (2LL * b <= slots) {  // few clouds: k CTAs per cloud (slices never straddle two clouds -> one build each)
+      const int k = (int)(slots / b < ppc ? slots / b : ppc);
+      ctas = b * k;
+    } else {
+      ctas = (int)(items < slots ? items : slots);
+    }
+    DFB_CUDA(cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    int scpw = 8;
+    while (scpw > 1 && (long long)b * cdiv(m, 8 * scpw) < 148 * 4) scpw /= 2;
+    ball_query_grid_kernel<<<ctas, BQG_T, gsm, st>>>(b, n, m, radius, radius2, nsample, 8 * scpw, new_xyz, xyz, idx);
+    DFB_LAUNCH_CHECK();
+    const size_t ssm = sizeof(float) * 3 * (size_t)n;
+    if (ssm > 48 * 1024)
+      DFB_CUDA(cudaFuncSetAttribute(ball_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+    ball_query_kernel<true><<<dim3(cdiv(m, 8 * scpw), b), 256, ssm, st>>>(n, m, radius2, nsample, scpw, 1, new_xyz, xyz, idx);
+    DFB_LAUNCH_CHECK();
+    return DFB200_OK;
+  }
   // centres per warp: keep >= ~4 waves of CTAs on 148 SMs but amortise the smem staging
   int cpw = 8;
   while (cpw > 1 && (long long)b * cdiv(m, 8 * cpw) < 148 * 4) cpw /= 2;
@@ -616,9 +1058,9 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
   if (smem <= 160 * 1024) {
     if (smem > 48 * 1024)
       DFB_CUDA(cudaFuncSetAttribute(ball_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ball_query_kernel<true><<<grid, 256, smem, st>>>(n, m, radius2, nsample, cpw, new_xyz, xyz, idx);
+    ball_query_kernel<true><<<grid, 256, smem, st>>>(n, m, radius2, nsample, cpw, 0, new_xyz, xyz, idx);
   } else {
-    ball_query_kernel<false><<<grid, 256, 0, st>>>(n, m, radius2, nsample, cpw, new_xyz, xyz, idx);
+    ball_query_kernel<false><<<grid, 256, 0, st>>>(n, m, radius2, nsample, cpw, 0, new_xyz, xyz, idx);
   }
   DFB_LAUNCH_CHECK();
   return DFB200_OK;

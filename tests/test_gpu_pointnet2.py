@@ -18,7 +18,8 @@ def pu():
 
 
 FPS_SHAPES = [(3, 2048, 512), (2, 512, 128), (2, 128, 32), (1, 1000, 77), (2, 8192, 256), (1, 33, 33), (1, 1, 1),
-              (1, 5000, 64), (1, 12000, 40)]
+              (1, 5000, 64), (1, 12000, 40), (2, 4096, 300), (1, 1024, 1024), (2, 600, 100), (1, 300, 64), (1, 70, 70),
+              (1, 511, 50), (1, 513, 50)]
 
 
 @pytest.mark.parametrize("B,N,M", FPS_SHAPES)
@@ -61,7 +62,10 @@ def test_fps_temp_output_matches_reference_state():
 
 
 BQ = [(0.2, 64, 2048, 512), (0.4, 64, 512, 128), (0.1, 16, 2048, 512), (0.4, 128, 2048, 512), (0.8, 128, 512, 128),
-      (0.05, 7, 300, 50), (10.0, 5, 100, 3), (0.3, 33, 20000, 64)]
+      (0.05, 7, 300, 50), (10.0, 5, 100, 3), (0.3, 33, 20000, 64),
+      # grid path (1024 <= n <= 4096): ragged m, dense fall-back (0.8 / 2.0), tiny radius, n not a multiple of 32
+      (0.1, 16, 1024, 300), (0.2, 32, 4096, 777), (0.05, 8, 3001, 100), (0.8, 128, 2048, 512), (2.0, 64, 2048, 100),
+      (0.013, 4, 2048, 33), (0.2, 200, 2048, 512), (0.3, 1, 1500, 257), (0.15, 40, 8192, 700), (0.1, 16, 2048, 31)]
 
 
 @pytest.mark.parametrize("r,ns,N,M", BQ)
@@ -77,6 +81,39 @@ def test_ball_query_bit_exact(pu, ref_ext, r, ns, N, M):
     if "ref_pointnet2_ext" in ref_ext:
         ref = ref_ext["ref_pointnet2_ext"].ball_query(cu(new_xyz), cu(xyz), r, ns).cpu().numpy()
         assert np.array_equal(got, ref)
+
+
+def test_ball_query_grid_path_edge_cases(pu, ref_ext):
+    """Inputs that stress the binned path: centres outside / on the faces of the cloud's bounding box, a degenerate
+    (single-point) cloud, planar clouds (one grid axis collapses), non-finite coordinates and r = 0 (ordered-scan
+    fall-back inside the same kernel), many clouds (256-thread variant)."""
+    rng = np.random.default_rng(11)
+    N = 2048
+    cases = []
+    xyz = part_cloud(rng, 2, N)
+    far = np.concatenate([xyz[:, :300] + 0.15 * rng.standard_normal((2, 300, 3)).astype(np.float32),
+                          3.0 * rng.standard_normal((2, 100, 3)).astype(np.float32),
+                          np.stack([xyz.min(1), xyz.max(1)], 1),
+                          np.stack([xyz.min(1) - 0.05, xyz.max(1) + 0.05], 1)], 1).astype(np.float32)
+    cases += [(xyz, far, 0.1, 16), (xyz, far, 0.25, 48)]
+    same = np.tile(np.array([[[0.3, -0.2, 0.1]]], np.float32), (1, N, 1))
+    cases.append((same, same[:, :40] + np.float32(0.01), 0.1, 8))
+    plane = part_cloud(rng, 1, N)
+    plane[..., 2] = 0.25
+    cases.append((plane, plane[:, :128].copy(), 0.1, 32))
+    bad = part_cloud(rng, 3, N)
+    bad[0, 5] = np.nan
+    bad[1, 7, 1] = np.inf
+    bad[2, 9, 2] = -np.inf
+    cases.append((bad, bad[:, 100:200].copy(), 0.2, 16))
+    cases.append((xyz, xyz[:, :64].copy(), 0.0, 4))
+    many = part_cloud(rng, 300, 1024)
+    cases.append((many, many[:, rng.permutation(1024)[:256]].copy(), 0.15, 24))
+    for (p, c, r, ns) in cases:
+        got = pu.ball_query(r, ns, cu(p), cu(c)).cpu().numpy()
+        assert np.array_equal(got, O.ball_query(c, p, r, ns)), (p.shape, c.shape, r, ns)
+        if "ref_pointnet2_ext" in ref_ext:
+            assert np.array_equal(got, ref_ext["ref_pointnet2_ext"].ball_query(cu(c), cu(p), r, ns).cpu().numpy())
 
 
 @pytest.mark.parametrize("B,C,N,NP,NS", [(4, 7, 2048, 512, 64), (2, 131, 512, 128, 64), (2, 320, 512, 128, 32), (1, 3, 50, 7, 5), (2, 4, 100, 9, 1)])
