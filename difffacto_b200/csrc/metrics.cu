@@ -133,7 +133,7 @@ chamfer_grad_kernel(int n, int m, const float* __restrict__ xyz1, const float* _
 // bid -> pick the highest bidder per target -> assign, separated by cluster barriers instead of the reference's 7
 // kernel launches per round (70 000 launches at the evaluation setting iters=10000), and leaves the loop as soon as
 // no point is unassigned (later rounds are no-ops in the reference too, so the result is unchanged).
-//   * The O(U.n) bid scan is split over the C CTAs of the cluster (C = 1..8, chosen so that batch x C fills the SMs):
+//   * The O(U.n) bid scan is split over the C CTAs of the cluster (C = 1..8, or 16 for <= 4 large pairs; chosen so that batch x C fills the SMs):
 //     every CTA keeps a replica of price[] and its own staged target tile; per-target max increment / winner live in
 //     rank 0's shared memory and are updated with distributed-shared-memory atomics; the winner's price update is
 //     written to every replica.  assignment / bids live in global memory (cluster-scope visible across the barriers).
@@ -570,6 +570,23 @@ extern "C" int dfb200_emd_forward(int b, int n, const float* xyz1, const float* 
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.gridDim = dim3(b * C); cfg.blockDim = dim3(EMD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
   cfg.attrs = attr; cfg.numAttrs = 1;
+  // very few, large cloud pairs (batch <= 4, n >= 4096): 8 SMs per pair leave the bid scan far behind the reference's
+  // whole-GPU launches, so opt in to the non-portable 16-CTA cluster when the device can co-schedule one per pair
+  if (C == 8 && b * 16 * 2 <= n_sm && n / 32 >= EMD_SOLO / 2) {
+    static bool np_ok = cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (np_ok) {
+      attr[0].val.clusterDim.x = 16;
+      cfg.gridDim = dim3(b * 16);
+      int active = 0;
+      if (cudaOccupancyMaxActiveClusters(&active, emd_auction_kernel, &cfg) == cudaSuccess && active >= b) {
+        C = 16;
+      } else {
+        (void)cudaGetLastError();
+        attr[0].val.clusterDim.x = C;
+        cfg.gridDim = dim3(b * C);
+      }
+    }
+  }
   DFB_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel, n, xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments,
                               max_increments, unass_idx, unass_cnt, unass_cnt_sum, cnt_tmp, max_idx, eps, iters));
   count_launch();

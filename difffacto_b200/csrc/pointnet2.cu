@@ -520,6 +520,7 @@ constexpr int BQG_MIN_OCCUPIED = 135;  // ~27 n / occupied candidates per centre
 constexpr int BQG_T = 256;            // threads per CTA
 constexpr int BQG_LPC = 8;            // lanes per centre
 constexpr int BQG_GPW = 32 / BQG_LPC; // centres per warp and pass
+constexpr int BQG_MAXSORT = 2048;     // clouds with at most this many centres get them sorted by cell
 __device__ __forceinline__ int bqg_phys(int c) { return c + (c >> 5); }  // de-conflicts the chunked scan
 // words of one bitmap, padded so that the 4 maps of a warp start 8 banks apart
 static __host__ __device__ inline int bqg_stride(int n) { return ((n + 1023) / 1024) * 32 + BQG_LPC; }
@@ -528,11 +529,13 @@ static size_t bqg_smem_bytes(int n) {
   const size_t bitmaps = 4 * (size_t)(BQG_T / BQG_LPC) * bqg_stride(n);
   const size_t counters = 4 * (size_t)(BQG_CELLS + BQG_CELLS / 32 + 1);
   const size_t u = bitmaps > counters ? bitmaps : counters;
-  return 16 * (size_t)n + (size_t)((2 * (BQG_CELLS + 1) + 15) / 16 * 16) + (u + 15) / 16 * 16;
+  return 16 * (size_t)n + (size_t)((2 * (BQG_CELLS + 1) + 15) / 16 * 16) + (u + 15) / 16 * 16 + 4 * (size_t)BQG_MAXSORT;
 }
+static size_t bqg_keys_offset(int n) { return bqg_smem_bytes(n) - 4 * (size_t)BQG_MAXSORT; }
 
 __global__ void __launch_bounds__(BQG_T)
-ball_query_grid_kernel(int nb, int n, int m, float radius, float radius2, int nsample, int scan_tile,
+ball_query_grid_kernel(int nb, int n, int m, int mpad, int keys_off, int min_occupied, float radius, float radius2,
+                       int nsample, int scan_tile,
                        const float* __restrict__ new_xyz, const float* __restrict__ xyz,
                        int* __restrict__ idx) {
   extern __shared__ __align__(16) unsigned char bqg_smem[];
@@ -546,6 +549,7 @@ ball_query_grid_kernel(int nb, int n, int m, float radius, float radius2, int ns
   float4* S = reinterpret_cast<float4*>(bqg_smem);                                    // sorted (x, y, z, index)
   unsigned short* E = reinterpret_cast<unsigned short*>(bqg_smem + 16 * (size_t)n);    // E[c] = start of cell c
   unsigned* U = reinterpret_cast<unsigned*>(bqg_smem + 16 * (size_t)n + (2 * (BQG_CELLS + 1) + 15) / 16 * 16);
+  unsigned* K = reinterpret_cast<unsigned*>(bqg_smem + keys_off);  // (cell << 16 | centre) keys, sorted
   // Balanced static partition: the work items are (cloud, pass of 32 centres), cloud-major; CTA i owns
   // a contiguous slice, i.e. a few whole or partial clouds, and builds the grid once per cloud it touches.
   const int ppc = (m + NW * GPW - 1) / (NW * GPW);
@@ -600,7 +604,7 @@ ball_query_grid_kernel(int nb, int n, int m, float radius, float radius2, int ns
   }
   const int ncell = gx * gy * gz;
   // coarse grids cannot have enough occupied cells: skip the build (r = 0.4 on a unit-scale cloud)
-  brute = brute || ncell < 2 * BQG_MIN_OCCUPIED;
+  brute = brute || ncell < 2 * min_occupied;
   auto cell_of = [&](float x, float y, float z) {
     const int ix = min(max((int)floorf((x - lx) * ivx), 0), gx - 1);
     const int iy = min(max((int)floorf((y - ly) * ivy), 0), gy - 1);
@@ -659,7 +663,7 @@ ball_query_grid_kernel(int nb, int n, int m, float radius, float radius2, int ns
     __syncthreads();
     if (tid == 0) E[0] = 0;
     for (int c = tid; c < ncell; c += T) E[c + 1] = (unsigned short)U[bqg_phys(c)];
-    brute = s_occ < BQG_MIN_OCCUPIED;
+    brute = s_occ < min_occupied;
     __syncthreads();
   }
 
@@ -680,10 +684,42 @@ ball_query_grid_kernel(int nb, int n, int m, float radius, float radius2, int ns
   unsigned* BM = U + (size_t)(warp * GPW + g) * stride;
   for (int i = gl; i < stride; i += LPC) BM[i] = 0u;
   __syncwarp();
+  // Centres in FPS order are scattered over the cloud, so the four groups of a warp see very different
+  // run lengths (the warp pays the maximum).  Sort the cloud's centres by cell (bitonic sort of unique
+  // (cell << 16 | centre) keys: deterministic, every CTA working on this cloud derives the same order) and
+  // let the slices index the sorted order: 33 -> 21 pair-test iterations per warp and pass at r = 0.2.
+  // The sort costs ~9 us per cloud and CTA: worth it only when a CTA runs several passes of the cloud and
+  // the pair-test loop dominates (many candidates per centre).  Both tests use cloud-/launch-level numbers
+  // only, so every CTA working on this cloud takes the same decision.
+  const bool sorted = mpad > 0 && items / gridDim.x >= 6 && 27 * n >= 128 * s_occ;
+  if (sorted) {
+    for (int i = tid; i < mpad; i += T) {
+      unsigned key = 0xFFFFFFFFu;
+      if (i < m) {
+        const float* cq = new_xyz + ((size_t)b * m + i) * 3;
+        key = ((unsigned)cell_of(__ldg(cq), __ldg(cq + 1), __ldg(cq + 2)) << 16) | (unsigned)i;
+      }
+      K[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= mpad; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = tid; i < mpad; i += T) {
+          const int ixj = i ^ jj;
+          if (ixj > i) {
+            const unsigned a = K[i], c = K[ixj];
+            if ((a > c) == ((i & k) == 0)) { K[i] = c; K[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
   const int npass = (jhi - jlo + NW * GPW - 1) / (NW * GPW);
   for (int pass = 0; pass < npass; ++pass) {
-    const int j = jlo + pass * NW * GPW + warp * GPW + g;
-    const bool valid = j < jhi;
+    const int jpos = jlo + pass * NW * GPW + warp * GPW + g;
+    const bool valid = jpos < jhi;
+    const int j = (valid && sorted) ? (int)(K[jpos] & 0xFFFFu) : jpos;
     float cx = 0.f, cy = 0.f, cz = 0.f;
     if (valid) {
       const float* cq = new_xyz + ((size_t)b * m + j) * 3;
@@ -1041,7 +1077,14 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
     DFB_CUDA(cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
     int scpw = 8;
     while (scpw > 1 && (long long)b * cdiv(m, 8 * scpw) < 148 * 4) scpw /= 2;
-    ball_query_grid_kernel<<<ctas, BQG_T, gsm, st>>>(b, n, m, radius, radius2, nsample, 8 * scpw, new_xyz, xyz, idx);
+    int mpad = 0;  // centres are sorted by cell when they fit the key array
+    if (m <= BQG_MAXSORT) {
+      mpad = 32;
+      while (mpad < m) mpad <<= 1;
+    }
+    static const int min_occ = [] { const char* e = getenv("DFB200_BQ_MIN_OCCUPIED"); return e != nullptr ? atoi(e) : BQG_MIN_OCCUPIED; }();
+    ball_query_grid_kernel<<<ctas, BQG_T, gsm, st>>>(b, n, m, mpad, (int)bqg_keys_offset(n), min_occ, radius, radius2, nsample,
+                                                    8 * scpw, new_xyz, xyz, idx);
     DFB_LAUNCH_CHECK();
     const size_t ssm = sizeof(float) * 3 * (size_t)n;
     if (ssm > 48 * 1024)

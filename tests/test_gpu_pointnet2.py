@@ -116,6 +116,20 @@ def test_ball_query_grid_path_edge_cases(pu, ref_ext):
             assert np.array_equal(got, ref_ext["ref_pointnet2_ext"].ball_query(cu(c), cu(p), r, ns).cpu().numpy())
 
 
+def test_ball_query_grid_path_large_batch_sorted_centres(pu, ref_ext):
+    """Batch large enough that every persistent CTA runs >= 6 passes of a cloud: the grid kernel then sorts the
+    centres by cell (bitonic sort) and the slices of different CTAs must still cover every centre exactly once."""
+    rng = np.random.default_rng(21)
+    xyz = part_cloud(rng, 200, 2048)
+    sel = np.stack([rng.permutation(2048)[:500] for _ in range(200)])
+    new_xyz = np.take_along_axis(xyz, sel[..., None].repeat(3, -1), 1).copy()
+    for (r, ns) in ((0.2, 32), (0.25, 20)):
+        got = pu.ball_query(r, ns, cu(xyz), cu(new_xyz)).cpu().numpy()
+        assert np.array_equal(got, O.ball_query(new_xyz, xyz, r, ns))
+        if "ref_pointnet2_ext" in ref_ext:
+            assert np.array_equal(got, ref_ext["ref_pointnet2_ext"].ball_query(cu(new_xyz), cu(xyz), r, ns).cpu().numpy())
+
+
 @pytest.mark.parametrize("B,C,N,NP,NS", [(4, 7, 2048, 512, 64), (2, 131, 512, 128, 64), (2, 320, 512, 128, 32), (1, 3, 50, 7, 5), (2, 4, 100, 9, 1)])
 def test_group_and_gather_bit_exact(pu, ref_ext, B, C, N, NP, NS):
     rng = np.random.default_rng(C + NP)
