@@ -325,3 +325,33 @@ def test_bf16_fused_loop_odd_shapes_track_the_stepwise_fp32_path(B, N, T):
     assert torch.isfinite(a).all() and (a - x).abs().max().item() < 5e-2
     for s_ in range(traj.shape[0]):  # trajectory slot s holds x_t for t = (s+1)*interval
         assert (traj[s_] - kept[(s_ + 1) * 2]).abs().max().item() < 5e-2
+
+
+def test_full_length_sampling_properties_at_baseline_size():
+    """BASELINE configs[1] at full depth (T = 1000 steps, 2048 points x 4 parts; batch 8 keeps the fp32 path short):
+      * determinism: the persistent work-list kernel walks (step, unit) items in a schedule that depends on SM timing, the
+        result must not -- two runs with one Philox seed are bit-identical, a different seed gives a different cloud;
+      * bf16 (tcgen05) vs fp32 (CUDA-core, reference numerics) from IDENTICAL noise, end to end over 1000 steps: the final
+        clouds agree point by point within 2 % of the cloud's scale (measured: mean 0.044, max 0.28 on clouds whose two-seed
+        Chamfer distance is 222 -- random-init weights do not contract), and their Chamfer distance is orders of magnitude
+        below the distance between two independent samples of the same shape (end-to-end criterion)."""
+    from difffacto_b200.metrics.chamfer import chamfer_forward
+    T, B, N = 1000, 8, 2048
+    i = dev(R.synthetic_inputs(77, B, N, False))
+    kw = dict(ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"], valid_id=i["valid"], rng="philox")
+    d16, d32 = build(T, "bf16"), build(T, "fp32")
+    a = d16.p_sample_loop([B, 3, N], i["anchors"], seed=5, **kw)
+    b = d16.p_sample_loop([B, 3, N], i["anchors"], seed=5, **kw)
+    c = d16.p_sample_loop([B, 3, N], i["anchors"], seed=6, **kw)
+    f = d32.p_sample_loop([B, 3, N], i["anchors"], seed=5, **kw)
+    assert torch.isfinite(a).all() and torch.isfinite(f).all()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    spread = (f - i["anchors"]).abs().mean().item()  # scale of the sampled cloud around its anchors (random-init weights: large)
+    dev_pt = (a - f).abs().mean().item()
+    dev_max = (a - f).abs().max().item()
+    pts = lambda x: x.transpose(1, 2).contiguous()
+    cd = lambda x, y: sum(t.mean().item() for t in chamfer_forward(pts(x), pts(y))[:2])
+    cd_prec, cd_seed = cd(a, f), cd(a, c)
+    print(f"[full-length] |bf16 - fp32| mean {dev_pt:.3e} max {dev_max:.3e} (cloud scale {spread:.3f}); CD(bf16, fp32) = {cd_prec:.3e}, CD(seed 5, seed 6) = {cd_seed:.3e}")
+    assert dev_pt < 2e-2 * spread
+    assert cd_prec < 1e-2 * cd_seed
