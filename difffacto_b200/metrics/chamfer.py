@@ -20,7 +20,7 @@ def chamfer_forward(xyz1, xyz2):
     dist2 = torch.empty(B, m, device=dev)
     idx1 = torch.empty(B, n, dtype=torch.int32, device=dev)
     idx2 = torch.empty(B, m, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on(dev):
         check(_lib.load().dfb200_chamfer_forward(B, n, ptr(xyz1), m, ptr(xyz2), ptr(dist1), ptr(dist2), ptr(idx1), ptr(idx2), stream()))
     return dist1, dist2, idx1, idx2
 
@@ -40,7 +40,7 @@ class ChamferFunction(torch.autograd.Function):
         g1 = torch.empty_like(xyz1)
         g2 = torch.empty_like(xyz2)
         B, n, _ = xyz1.shape
-        with torch.cuda.device(xyz1.device):
+        with _lib.on(xyz1.device):
             check(_lib.load().dfb200_chamfer_backward(B, n, ptr(xyz1), xyz2.shape[1], ptr(xyz2), ptr(idx1), ptr(idx2),
                                                       ptr(grad_dist1.contiguous()), ptr(grad_dist2.contiguous()),
                                                       ptr(g1), ptr(g2), stream()))

@@ -36,7 +36,7 @@ class emdFunction(Function):
         unass_cnt = torch.zeros(512, **i32)
         rounds = torch.zeros(512, **i32)      # diagnostics: auction rounds executed per pair ...
         solo_from = torch.zeros(512, **i32)   # ... and the round from which one CTA finished alone
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             check(_lib.load().dfb200_emd_forward(batchsize, n, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(assignment), ptr(price),
                                                  ptr(assignment_inv), ptr(bid), ptr(bid_increments), ptr(max_increments),
                                                  ptr(unass_idx), ptr(unass_cnt), ptr(rounds), ptr(solo_from), ptr(max_idx), float(eps),
@@ -52,7 +52,7 @@ class emdFunction(Function):
         gradxyz1 = torch.empty_like(xyz1)
         gradxyz2 = torch.zeros_like(xyz2)
         B, n, _ = xyz1.shape
-        with torch.cuda.device(xyz1.device):
+        with _lib.on(xyz1.device):
             check(_lib.load().dfb200_emd_backward(B, n, ptr(xyz1), ptr(xyz2), ptr(gradxyz1), ptr(graddist), ptr(assignment), stream()))
         return gradxyz1, gradxyz2, None, None
 

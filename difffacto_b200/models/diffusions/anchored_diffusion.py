@@ -141,7 +141,7 @@ class AnchoredDiffusion(Module):
             from ... import train_ops
             return train_ops.QSampleFn.apply(x_start, anchors, variance, noise, ti, self._sched(x_start.device), self.num_timesteps)
         out = torch.empty_like(x_start)
-        with torch.cuda.device(x_start.device):
+        with _lib.on(x_start.device):
             check(_lib.load().dfb200_q_sample(B, N, self.num_timesteps, ptr(self._sched(x_start.device)), ptr(ti),
                                               ptr(x_start), ptr(anchors), ptr(variance), ptr(noise), ptr(out), stream()))
         return out
@@ -174,7 +174,7 @@ class AnchoredDiffusion(Module):
         uncond = self.model(x, self._scale_timesteps(t), [torch.zeros_like(r) for r in ctx], anchors=anchors.transpose(1, 2),
                             anchor_assignment=anchor_assignment, variances=variance.transpose(1, 2), valid_id=valid_id)
         out = torch.empty_like(cond)
-        with torch.cuda.device(cond.device):
+        with _lib.on(cond.device):
             check(_lib.load().dfb200_guidance_mix(cond.numel(), float(self.classifier_weight), ptr(uncond.contiguous()),
                                                   ptr(cond.contiguous()), ptr(out), stream()))
         return out
@@ -194,7 +194,7 @@ class AnchoredDiffusion(Module):
         sample = torch.empty_like(x)
         pred_xstart = torch.empty_like(x)
         ti = t.to(torch.int32).contiguous()
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             if self.ddim_sampling:
                 tab = self._ddim_tables(x.device)
                 check(_lib.load().dfb200_ddim_step(B, N, self.num_timesteps, ptr(self._sched(x.device)), ptr(ti), ptr(x),
@@ -283,7 +283,7 @@ class AnchoredDiffusion(Module):
         traj = None
         if traj_interval:
             traj = torch.empty(max((T - 1) // traj_interval, 0), B, C, N, device=device)
-        with torch.cuda.device(device):
+        with _lib.on(device):
             check(lib.dfb200_ddpm_sample_loop(cfg, ptr(packed), mode, B, N, T, ptr(self._sched(device)), ptr(x), from_noise,
                                               ptr(ctx), ptr(anchors), ptr(variance), ptr(assign), ptr(valid),
                                               ptr(step_noise), int(seed), ptr(traj), int(traj_interval or 1), ptr(ws), nws,

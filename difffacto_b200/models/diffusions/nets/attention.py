@@ -153,7 +153,7 @@ class TransformerNet(nn.Module):
             freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=128, dtype=torch.float32) / 128).to(dev)
             tensors.append(freqs)
             arr = (_lib.P * len(tensors))(*[t.data_ptr() for t in tensors])
-            with torch.cuda.device(dev):
+            with _lib.on(dev):
                 check(lib.dfb200_denoiser_pack(cfg, arr, len(tensors), ptr(packed), stream()))
                 torch.cuda.current_stream().synchronize()
             self._packed, self._packed_key, self._packed_buf = packed, key, buf
@@ -200,7 +200,7 @@ class TransformerNet(nn.Module):
         packed = self.packed_weights()
         nws = lib.dfb200_denoiser_workspace_bytes(cfg, mode, B, N)
         ws = self.workspace(nws, dev)
-        with torch.cuda.device(dev):
+        with _lib.on(dev):
             check(lib.dfb200_denoiser_forward(cfg, ptr(packed), mode, B, N, ptr(x), ptr(tf), ptr(ctx), ptr(anchors_cm),
                                               ptr(variances_cm), ptr(assign), ptr(valid), ptr(eps), ptr(ws), nws, stream()))
         return eps

@@ -27,7 +27,7 @@ from ..diffusions.nets.attention import _CrossAttention, _FeedForward
 
 
 def _call(name, *args, device):
-    with torch.cuda.device(device):
+    with _lib.on(device):
         check(getattr(_lib.load(), name)(*args, stream()))
 
 

@@ -30,7 +30,7 @@ class FurthestPointSampling(Function):
         require_cuda(xyz)
         B, N, _ = xyz.shape
         out = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
+        with _lib.on(xyz.device):
             check(_lib.load().dfb200_furthest_point_sampling(B, N, npoint, ptr(xyz), None, ptr(out), stream()))
         ctx.mark_non_differentiable(out)
         return out
@@ -53,7 +53,7 @@ class GatherOperation(Function):
         B, C, N = features.shape
         M = idx.shape[1]
         out = torch.empty(B, C, M, dtype=torch.float32, device=features.device)
-        with torch.cuda.device(features.device):
+        with _lib.on(features.device):
             check(_lib.load().dfb200_gather_points(B, C, N, M, ptr(features), ptr(idx), ptr(out), stream()))
         return out
 
@@ -63,7 +63,7 @@ class GatherOperation(Function):
         B, C, N = features.shape
         grad_out = grad_out.contiguous()
         grad = torch.empty(B, C, N, dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on(grad_out.device):
             check(_lib.load().dfb200_gather_points_grad(B, C, N, idx.shape[1], ptr(grad_out), ptr(idx), ptr(grad), stream()))
         return grad, None
 
@@ -81,7 +81,7 @@ class ThreeNN(Function):
         m = known.shape[1]
         dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
         idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
-        with torch.cuda.device(unknown.device):
+        with _lib.on(unknown.device):
             check(_lib.load().dfb200_three_nn(B, n, m, ptr(unknown), ptr(known), ptr(dist2), ptr(idx), stream()))
         dist = torch.sqrt(dist2)
         ctx.mark_non_differentiable(dist, idx)
@@ -105,7 +105,7 @@ class ThreeInterpolate(Function):
         B, c, m = features.shape
         n = idx.shape[1]
         out = torch.empty(B, c, n, dtype=torch.float32, device=features.device)
-        with torch.cuda.device(features.device):
+        with _lib.on(features.device):
             check(_lib.load().dfb200_three_interpolate(B, c, m, n, ptr(features), ptr(idx), ptr(weight), ptr(out), stream()))
         return out
 
@@ -116,7 +116,7 @@ class ThreeInterpolate(Function):
         n = idx.shape[1]
         grad_out = grad_out.contiguous()
         grad = torch.empty(B, c, m, dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on(grad_out.device):
             check(_lib.load().dfb200_three_interpolate_grad(B, c, n, m, ptr(grad_out), ptr(idx), ptr(weight), ptr(grad), stream()))
         return grad, torch.zeros_like(idx), torch.zeros_like(weight)
 
@@ -134,7 +134,7 @@ class GroupingOperation(Function):
         B, C, N = features.shape
         _, npoint, nsample = idx.shape
         out = torch.empty(B, C, npoint, nsample, dtype=torch.float32, device=features.device)
-        with torch.cuda.device(features.device):
+        with _lib.on(features.device):
             check(_lib.load().dfb200_group_points(B, C, N, npoint, nsample, ptr(features), ptr(idx), ptr(out), stream()))
         return out
 
@@ -145,7 +145,7 @@ class GroupingOperation(Function):
         _, npoint, nsample = idx.shape
         grad_out = grad_out.contiguous()
         grad = torch.empty(B, C, N, dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on(grad_out.device):
             check(_lib.load().dfb200_group_points_grad(B, C, N, npoint, nsample, ptr(grad_out), ptr(idx), ptr(grad), stream()))
         return grad, torch.zeros_like(idx)
 
@@ -162,7 +162,7 @@ class BallQuery(Function):
         B, N, _ = xyz.shape
         npoint = new_xyz.shape[1]
         out = torch.empty(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
+        with _lib.on(xyz.device):
             check(_lib.load().dfb200_query_ball_point(B, N, npoint, float(radius), int(nsample), ptr(new_xyz), ptr(xyz), ptr(out), stream()))
         ctx.mark_non_differentiable(out)
         return out

@@ -32,7 +32,7 @@ def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split
             split_k = max(1, min(K // 64, 148 // tiles))
             if split_k > 1 and not beta:
                 C.zero_()
-    with torch.cuda.device(C.device):
+    with _lib.on(C.device):
         check(getattr(_lib.load(), fn)(int(a_kc), int(b_kc), M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), int(beta),
                                        int(split_k), stream()))
 
@@ -95,7 +95,7 @@ class LinearFn(Function):
             _sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=split, bf16=ctx.bf16)  # dW(n,k) = sum_m dy(m,n) x(m,k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.zeros(N, device=x.device, dtype=torch.float32)
-            with torch.cuda.device(x.device):
+            with _lib.on(x.device):
                 check(_lib.load().dfb200_colsum_accumulate(M, N, ptr(dy), N, ptr(db), stream()))
         return dx, dw, db, (dy if ctx.has_res and ctx.needs_input_grad[3] else None)
 
@@ -113,7 +113,7 @@ class LayerNorm128Fn(Function):
         y = torch.empty_like(x)
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty(M, device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             check(_lib.load().dfb200_layernorm128_forward(M, ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), ptr(mean), ptr(rstd), stream()))
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
@@ -125,7 +125,7 @@ class LayerNorm128Fn(Function):
         dx = torch.empty_like(x)
         dg = torch.zeros(128, device=x.device, dtype=torch.float32)
         db = torch.zeros(128, device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             check(_lib.load().dfb200_layernorm128_backward(x.shape[0], ptr(x), ptr(_c(gamma)), ptr(mean), ptr(rstd), ptr(dy), ptr(dx),
                                                            ptr(dg), ptr(db), stream()))
         return dx, dg, db
@@ -141,7 +141,7 @@ class GegluFn(Function):
         h = _c(h)
         M, H2 = h.shape
         u = torch.empty(M, H2 // 2, device=h.device, dtype=torch.float32)
-        with torch.cuda.device(h.device):
+        with _lib.on(h.device):
             check(_lib.load().dfb200_geglu_forward(M, H2 // 2, ptr(h), ptr(u), stream()))
         ctx.save_for_backward(h)
         return u
@@ -150,7 +150,7 @@ class GegluFn(Function):
     def backward(ctx, du):
         (h,) = ctx.saved_tensors
         dh = torch.empty_like(h)
-        with torch.cuda.device(h.device):
+        with _lib.on(h.device):
             check(_lib.load().dfb200_geglu_backward(h.shape[0], h.shape[1] // 2, ptr(h), ptr(_c(du)), ptr(dh), stream()))
         return dh
 
@@ -167,7 +167,7 @@ class PartAttentionFn(Function):
         q, k, v = _c(q), _c(k), _c(v)
         o = torch.empty_like(q)
         probs = torch.empty(B * N, 32, device=q.device, dtype=torch.float32)
-        with torch.cuda.device(q.device):
+        with _lib.on(q.device):
             check(_lib.load().dfb200_part_attention_forward(B, N, ptr(q), ptr(k), ptr(v), ptr(valid), ptr(o), ptr(probs), stream()))
         ctx.save_for_backward(q, k, v, probs)
         ctx.valid, ctx.B, ctx.N = valid, B, N
@@ -179,7 +179,7 @@ class PartAttentionFn(Function):
         dq = torch.empty_like(q)
         dk = torch.zeros_like(k)
         dv = torch.zeros_like(v)
-        with torch.cuda.device(q.device):
+        with _lib.on(q.device):
             check(_lib.load().dfb200_part_attention_backward(ctx.B, ctx.N, ptr(q), ptr(k), ptr(v), ptr(ctx.valid), ptr(probs), ptr(_c(d_o)),
                                                              ptr(dq), ptr(dk), ptr(dv), stream()))
         return dq, dk, dv, None, None, None
@@ -199,7 +199,7 @@ class DropoutFn(Function):
     def forward(ctx, x, p, seed, offset, residual):
         x = _c(x)
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             check(_lib.load().dfb200_dropout(x.numel(), float(p), int(seed), int(offset), ptr(x), ptr(None if residual is None else _c(residual)),
                                              ptr(y), stream()))
         ctx.args = (float(p), int(seed), int(offset))
@@ -211,7 +211,7 @@ class DropoutFn(Function):
         dy = _c(dy)
         dx = torch.empty_like(dy)
         p, seed, offset = ctx.args
-        with torch.cuda.device(dy.device):
+        with _lib.on(dy.device):
             check(_lib.load().dfb200_dropout(dy.numel(), p, seed, offset, ptr(dy), None, ptr(dx), stream()))
         return dx, None, None, None, (dy if ctx.has_res else None)
 
@@ -232,7 +232,7 @@ def timestep_embedding(t, freqs):
     """(B,) float timesteps -> (B,256) sinusoid (no parameters, no gradient)."""
     t = _c(t.to(torch.float32))
     out = torch.empty(t.shape[0], 256, device=t.device, dtype=torch.float32)
-    with torch.cuda.device(t.device):
+    with _lib.on(t.device):
         check(_lib.load().dfb200_timestep_embedding(t.shape[0], ptr(t), ptr(freqs), ptr(out), stream()))
     return out
 
@@ -245,7 +245,7 @@ class QSampleFn(Function):
         x_start, anchors, variance, noise = _c(x_start), _c(anchors), _c(variance), _c(noise)
         B, C, N = x_start.shape
         out = torch.empty_like(x_start)
-        with torch.cuda.device(x_start.device):
+        with _lib.on(x_start.device):
             check(_lib.load().dfb200_q_sample(B, N, T, ptr(sched), ptr(t_i32), ptr(x_start), ptr(anchors), ptr(variance), ptr(noise),
                                               ptr(out), stream()))
         ctx.save_for_backward(variance, noise, t_i32, sched)
@@ -261,7 +261,7 @@ class QSampleFn(Function):
         dx0 = torch.empty_like(g) if need[0] else None
         da = torch.empty_like(g) if need[1] else None
         dv = torch.empty_like(g) if need[2] else None
-        with torch.cuda.device(g.device):
+        with _lib.on(g.device):
             check(_lib.load().dfb200_q_sample_backward(B, N, ctx.T, ptr(sched), ptr(t_i32), ptr(variance), ptr(noise), ptr(g), ptr(dx0),
                                                        ptr(da), ptr(dv), stream()))
         return dx0, da, dv, None, None, None, None
@@ -282,13 +282,13 @@ class BatchNormFn(Function):
             mean = torch.empty(C, device=x.device)
             rstd = torch.empty(C, device=x.device)
             scratch = torch.empty(2 * C, device=x.device)
-            with torch.cuda.device(x.device):
+            with _lib.on(x.device):
                 check(lib.dfb200_batchnorm_forward(M, C, int(relu), ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd),
                                                    ptr(running_mean), ptr(running_var), float(momentum), ptr(scratch), stream()))
         else:
             mean = running_mean
             rstd = torch.rsqrt(running_var + 1e-5)  # C numbers of statistics bookkeeping
-            with torch.cuda.device(x.device):
+            with _lib.on(x.device):
                 check(lib.dfb200_batchnorm_apply(M, C, int(relu), ptr(x), ptr(_c(mean)), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), stream()))
         ctx.save_for_backward(x, y, gamma, mean, rstd)
         ctx.relu, ctx.training = relu, training
@@ -304,7 +304,7 @@ class BatchNormFn(Function):
         dx = torch.empty_like(x)
         dg = torch.empty(C, device=x.device)
         db = torch.empty(C, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             check(_lib.load().dfb200_batchnorm_backward(M, C, int(ctx.relu), ptr(x), ptr(y), ptr(dy), ptr(gamma), ptr(mean), ptr(rstd),
                                                         ptr(dx), ptr(dg), ptr(db), stream()))
         return dx, dg, db, None, None, None, None, None
@@ -322,7 +322,7 @@ class ReluFn(Function):
     @staticmethod
     def forward(ctx, x):
         y = _c(x).clone()
-        with torch.cuda.device(y.device):
+        with _lib.on(y.device):
             check(_lib.load().dfb200_relu(y.numel(), ptr(y), stream()))
         ctx.save_for_backward(y)
         return y
@@ -331,7 +331,7 @@ class ReluFn(Function):
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
         dx = torch.empty_like(y)
-        with torch.cuda.device(y.device):
+        with _lib.on(y.device):
             check(_lib.load().dfb200_relu_backward(y.numel(), ptr(y), ptr(_c(dy)), ptr(dx), stream()))
         return dx
 
@@ -350,7 +350,7 @@ class WeightedMaxPoolFn(Function):
         A = w.shape[2]
         out = torch.empty(B, C, A, device=x.device)
         arg = torch.empty(B, C, A, dtype=torch.int32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.on(x.device):
             check(_lib.load().dfb200_weighted_maxpool_forward(B, N, C, A, float(scale), ptr(x), ptr(w), ptr(out), ptr(arg), stream()))
         ctx.save_for_backward(w, arg)
         ctx.dims, ctx.scale = (B, N, C, A), float(scale)
@@ -361,7 +361,7 @@ class WeightedMaxPoolFn(Function):
         w, arg = ctx.saved_tensors
         B, N, C, A = ctx.dims
         dx = torch.zeros(B, N, C, device=dout.device)
-        with torch.cuda.device(dout.device):
+        with _lib.on(dout.device):
             check(_lib.load().dfb200_weighted_maxpool_backward(B, N, C, A, ctx.scale, ptr(w), ptr(arg), ptr(_c(dout)), ptr(dx), stream()))
         return dx, None, None
 
@@ -379,7 +379,7 @@ class CouplingForwardFn(Function):
         B, d = x2.shape
         y1 = torch.empty_like(x2)
         logdet = torch.empty(B, device=x2.device)
-        with torch.cuda.device(x2.device):
+        with _lib.on(x2.device):
             check(_lib.load().dfb200_coupling_forward(B, d, ptr(s_t), ptr(x2), d, ptr(y1), d, ptr(logdet), stream()))
         ctx.save_for_backward(s_t, x2)
         return y1, logdet
@@ -390,7 +390,7 @@ class CouplingForwardFn(Function):
         B, d = x2.shape
         ds_t = torch.empty_like(s_t)
         dx2 = torch.empty_like(x2)
-        with torch.cuda.device(x2.device):
+        with _lib.on(x2.device):
             check(_lib.load().dfb200_coupling_backward(B, d, ptr(s_t), ptr(x2), d, ptr(_c(dy1)), d, ptr(_c(dlogdet)), ptr(ds_t), ptr(dx2), d,
                                                        stream()))
         return ds_t, dx2
