@@ -869,6 +869,71 @@ three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __
   }
 }
 
+// Two unknown points per thread on the packed fp32x2 pipe (3 FP issue slots per pair test instead of 6), known points
+// staged NEGATED as float4 (u - k == u + (-k) exactly; one broadcast LDS.128 per known point), and ONE compare against
+// the current third-best as the common case: the three-way insertion (the reference's strict `<` chain, so equal
+// distances keep the earlier index) runs only for the ~3 ln(m) candidates per point that enter the top three.
+__device__ __forceinline__ void nn3_insert(float d, int k, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+  if (d < b1) {
+    b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
+  } else if (d < b2) {
+    b3 = b2; i3 = i2; b2 = d; i2 = k;
+  } else {
+    b3 = d; i3 = k;
+  }
+}
+
+constexpr int NN2_TILE = 1024;
+__global__ void __launch_bounds__(256)
+three_nn2_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
+                 float* __restrict__ dist2, int* __restrict__ idx) {
+  __shared__ float4 kt[NN2_TILE];
+  const int b = blockIdx.y;
+  const int j0 = blockIdx.x * (2 * blockDim.x) + threadIdx.x, j1 = j0 + blockDim.x;
+  const float* kn = known + (size_t)b * m * 3;
+  float2 ux = make_float2(0.f, 0.f), uy = ux, uz = ux;
+  if (j0 < n) {
+    const float* u = unknown + ((size_t)b * n + j0) * 3;
+    ux.x = __ldg(u); uy.x = __ldg(u + 1); uz.x = __ldg(u + 2);
+  }
+  if (j1 < n) {
+    const float* u = unknown + ((size_t)b * n + j1) * 3;
+    ux.y = __ldg(u); uy.y = __ldg(u + 1); uz.y = __ldg(u + 2);
+  }
+  float a1 = INFINITY, a2 = INFINITY, a3 = INFINITY, c1 = INFINITY, c2 = INFINITY, c3 = INFINITY;
+  int ia1 = 0, ia2 = 0, ia3 = 0, ic1 = 0, ic2 = 0, ic3 = 0;
+  for (int k0 = 0; k0 < m; k0 += NN2_TILE) {
+    const int tile = min(NN2_TILE, m - k0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tile; k += blockDim.x) {
+      const float* p = kn + (size_t)(k0 + k) * 3;
+      kt[k] = make_float4(-__ldg(p), -__ldg(p + 1), -__ldg(p + 2), 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < tile; ++k) {
+      const float4 q = kt[k];
+      const float2 dx = __fadd2_rn(ux, make_float2(q.x, q.x)), dy = __fadd2_rn(uy, make_float2(q.y, q.y)),
+                   dz = __fadd2_rn(uz, make_float2(q.z, q.z));
+      const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+      if (d.x < a3) nn3_insert(d.x, k0 + k, a1, a2, a3, ia1, ia2, ia3);
+      if (d.y < c3) nn3_insert(d.y, k0 + k, c1, c2, c3, ic1, ic2, ic3);
+    }
+  }
+  if (j0 < n) {
+    float* d = dist2 + ((size_t)b * n + j0) * 3;
+    int* o = idx + ((size_t)b * n + j0) * 3;
+    d[0] = a1; d[1] = a2; d[2] = a3;
+    o[0] = ia1; o[1] = ia2; o[2] = ia3;
+  }
+  if (j1 < n) {
+    float* d = dist2 + ((size_t)b * n + j1) * 3;
+    int* o = idx + ((size_t)b * n + j1) * 3;
+    d[0] = c1; d[1] = c2; d[2] = c3;
+    o[0] = ic1; o[1] = ic2; o[2] = ic3;
+  }
+}
+
 // out[b,l,j] = p1*w1 + p2*w2 + p3*w3 rounded as the reference's SASS does:
 // fma(p3,w3, fma(p1,w1, mul(p2,w2))).  idx/weight of a point are loaded once and reused for the
 // whole channel tile; writes are coalesced along j.
@@ -1114,6 +1179,13 @@ extern "C" int dfb200_three_nn(int b, int n, int m, const float* unknown, const 
   DFB_REQUIRE(b >= 0 && n >= 0 && m >= 0, DFB200_ERR_INVALID_ARG, "three_nn: negative size");
   if (b == 0 || n == 0) return DFB200_OK;
   DFB_REQUIRE(b <= 65535, DFB200_ERR_INVALID_ARG, "three_nn: b > 65535");
+  static const bool legacy = [] { const char* e = getenv("DFB200_THREE_NN"); return e != nullptr && e[0] == '1'; }();  // A/B
+  if (!legacy && (long long)b * cdiv(n, 128) >= 148 * 2) {  // enough work for two unknown points per thread
+    const int threads = (long long)b * cdiv(n, 512) >= 148 * 2 ? 256 : 64;
+    three_nn2_kernel<<<dim3(cdiv(n, 2 * threads), b), threads, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+    DFB_LAUNCH_CHECK();
+    return DFB200_OK;
+  }
   const int threads = (long long)b * cdiv(n, 256) >= 148 * 2 ? 256 : 64;
   dim3 grid(cdiv(n, threads), b);
   three_nn_kernel<<<grid, threads, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);

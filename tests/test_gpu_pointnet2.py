@@ -163,7 +163,10 @@ def test_gather_all_shapes_of_the_sampling_path(pu):
     assert np.array_equal(out, O.gather_points(mean, seg))
 
 
-@pytest.mark.parametrize("B,n,m", [(3, 2048, 512), (2, 512, 128), (1, 100, 5000), (2, 7, 2), (1, 5, 3)])
+@pytest.mark.parametrize("B,n,m", [(3, 2048, 512), (2, 512, 128), (1, 100, 5000), (2, 7, 2), (1, 5, 3),
+                                   # two-unknowns-per-thread kernel (batch x n large enough): 64- and 256-thread variants,
+                                   # odd n, several known tiles, fewer than 3 known points
+                                   (40, 2048, 512), (300, 1001, 77), (80, 600, 2500), (200, 300, 2)])
 def test_three_nn_bit_exact(pu, ref_ext, B, n, m):
     rng = np.random.default_rng(n + m)
     unknown = part_cloud(rng, B, n, origin_frac=0)
