@@ -511,10 +511,14 @@ extern "C" int dfb200_chamfer_forward(int b, int n, const float* xyz1, int m, co
     return DFB200_OK;
   }
   const int nq = n > m ? n : m;
-  // 4 queries per thread when that still gives >= 2 waves of CTAs, else 1
+  // 4 queries per thread when that still gives >= 2 CTAs per SM, 2 (still on the packed fp32x2 pipe) for mid-size
+  // batches, else 1
   if ((long long)cdiv(nq, 512) * b * 2 >= 148 * 2) {
     dim3 grid(cdiv(nq, 512), b, 2);
     chamfer_kernel<4><<<grid, 128, 0, st>>>(n, m, xyz1, xyz2, dist1, dist2, idx1, idx2);
+  } else if ((long long)cdiv(nq, 256) * b * 2 >= 148) {
+    dim3 grid(cdiv(nq, 256), b, 2);
+    chamfer_kernel<2><<<grid, 128, 0, st>>>(n, m, xyz1, xyz2, dist1, dist2, idx1, idx2);
   } else {
     dim3 grid(cdiv(nq, 128), b, 2);
     chamfer_kernel<1><<<grid, 128, 0, st>>>(n, m, xyz1, xyz2, dist1, dist2, idx1, idx2);

@@ -10,7 +10,8 @@ from oracle import pointnet2_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,n,m", [(4, 2048, 2048), (2, 512, 700), (1, 8192, 2048), (3, 70, 600), (64, 1024, 1024), (1, 1, 5)])
+@pytest.mark.parametrize("B,n,m", [(4, 2048, 2048), (2, 512, 700), (1, 8192, 2048), (3, 70, 600), (64, 1024, 1024), (1, 1, 5),
+                                   (40, 2048, 1900)])  # 1 / 2 (packed) / 4 (packed) query points per thread
 def test_chamfer_forward_bit_exact(ref_ext, B, n, m):
     from difffacto_b200.metrics.chamfer import chamfer_forward
     rng = np.random.default_rng(n + m)
