@@ -399,6 +399,123 @@ static int launch_fps_fast(int b, int n, int m, int log2bs, int qbits, const flo
   return DFB200_OK;
 }
 
+// Wide variant for n >= 512 (reference block size bs = 512): THREADS = 512 >> S threads own PPT = 2^S * q points each, so
+// a round issues the same FP work from fewer warps (half / a quarter of the REDUX, barrier and slot traffic) and the
+// arg-max inside a thread is a TREE over the thread's points instead of a chain.
+// Tie order: point k = tid + i*THREADS has rank (bitrev9(k mod 512) << qbits) | (k / 512) with
+// bitrev9(k mod 512) = bitrev9(tid) | bitrev_S(i mod 2^S).  Register slot o = c * 2^qbits + w holds the point
+// i = w * 2^S + bitrev_S(c); then rank = (bitrev9(tid) << qbits) | o: ascending in the slot number, so "left operand wins
+// ties" at every tree level reproduces the reference's winner.
+__host__ __device__ constexpr int fps_brev_small(int c, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) r |= ((c >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+
+template <int PPT, int THREADS, int S>
+__global__ void __launch_bounds__(THREADS)
+fps_wide_kernel(int n, int m, int qbits, const float* __restrict__ dataset, float* __restrict__ temp,
+                int* __restrict__ idxs) {
+  extern __shared__ float fps_smem[];  // xs[n], ys[n], zs[n]
+  constexpr int NW = THREADS / 32;
+  constexpr int NP = PPT / 2;
+  constexpr int QP = PPT >> S;  // slots per residue class = 2^qbits (launch_fps_wide checks it)
+  static_assert(PPT >= 2 && (PPT & (PPT - 1)) == 0, "PPT must be a power of two >= 2");
+  __shared__ uint2 slot[2][NW];
+  float* xs = fps_smem;
+  float* ys = xs + n;
+  float* zs = ys + n;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* pts = dataset + (size_t)b * n * 3;
+  int* out = idxs + (size_t)b * m;
+
+  for (int i = tid; i < n * 3; i += THREADS) {
+    const float v = __ldg(pts + i);
+    const int k = i / 3, ch = i - k * 3;
+    (ch == 0 ? xs : ch == 1 ? ys : zs)[k] = v;
+  }
+  __syncthreads();
+
+  float2 px[NP], py[NP], pz[NP], td[NP];
+#pragma unroll
+  for (int o = 0; o < PPT; ++o) {
+    const int i = (o % QP) * (1 << S) + fps_brev_small(o / QP, S);
+    const int k = tid + i * THREADS;
+    const bool in = k < n;
+    const float x = in ? xs[k] : 0.f, y = in ? ys[k] : 0.f, z = in ? zs[k] : 0.f;
+    const float mag = sq3(x, y, z);
+    const bool ok = in && !((double)mag <= 1e-3);  // reference: fp32 mag, double compare
+    const float t0 = ok ? 1e10f : -1.f;
+    if (o & 1) { px[o >> 1].y = x; py[o >> 1].y = y; pz[o >> 1].y = z; td[o >> 1].y = t0; }
+    else       { px[o >> 1].x = x; py[o >> 1].x = y; pz[o >> 1].x = z; td[o >> 1].x = t0; }
+  }
+  const unsigned rbase = (__brev((unsigned)tid) >> 23) << qbits;  // bitrev9(tid); its low S bits are zero
+
+  int old = 0;
+  if (tid == 0 && m > 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float nx = -xs[old], ny = -ys[old], nz = -zs[old];
+    const float2 nx2 = make_float2(nx, nx), ny2 = make_float2(ny, ny), nz2 = make_float2(nz, nz);
+    float bv[NP];
+    int bo[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float2 d = sq3x2(__fadd2_rn(px[i], nx2), __fadd2_rn(py[i], ny2), __fadd2_rn(pz[i], nz2));
+      const float a = fminf(d.x, td[i].x), c = fminf(d.y, td[i].y);
+      td[i] = make_float2(a, c);
+      const bool take = c > a;  // strict: the lower slot keeps ties
+      bv[i] = take ? c : a;
+      bo[i] = 2 * i + (take ? 1 : 0);
+    }
+#pragma unroll
+    for (int w = 1; w < NP; w <<= 1) {
+#pragma unroll
+      for (int i = 0; i + w < NP; i += 2 * w) {
+        const bool take = bv[i + w] > bv[i];
+        bv[i] = take ? bv[i + w] : bv[i];
+        bo[i] = take ? bo[i + w] : bo[i];
+      }
+    }
+    const float best = bv[0];
+    const unsigned key = best < 0.f ? 0u : (__float_as_uint(best) + 1u);
+    const unsigned brank = best < 0.f ? 0xFFFFFFFFu : (rbase | (unsigned)bo[0]);
+    unsigned wkey = __reduce_max_sync(0xFFFFFFFFu, key);
+    unsigned wrank = __reduce_min_sync(0xFFFFFFFFu, key == wkey ? brank : 0xFFFFFFFFu);
+    if (NW > 1) {
+      if (lane == 0) slot[j & 1][warp] = make_uint2(wkey, wrank);
+      __syncthreads();
+      const uint2 sv = lane < NW ? slot[j & 1][lane] : make_uint2(0u, 0xFFFFFFFFu);
+      wkey = __reduce_max_sync(0xFFFFFFFFu, sv.x);
+      wrank = __reduce_min_sync(0xFFFFFFFFu, sv.x == wkey ? sv.y : 0xFFFFFFFFu);
+    }
+    old = (wkey == 0u) ? 0 : fps_unrank(wrank, 9, qbits);
+    if (tid == 0) out[j] = old;
+  }
+  if (temp != nullptr) {  // skipped points keep the caller's 1e10 initialisation
+    float* t = temp + (size_t)b * n;
+#pragma unroll
+    for (int o = 0; o < PPT; ++o) {
+      const int i = (o % QP) * (1 << S) + fps_brev_small(o / QP, S);
+      const int k = tid + i * THREADS;
+      const float v = (o & 1) ? td[o >> 1].y : td[o >> 1].x;
+      if (k < n) t[k] = v < 0.f ? 1e10f : v;
+    }
+  }
+}
+
+template <int PPT, int THREADS, int S>
+static int launch_fps_wide(int b, int n, int m, int qbits, const float* dataset, float* temp, int* idxs, cudaStream_t st) {
+  DFB_REQUIRE((PPT >> S) == (1 << qbits), DFB200_ERR_INVALID_ARG, "fps: internal slot/rank mismatch");
+  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  if (smem + 1024 > 48 * 1024) {
+    DFB_CUDA(cudaFuncSetAttribute(fps_wide_kernel<PPT, THREADS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  fps_wide_kernel<PPT, THREADS, S><<<b, THREADS, smem, st>>>(n, m, qbits, dataset, temp, idxs);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
 // reference cuda_utils.h:15-19 -- evaluated in double exactly as there (the quotient of logs can
 // land just below an integer, which changes the block size and therefore the tie rule).
 static int ref_opt_n_threads(int work_size) {
@@ -1088,6 +1205,22 @@ extern "C" int dfb200_furthest_point_sampling(int b, int n, int m, const float* 
   while ((1 << qbits) < q) ++qbits;
   // fast path: one thread block of exactly the reference's block size (see fps_fast_kernel)
 #define FPS_FAST(PPT, THREADS) return launch_fps_fast<PPT, THREADS>(b, n, m, log2bs, qbits, dataset, temp, idxs, st)
+  // threads per cloud = 512 >> S.  Measured 2048 -> 512 at batch 32 / 256: S=0 186 / 304 us, S=1 146 / 204 us, S=2 175 / 204 us
+  // (DFB200_FPS_S overrides for A/B measurements)
+  static const int fps_s = [] { const char* e = getenv("DFB200_FPS_S"); return e != nullptr ? atoi(e) : 1; }();
+#define FPS_WIDE(PPT, THREADS, S) return launch_fps_wide<PPT, THREADS, S>(b, n, m, qbits, dataset, temp, idxs, st)
+  if (bs == 512 && fps_s == 1 && q >= 1 && q <= 8) {
+    if (qbits == 0) FPS_WIDE(2, 256, 1);
+    if (qbits == 1) FPS_WIDE(4, 256, 1);
+    if (qbits == 2) FPS_WIDE(8, 256, 1);
+    if (qbits == 3) FPS_WIDE(16, 256, 1);
+  }
+  if (bs == 512 && fps_s == 2 && q >= 1 && q <= 4) {
+    if (qbits == 0) FPS_WIDE(4, 128, 2);
+    if (qbits == 1) FPS_WIDE(8, 128, 2);
+    if (qbits == 2) FPS_WIDE(16, 128, 2);
+  }
+#undef FPS_WIDE
   if (bs == 512) {
     if (q <= 1) FPS_FAST(1, 512);
     if (q <= 2) FPS_FAST(2, 512);
