@@ -616,6 +616,75 @@ ball_query_kernel(int n, int m, float radius2, int nsample, int centres_per_warp
   }
 }
 
+// Shared-memory variant of the ordered scan on the packed fp32x2 pipe: the cloud is staged NEGATED (c - p == c + (-p)
+// exactly) as three arrays padded to a multiple of 4 points, a lane owns 4 CONSECUTIVE candidates per 128-candidate step
+// (three LDS.128 instead of twelve LDS, 12 packed FP instructions instead of 24) and the compaction counts the hits of
+// the lower lanes over the four ballots -- index order is lane-major, so the output is unchanged.
+__global__ void __launch_bounds__(256)
+ball_query_scan4_kernel(int n, int m, float radius2, int nsample, int centres_per_warp, int only_marked,
+                        const float* __restrict__ new_xyz, const float* __restrict__ xyz, int* __restrict__ idx) {
+  extern __shared__ __align__(16) float bq4_smem[];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (only_marked && idx[((size_t)b * m + (size_t)blockIdx.x * 8 * centres_per_warp) * nsample] != -1) return;
+  const int npad = (n + 3) & ~3;
+  const float* pts = xyz + (size_t)b * n * 3;
+  float* xs = bq4_smem;
+  float* ys = xs + npad;
+  float* zs = ys + npad;
+  for (int i = threadIdx.x; i < npad * 3; i += blockDim.x) {
+    const int k = i / 3, ch = i - k * 3;
+    (ch == 0 ? xs : ch == 1 ? ys : zs)[k] = k < n ? -__ldg(pts + i) : 0.f;
+  }
+  __syncthreads();
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+  const float4* ys4 = reinterpret_cast<const float4*>(ys);
+  const float4* zs4 = reinterpret_cast<const float4*>(zs);
+  const unsigned lt = lanemask_lt();
+  const int j0 = (blockIdx.x * 8 + warp) * centres_per_warp;
+  for (int jj = 0; jj < centres_per_warp; ++jj) {
+    const int j = j0 + jj;
+    if (j >= m) break;
+    const float* cq = new_xyz + ((size_t)b * m + j) * 3;
+    const float cx = __ldg(cq), cy = __ldg(cq + 1), cz = __ldg(cq + 2);
+    const float2 cx2 = make_float2(cx, cx), cy2 = make_float2(cy, cy), cz2 = make_float2(cz, cz);
+    int* o = idx + ((size_t)b * m + j) * nsample;
+    int cnt = 0, first = 0;
+    for (int k0 = 0; k0 < n && cnt < nsample; k0 += 128) {
+      const int k = k0 + 4 * lane;
+      bool h0 = false, h1 = false, h2 = false, h3 = false;
+      if (k < n) {
+        const float4 X = xs4[k >> 2], Y = ys4[k >> 2], Z = zs4[k >> 2];
+        const float2 da = sq3x2(__fadd2_rn(cx2, make_float2(X.x, X.y)), __fadd2_rn(cy2, make_float2(Y.x, Y.y)),
+                                __fadd2_rn(cz2, make_float2(Z.x, Z.y)));
+        const float2 db = sq3x2(__fadd2_rn(cx2, make_float2(X.z, X.w)), __fadd2_rn(cy2, make_float2(Y.z, Y.w)),
+                                __fadd2_rn(cz2, make_float2(Z.z, Z.w)));
+        h0 = da.x < radius2;  // reference: `if (d2 < radius2)`
+        h1 = (k + 1 < n) && da.y < radius2;
+        h2 = (k + 2 < n) && db.x < radius2;
+        h3 = (k + 3 < n) && db.y < radius2;
+      }
+      const unsigned m0 = __ballot_sync(0xFFFFFFFFu, h0), m1 = __ballot_sync(0xFFFFFFFFu, h1),
+                     m2 = __ballot_sync(0xFFFFFFFFu, h2), m3 = __ballot_sync(0xFFFFFFFFu, h3);
+      const unsigned any = m0 | m1 | m2 | m3;
+      if (any != 0u) {
+        if (cnt == 0) {
+          const int fl = __ffs(any) - 1;  // lowest lane with a hit; its lowest hit is the first hit
+          const unsigned hb = ((m0 >> fl) & 1u) | (((m1 >> fl) & 1u) << 1) | (((m2 >> fl) & 1u) << 2) | (((m3 >> fl) & 1u) << 3);
+          first = k0 + 4 * fl + __ffs(hb) - 1;
+        }
+        int pos = cnt + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+        if (h0) { if (pos < nsample) o[pos] = k; ++pos; }
+        if (h1) { if (pos < nsample) o[pos] = k + 1; ++pos; }
+        if (h2) { if (pos < nsample) o[pos] = k + 2; ++pos; }
+        if (h3) { if (pos < nsample) o[pos] = k + 3; ++pos; }
+        cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+      }
+    }
+    for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) o[l] = first;
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // Grid path (1024 <= n <= 8192): sparse balls (r = 0.1 / 0.2 on a unit-scale cloud hold 6 / 43 of
 // 2048 points on average, so 77-92 % of the centres scan ALL n points in the brute-force kernel).
@@ -1284,10 +1353,10 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
     ball_query_grid_kernel<<<ctas, BQG_T, gsm, st>>>(b, n, m, mpad, (int)bqg_keys_offset(n), min_occ, radius, radius2, nsample,
                                                     8 * scpw, new_xyz, xyz, idx);
     DFB_LAUNCH_CHECK();
-    const size_t ssm = sizeof(float) * 3 * (size_t)n;
+    const size_t ssm = sizeof(float) * 3 * (size_t)((n + 3) & ~3);
     if (ssm > 48 * 1024)
-      DFB_CUDA(cudaFuncSetAttribute(ball_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-    ball_query_kernel<true><<<dim3(cdiv(m, 8 * scpw), b), 256, ssm, st>>>(n, m, radius2, nsample, scpw, 1, new_xyz, xyz, idx);
+      DFB_CUDA(cudaFuncSetAttribute(ball_query_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+    ball_query_scan4_kernel<<<dim3(cdiv(m, 8 * scpw), b), 256, ssm, st>>>(n, m, radius2, nsample, scpw, 1, new_xyz, xyz, idx);
     DFB_LAUNCH_CHECK();
     return DFB200_OK;
   }
@@ -1295,8 +1364,13 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
   int cpw = 8;
   while (cpw > 1 && (long long)b * cdiv(m, 8 * cpw) < 148 * 4) cpw /= 2;
   dim3 grid(cdiv(m, 8 * cpw), b);
-  const size_t smem = sizeof(float) * 3 * (size_t)n;
-  if (smem <= 160 * 1024) {
+  const size_t smem = sizeof(float) * 3 * (size_t)((n + 3) & ~3);
+  static const bool scan1 = [] { const char* e = getenv("DFB200_BALL_QUERY"); return e != nullptr && e[0] == 's' && e[1] == '1'; }();  // A/B
+  if (smem <= 160 * 1024 && !scan1) {
+    if (smem > 48 * 1024)
+      DFB_CUDA(cudaFuncSetAttribute(ball_query_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ball_query_scan4_kernel<<<grid, 256, smem, st>>>(n, m, radius2, nsample, cpw, 0, new_xyz, xyz, idx);
+  } else if (smem <= 160 * 1024) {
     if (smem > 48 * 1024)
       DFB_CUDA(cudaFuncSetAttribute(ball_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ball_query_kernel<true><<<grid, 256, smem, st>>>(n, m, radius2, nsample, cpw, 0, new_xyz, xyz, idx);
