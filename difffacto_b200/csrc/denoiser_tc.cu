@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(256)
 context_fold_kernel(int depth, const float* __restrict__ kv, const float* __restrict__ kv_time, int t_first,
                     const float* __restrict__ extras, uint8_t* __restrict__ fold_all) {
   __shared__ float K[MAX_TOKENS][D_MODEL], V[MAX_TOKENS][D_MODEL];
+  // the packet is assembled in shared memory and leaves as coalesced 16-byte stores: the tile layout scatters a thread's
+  // bf16 values 16..512 bytes apart, and 66 2-byte global stores per thread made this kernel store-issue bound
+  __shared__ __align__(16) uint8_t img[FOLD_BYTES];
   const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
   const float* src = kv + ((size_t)b * depth + l) * 1024;
   uint8_t* fold = fold_all + (size_t)blockIdx.z * gridDim.x * depth * FOLD_BYTES;
@@ -271,7 +274,8 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
   const float* WqG = extras + HEAD_FLOATS + (size_t)l * FOLDW_FLOATS;
   const float* bqG = WqG + D_MODEL * D_MODEL;
   const float* WoT = bqG + D_MODEL;
-  uint8_t* out = fold + ((size_t)b * depth + l) * FOLD_BYTES;
+  uint8_t* gout = fold + ((size_t)b * depth + l) * FOLD_BYTES;
+  uint8_t* out = img;
   const int col = t & 127, half = t >> 7;
   // W_sim: thread = column k, rows r = (h,j) with h in this half's 4 heads
   for (int hh = 0; hh < 4; ++hh) {
@@ -312,6 +316,10 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
 #pragma unroll
     for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
   }
+  __syncthreads();
+  static_assert(FOLD_BYTES % 16 == 0, "fold packet must be a whole number of 16-byte chunks");
+  for (int i = t; i < FOLD_BYTES / 16; i += 256)
+    reinterpret_cast<uint4*>(gout)[i] = reinterpret_cast<const uint4*>(img)[i];
 }
 
 // ---------------------------------------------------------------------------------------------
