@@ -220,6 +220,8 @@ class TransformerNet(nn.Module):
         B, C, N = x.shape
         f32 = torch.float32
         dev = x.device
+        if torch.is_grad_enabled():  # one zero fill for all atomically accumulated gradients of this step's backward pass
+            T.begin_zero_arena(dev, sum(p.numel() for p in self.parameters()) + 2 * self.depth * B * self.n_class * 128 + 64 * 160)
         # context (B,4,522) = [part code | mean, var | one-hot class | t_embed]  (:389-398)
         ctx = ctx.to(f32).transpose(1, 2)
         class_embed = torch.eye(self.n_class, device=dev, dtype=f32).unsqueeze(0).expand(B, -1, -1)

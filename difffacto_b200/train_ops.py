@@ -18,6 +18,32 @@ def _c(t):
     return t.contiguous() if not t.is_contiguous() else t
 
 
+class _ZeroArena:
+    """Zero-initialised scratch for the backward pass.  Every weight / bias / LayerNorm / K-V gradient is accumulated with
+    atomics (split-K wgrad, column sums) and used to cost one torch.zeros (allocation + fill launch) each: ~80 launches of a
+    launch-bound step.  begin() zero-fills ONE flat buffer per training forward; zeros() hands out disjoint, never reused
+    slices of it (bump pointer), and falls back to torch.zeros when the buffer is absent, on another device or exhausted."""
+    buf = None
+    off = 0
+
+
+def begin_zero_arena(device, numel):
+    _ZeroArena.buf = torch.zeros(int(numel), device=device, dtype=torch.float32)
+    _ZeroArena.off = 0
+
+
+def zeros(shape, device):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    a = _ZeroArena
+    if a.buf is not None and a.buf.device == device and a.off + n <= a.buf.numel():
+        out = a.buf[a.off:a.off + n].view(shape)
+        a.off += (n + 63) // 64 * 64  # keep every slice 256-byte aligned
+        return out
+    return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
 def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split_k=1, bf16=False):
     """fp32 CUDA-core GEMM, or - bf16=True and the problem is big enough for 128x128x64 tensor-core tiles - the tcgen05 GEMM
     with bf16-rounded operands and fp32 accumulation (same layout contract)."""
@@ -87,14 +113,14 @@ class LinearFn(Function):
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
             _sgemm(True, False, M, K, N, dy, N, weight, K, dx, K, bf16=ctx.bf16)  # dx(i,k) = sum_n dy(i,n) W(n,k)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros(N, K, device=x.device, dtype=torch.float32)
+            dw = zeros((N, K), x.device)
             tc = ctx.bf16 and N >= 128 and K >= 64 and M >= 64
             t = 128 if tc else 64
             tiles = ((N + t - 1) // t) * ((K + t - 1) // t)
             split = max(1, min((M + 255) // 256, (148 * (2 if tc else 4) + tiles - 1) // tiles))
             _sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=split, bf16=ctx.bf16)  # dW(n,k) = sum_m dy(m,n) x(m,k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(N, device=x.device, dtype=torch.float32)
+            db = zeros((N,), x.device)
             with _lib.on(x.device):
                 check(_lib.load().dfb200_colsum_accumulate(M, N, ptr(dy), N, ptr(db), stream()))
         return dx, dw, db, (dy if ctx.has_res and ctx.needs_input_grad[3] else None)
@@ -123,8 +149,8 @@ class LayerNorm128Fn(Function):
         x, gamma, mean, rstd = ctx.saved_tensors
         dy = _c(dy)
         dx = torch.empty_like(x)
-        dg = torch.zeros(128, device=x.device, dtype=torch.float32)
-        db = torch.zeros(128, device=x.device, dtype=torch.float32)
+        dg = zeros((128,), x.device)
+        db = zeros((128,), x.device)
         with _lib.on(x.device):
             check(_lib.load().dfb200_layernorm128_backward(x.shape[0], ptr(x), ptr(_c(gamma)), ptr(mean), ptr(rstd), ptr(dy), ptr(dx),
                                                            ptr(dg), ptr(db), stream()))
@@ -177,8 +203,8 @@ class PartAttentionFn(Function):
     def backward(ctx, d_o):
         q, k, v, probs = ctx.saved_tensors
         dq = torch.empty_like(q)
-        dk = torch.zeros_like(k)
-        dv = torch.zeros_like(v)
+        dk = zeros(tuple(k.shape), k.device)
+        dv = zeros(tuple(v.shape), v.device)
         with _lib.on(q.device):
             check(_lib.load().dfb200_part_attention_backward(ctx.B, ctx.N, ptr(q), ptr(k), ptr(v), ptr(ctx.valid), ptr(probs), ptr(_c(d_o)),
                                                              ptr(dq), ptr(dk), ptr(dv), stream()))
