@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int layout, int N, in
 }
 
 // CTA-pair variant of the rate microbenchmark: cta_group::2 MMAs (M = 256, N) issued by rank 0; mode bit0: A from tensor
-// memory (TS form), bit1: every MMA accumulates into the same TMEM tile.  The B half tile has N/2 rows per CTA.
+// memory (TS form), bit1: every MMA accumulates into the same TMEM tile, bit2: SWIZZLE_128B operand descriptors instead of
+// the no-swizzle layout.  The B half tile has N/2 rows per CTA.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma2_rate_kernel(int mode, int N, int iters, int ksteps, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);
@@ -314,8 +315,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma2_rate_k
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         const int kk = ks % ksteps;
-        ad[ks] = make_smem_desc(sbase + kk * 4096, 2048, TILE_SBO);
-        bd[ks] = make_smem_desc(sbase + 65536 + kk * (NH * 32), NH * 16, TILE_SBO);
+        if (mode & 4) {  // SWIZZLE_128B K-major operands (rows of 128 B, 8-row atoms of 1024 B, K=16 step = +32 B)
+          ad[ks] = make_smem_desc(sbase + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024) | ((uint64_t)2 << 61);
+          bd[ks] = make_smem_desc(sbase + 65536 + (kk >> 2) * (NH * 128) + (kk & 3) * 32, 16, 1024) | ((uint64_t)2 << 61);
+        } else {
+          ad[ks] = make_smem_desc(sbase + kk * 4096, 2048, TILE_SBO);
+          bd[ks] = make_smem_desc(sbase + 65536 + kk * (NH * 32), NH * 16, TILE_SBO);
+        }
       }
       t0 = clock64();
       for (int i = 0; i < iters; i += 8) {
