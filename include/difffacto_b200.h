@@ -61,6 +61,10 @@ int dfb200_furthest_point_sampling(int b, int n, int m, const float* dataset, fl
                                    int* idxs, dfb200_stream_t stream);
 /* idx[b,j,:] = first `nsample` indices k (ascending) with |new_xyz[b,j]-xyz[b,k]|^2 < radius^2,
  * padded with the first hit; all zeros if the ball is empty.  new_xyz (b,m,3), xyz (b,n,3).
+ * Every element of idx is written (no zero-initialisation by the caller is needed, unlike the
+ * reference).  For 1024 <= n <= 8192 two kernels are enqueued on `stream` (uniform-grid pass, then
+ * an ordered scan of the clouds the first pass handed over); idx is used to pass a -1 marker between
+ * them, so it must not be read concurrently on another stream before the call's work has finished.
  * Replaces query_ball_point_kernel_wrapper, ball_query.cpp:4-6 / ball_query_gpu.cu:46-54. */
 int dfb200_query_ball_point(int b, int n, int m, float radius, int nsample, const float* new_xyz,
                             const float* xyz, int* idx, dfb200_stream_t stream);
