@@ -1324,7 +1324,7 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
   DFB_REQUIRE(b <= 65535, DFB200_ERR_INVALID_ARG, "query_ball_point: b > 65535");
   cudaStream_t st = as_stream(stream);
   const float radius2 = radius * radius;  // one fp32 multiply, as in the reference
-  // sparse-ball path: uniform grid + one thread per centre (see ball_query_grid_kernel);
+  // sparse-ball path: uniform grid + 8 lanes per centre (see ball_query_grid_kernel), then the ordered scan for handed-over clouds;
   // DFB200_BALL_QUERY=scan forces the ordered brute-force scan (A/B measurements)
   static const bool force_scan = [] { const char* e = getenv("DFB200_BALL_QUERY"); return e != nullptr && e[0] == 's'; }();
   if (!force_scan && n >= 1024 && n <= 8192 && m >= 32) {
