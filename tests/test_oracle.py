@@ -189,3 +189,32 @@ def test_ddim_loop_port_matches_reference(variants_golden):
         x, _, _ = R.p_sample(sd, s, x, t, [inp["code"], inp["params"]], inp["anchors"], inp["variance"], inp["assign"], inp["valid"],
                              noises[k + 1], ddim_eta=1.0)
     assert np.abs(x.numpy() - g["ddim_loop_x0"]).max() < 5e-5
+
+
+def test_ball_query_grid_binning_covers_every_hit():
+    """Host-side model of the binning used by the CUDA grid path of ball_query (csrc/pointnet2.cu, ball_query_grid_kernel):
+    cell size max(1.001 r, extent / 15.99) per axis, at most 16 cells per axis, points clamped into the grid, centres clamped
+    to [-1, g].  Every point the oracle reports inside a ball must lie in the 3x3x3 cell neighbourhood of its centre --
+    including centres outside or on the faces of the cloud's bounding box and radii far below / above the cell limit."""
+    f = np.float32
+    rng = np.random.default_rng(3)
+    for r in (0.013, 0.05, 0.1, 0.2, 0.4, 0.8, 3.0):
+        xyz = (0.3 * rng.standard_normal((4, 3)).astype(f)[rng.integers(0, 4, 1500)]
+               + np.sqrt(np.exp(rng.uniform(np.log(0.01), np.log(0.1), (1, 3)))).astype(f) * rng.standard_normal((1500, 3)).astype(f))
+        centres = np.concatenate([xyz[:200], xyz[:100] + f(0.7) * f(r) * rng.standard_normal((100, 3)).astype(f),
+                                  f(3) * rng.standard_normal((50, 3)).astype(f), xyz.min(0)[None], xyz.max(0)[None],
+                                  xyz.max(0)[None] + f(0.999) * f(r)]).astype(f)
+        lo, hi = xyz.min(0), xyz.max(0)
+        cs = np.maximum(f(r) * f(1.001), (hi - lo) * f(1.0 / 15.99)).astype(f)
+        iv = (f(1.0) / cs).astype(f)
+        g = np.minimum(((hi - lo) * iv).astype(np.int32) + 1, 16)
+        pc = np.clip(np.floor((xyz - lo) * iv).astype(np.int64), 0, g - 1)
+        cc = np.clip(np.floor(((centres - lo) * iv).astype(f)), -1, g).astype(np.int64)
+        idx = O.ball_query(centres[None], xyz[None], float(r), 1500)[0]          # every hit of every ball, ascending
+        d = centres[:, None, :] - xyz[None, :, :]
+        hit = (d[..., 2] * d[..., 2] + (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])).astype(f) < f(r) * f(r)
+        near = (np.abs(pc[None, :, :] - cc[:, None, :]) <= 1).all(-1)
+        assert not (hit & ~near).any(), r
+        for j in range(0, len(centres), 37):  # the float32 model of `hit` is the oracle's
+            want = np.flatnonzero(hit[j])
+            assert np.array_equal(np.unique(idx[j]), want if len(want) else np.array([0]))
