@@ -182,7 +182,7 @@ def test_three_nn_bit_exact(pu, ref_ext, B, n, m):
         assert torch.equal(idx, ridx) and torch.equal(dist, torch.sqrt(rd2))
 
 
-@pytest.mark.parametrize("B,c,m,n", [(2, 256, 512, 2048), (2, 5, 30, 77)])
+@pytest.mark.parametrize("B,c,m,n", [(2, 256, 512, 2048), (2, 5, 30, 77), (3, 10, 64, 1000), (2, 7, 100, 1022), (40, 6, 128, 2052)])
 def test_three_interpolate_bit_exact(pu, ref_ext, B, c, m, n):
     rng = np.random.default_rng(c)
     feats = rng.standard_normal((B, c, m)).astype(np.float32)
