@@ -218,3 +218,39 @@ def test_ball_query_grid_binning_covers_every_hit():
         for j in range(0, len(centres), 37):  # the float32 model of `hit` is the oracle's
             want = np.flatnonzero(hit[j])
             assert np.array_equal(np.unique(idx[j]), want if len(want) else np.array([0]))
+
+
+def test_fps_wide_kernel_slot_order_reproduces_the_tree_tie_rule():
+    """Host-side model of fps_wide_kernel (csrc/pointnet2.cu): 512 >> S threads per cloud, register slot o = c * 2^qbits + w
+    of thread tid holds point k = tid + (w * 2^S + bitrev_S(c)) * THREADS, and the arg-max of a round is the maximum distance
+    with ties broken by the smallest rank (bitrev9(tid) << qbits) | o.  On an integer lattice (massive ties) this must pick
+    exactly the points of the oracle's literal simulation of the reference's shared-memory tree, for S = 0, 1, 2."""
+    rng = np.random.default_rng(9)
+    n, m = 2048, 40
+    xyz = rng.integers(1, 4, (1, n, 3)).astype(np.float32)
+    want = O.furthest_point_sampling(xyz, m)[0]
+    q = (n + 511) // 512
+    qbits = int(np.ceil(np.log2(q))) if q > 1 else 0
+    brev = lambda v, bits: int(format(v, f"0{bits}b")[::-1], 2) if bits else 0
+    p = xyz[0].astype(np.float32)
+    for S in (0, 1, 2):
+        threads, ppt = 512 >> S, (1 << qbits) << S
+        rank = np.zeros(n, np.int64)
+        for tid in range(threads):
+            for o in range(ppt):
+                c, w = o >> qbits, o & ((1 << qbits) - 1)
+                k = tid + (w * (1 << S) + brev(c, S)) * threads
+                if k < n:
+                    rank[k] = (brev(tid, 9) << qbits) | o
+        assert len(set(rank.tolist())) == n  # a total order
+        td = np.full(n, 1e10, np.float32)
+        got, old = [0], 0
+        for _ in range(1, m):
+            d = p - p[old]
+            d2 = (d[:, 2] * d[:, 2] + (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])).astype(np.float32)
+            td = np.minimum(td, d2)
+            best = td.max()
+            cand = np.flatnonzero(td == best)
+            old = int(cand[np.argmin(rank[cand])])
+            got.append(old)
+        assert got == want.tolist(), S
