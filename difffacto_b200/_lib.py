@@ -122,11 +122,17 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_GET_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
     """Current CUDA stream of the current device as a raw handle.  torch.cuda.current_stream() builds a Stream object
     through several Python layers (about 10 % of the host time of a training step, which is launch-bound); the C binding
     returns the same handle directly."""
-    return c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    if _RAW_STREAM is not None and _GET_DEVICE is not None:
+        return c_void_p(_RAW_STREAM(_GET_DEVICE()))
+    return c_void_p(torch.cuda.current_stream().cuda_stream)  # public API, if a torch build lacks the bindings
 
 
 class on:
@@ -136,7 +142,11 @@ class on:
 
     def __init__(self, device):
         idx = device.index if isinstance(device, torch.device) else int(device)
-        self.guard = None if idx is None or idx == torch._C._cuda_getDevice() else torch.cuda.device(idx)
+        if idx is None:  # not a CUDA device: nothing to guard (callers reject CPU tensors before launching)
+            self.guard = None
+        else:
+            cur = _GET_DEVICE() if _GET_DEVICE is not None else torch.cuda.current_device()
+            self.guard = None if idx == cur else torch.cuda.device(idx)
 
     def __enter__(self):
         if self.guard is not None:
