@@ -189,7 +189,7 @@ def run_ours(args):
         d = res if resident else {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         x0 = diff.p_sample_loop([B, 3, N], d["anchors"], ctx=[d["code"], d["params"]], variance=d["variance"],
                                 anchor_assignment=d["assign"], valid_id=d["valid"], rng="philox",
-                                seed=rank_seed(1000 * step, rank))
+                                seed=rank_seed(1000 + step, rank, world))
         pts = x0.transpose(1, 2).contiguous()
         return gather_shapes(pts, B * world) if world > 1 else pts
 

@@ -9,6 +9,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libdifffacto_b200.so")
+DIAG_LIB_PATH = os.path.join(_PKG, "lib", "libdifffacto_b200_diag.so")  # -DDFB200_DIAGNOSTICS build (tests / tools only)
 
 c_int, c_float, c_void_p, c_size_t, c_u64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64
 
@@ -79,32 +80,51 @@ SIGNATURES = {
     "dfb200_ddim_step": (c_int, [c_int] * 3 + [P] * 9 + [c_float, P, P, P]),
     "dfb200_guidance_mix": (c_int, [c_size_t, c_float, P, P, P, P]),
     "dfb200_philox_normal": (c_int, [P, c_size_t, c_u64, c_u64, P]),
-    "dfb200_bench_umma": (c_int, [c_int, c_int, c_int, c_int, P, P]),
-    "dfb200_bench_umma2": (c_int, [c_int, c_int, c_int, c_int, P, P]),
-    "dfb200_debug_tc_timeline": (c_int, [P, c_int]),
-    "dfb200_selftest_umma": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
-    "dfb200_selftest_umma2": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "dfb200_ddpm_sample_loop_workspace_bytes": (c_size_t, [_CFG, c_int, c_int, c_int, c_int]),
     "dfb200_ddpm_sample_loop": (c_int, [_CFG, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_u64, P,
                                          c_int, P, c_size_t, P]),
 }
 
+# include/difffacto_b200_diag.h: exported only by the diagnostic build
+DIAG_SIGNATURES = {
+    "dfb200_bench_umma": (c_int, [c_int, c_int, c_int, c_int, P, P]),
+    "dfb200_bench_umma2": (c_int, [c_int, c_int, c_int, c_int, P, P]),
+    "dfb200_debug_tc_timeline": (c_int, [P, c_int]),
+    "dfb200_selftest_umma": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "dfb200_selftest_umma2": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
+}
+
 _lib = None
+_diag = None
+
+
+def _open(path, signatures, how):
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `{how}` "
+                          "(difffacto_b200 has no CPU or eager-PyTorch fallback)")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in signatures.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
 
 
 def load():
-    """dlopen the in-tree library and type every entry point (no CUDA call is made here)."""
+    """dlopen the in-tree library and type every entry point (no CUDA call is made here).
+    DFB200_DIAGNOSTICS=1 in the environment makes the whole package run on the diagnostic build (tools/diag_*.py)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m difffacto_b200.build` "
-                              "(difffacto_b200 has no CPU or eager-PyTorch fallback)")
-        lib = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = res, args
-        _lib = lib
+        _lib = load_diag() if os.environ.get("DFB200_DIAGNOSTICS") == "1" else \
+            _open(LIB_PATH, SIGNATURES, "python -m difffacto_b200.build")
     return _lib
+
+
+def load_diag():
+    """The diagnostic build (all product entry points + include/difffacto_b200_diag.h); tests and tools only."""
+    global _diag
+    if _diag is None:
+        _diag = _open(DIAG_LIB_PATH, {**SIGNATURES, **DIAG_SIGNATURES}, "python -m difffacto_b200.build --diag")
+    return _diag
 
 
 class DFB200Error(RuntimeError):
@@ -141,8 +161,10 @@ class on:
     __slots__ = ("guard",)
 
     def __init__(self, device):
+        if isinstance(device, str):  # 'cuda' / 'cuda:1', as AnchorDiffAE.decode passes by default
+            device = torch.device(device)
         idx = device.index if isinstance(device, torch.device) else int(device)
-        if idx is None:  # not a CUDA device: nothing to guard (callers reject CPU tensors before launching)
+        if idx is None:  # 'cuda' without an index = the current device; CPU: nothing to guard (callers reject CPU tensors)
             self.guard = None
         else:
             cur = _GET_DEVICE() if _GET_DEVICE is not None else torch.cuda.current_device()

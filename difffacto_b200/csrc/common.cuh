@@ -50,6 +50,23 @@ void count_launch(unsigned n = 1);
     }                                                                                    \
   } while (0)
 
+// Per-device facts (a process may drive several GPUs through `_lib.on(device)`): nothing device-specific is cached in a
+// process-wide static.  current_device_sm_count() returns the SM count of the CURRENT device (0 on error);
+// DeviceOnce remembers, per device ordinal, whether a one-time setup (cudaFuncSetAttribute is per device) has run.
+int current_device_sm_count();
+int current_device_ordinal();  // -1 on error
+struct DeviceOnce {
+  bool done[64] = {};
+  // true the first time it is asked for the current device (ordinals >= 64 are never remembered: the setup just repeats)
+  bool first_time() {
+    const int d = current_device_ordinal();
+    if (d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 static inline cudaStream_t as_stream(dfb200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -16,6 +16,22 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int current_device_ordinal() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+int current_device_sm_count() {
+  static int cache[64] = {};
+  const int dev = current_device_ordinal();
+  if (dev < 0) return 0;
+  if (dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev < 64) cache[dev] = n;
+  return n;
+}
+
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace dfb200

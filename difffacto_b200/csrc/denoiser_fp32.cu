@@ -374,13 +374,12 @@ int denoiser_forward_fp32(const PackLayout& L, const float* P, int B, int N, con
                           const float* anchors, const float* variances, const int* assign,
                           const float* valid_id, float* eps_out, Workspace& ws, cudaStream_t st) {
   const long long M = (long long)B * N;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;  // cudaFuncSetAttribute is per device
+  if (attr_once.first_time()) {
     DFB_CUDA(cudaFuncSetAttribute(ln_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     DFB_CUDA(cudaFuncSetAttribute(ln_geglu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     DFB_CUDA(cudaFuncSetAttribute(gemm_residual_kernel<D_MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     DFB_CUDA(cudaFuncSetAttribute(gemm_residual_kernel<D_FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    attr_set = true;
   }
   const int mt = cdiv(M, GT);
   embed_kernel<<<cdiv(M, EMB_TOK), 256, 0, st>>>(N, M, L.d.flags, x, anchors, variances, assign, P + L.g[P_IN_W],

@@ -381,11 +381,16 @@ __device__ __forceinline__ float2 geglu2(float2 a_half, float2 g) {
   return __ffma2_rn(ag, t, ag);
 }
 
-// timeline instrumentation (off unless a buffer is supplied): slot layout [who][event], who 0 = tile-0 row 0, 1 = MMA lane
+// timeline instrumentation (diagnostic build only, and off unless a buffer is supplied): slot layout [who][event],
+// who 0 = tile-0 row 0, 1 = MMA lane
+#ifdef DFB200_DIAGNOSTICS
 #define TL(who, ev)                                                                                  \
   do {                                                                                               \
     if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) P.dbg[(who) * 512 + (ev)] = clock64(); \
   } while (0)
+#else
+#define TL(who, ev) do { (void)tl_on; } while (0)
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -502,12 +507,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     for (int j = 0; j < MAX_TOKENS; ++j)
       if (P.valid == nullptr || __ldg(P.valid + b * MAX_TOKENS + j) != 0.f) vmask |= 1u << j;
     TL(0, 0);
+#ifdef DFB200_DIAGNOSTICS
     const long long dbg_t0 = (P.dbg != nullptr && tl_on) ? clock64() : 0;
     if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       P.dbg[220] = (long long)ns;
     }
+#endif
     if (P.done != nullptr) {
       // x of this unit at this timestep is produced by the item (unit, previous step), possibly on another SM
       if (r == 0) {
@@ -520,7 +527,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       named_bar_sync(1 + T, 128);
     }
     TL(0, 210);
+#ifdef DFB200_DIAGNOSTICS
     if (P.dbg != nullptr && tl_on && blockIdx.x < 148) P.dbg[742 + blockIdx.x] += clock64() - dbg_t0;  // per-CTA dependency-wait cycles
+#endif
 
     // ---- proj_in (13 -> 128) + pre_norm on the tensor core: analytic variance -> scaled K=32 A row -> one MMA into X ----
     {
@@ -750,12 +759,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(P.done + unit), "r"(1) : "memory");
     }
     TL(0, 3 + P.depth * 40);
+#ifdef DFB200_DIAGNOSTICS
     if (P.dbg != nullptr && tl_on && blockIdx.x < 148) P.dbg[230 + blockIdx.x] += clock64() - dbg_t0;  // per-CTA item cycles
     if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       P.dbg[221] = (long long)ns;
     }
+#endif
     }  // items
     tc_fence_before();
   } else if (warp == 8) {
@@ -937,8 +948,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
   }
 }
 
+#ifdef DFB200_DIAGNOSTICS
 static long long* g_tc_timeline = nullptr;  // set by dfb200_debug_tc_timeline
 static int g_tc_timeline_item = 0;
+#endif
 
 static const float* tc_extras(const PackLayout& L, const void* packed) {
   const uint8_t* S = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
@@ -958,11 +971,9 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
                      const float* variances, const int* assign, const float* valid_id, const void* fold, float* eps_out,
                      const TcUpdate* upd, cudaStream_t st) {
   DFB_REQUIRE(N % 128 == 0, DFB200_ERR_UNSUPPORTED, "denoiser (bf16 mode): N must be a multiple of 128 (got %d); use fp32 mode", N);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;  // cudaFuncSetAttribute is per device
+  if (attr_once.first_time())
     DFB_CUDA(cudaFuncSetAttribute(denoiser_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    attr_set = true;
-  }
   TcParams p{};
   p.stream = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
   p.fold = reinterpret_cast<const uint8_t*>(fold);
@@ -971,8 +982,10 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   p.eps_out = eps_out;
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
   p.M = (long long)B * N;
+#ifdef DFB200_DIAGNOSTICS
   p.dbg = g_tc_timeline;
   p.dbg_item = g_tc_timeline_item;
+#endif
   p.n_units = cdiv(p.M, 256);
   p.n_steps = 1;
   p.t_first = 0;
@@ -981,12 +994,9 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
     p.n_steps = upd->n_steps; p.fold_step_bytes = upd->fold_step_bytes; p.noise_step_elems = (size_t)p.M * 3;
     p.done = upd->done; p.traj = upd->traj; p.traj_interval = upd->traj_interval;
   }
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    DFB_CUDA(cudaGetDevice(&dev));
-    DFB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  // the spin-wait on P.done assumes every CTA of the grid is resident: size it by the LAUNCHING device's SM count
+  const int n_sm = current_device_sm_count();
+  DFB_REQUIRE(n_sm > 0, DFB200_ERR_CUDA, "denoiser (bf16 mode): cannot query the SM count of the current device");
   // persistent: one CTA per SM walks the (step, unit) work list; dependencies between steps of a unit go through P.done
   const long long items = (long long)p.n_units * p.n_steps;
   const int grid = (int)(items < n_sm ? items : n_sm);
@@ -1008,9 +1018,12 @@ int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, c
 
 using namespace dfb200;
 
-// Debug hook: device buffer of 1024 int64 that CTA 0 of the fused kernel fills with clock64() stamps (NULL = off).
+#ifdef DFB200_DIAGNOSTICS
+// Debug hook (diagnostic build only): device buffer of 1024 int64 that CTA 0 of the fused kernel fills with clock64()
+// stamps (NULL = off).  Declared in include/difffacto_b200_diag.h.
 extern "C" int dfb200_debug_tc_timeline(long long* device_buffer, int item) {
   g_tc_timeline = device_buffer;
   g_tc_timeline_item = item;
   return DFB200_OK;
 }
+#endif

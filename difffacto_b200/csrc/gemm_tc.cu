@@ -159,8 +159,8 @@ extern "C" int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, i
   cudaStream_t st = as_stream(stream);
 #define GT_LAUNCH(AK, BK)                                                                                                      \
   do {                                                                                                                         \
-    static bool set = false;                                                                                                   \
-    if (!set) { DFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; } \
+    static DeviceOnce once; /* cudaFuncSetAttribute is per device */                                                          \
+    if (once.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     gemm_tc_kernel<AK, BK><<<grid, GT_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta, kps);                  \
   } while (0)
   if (a_k_contiguous && b_k_contiguous) GT_LAUNCH(true, true);

@@ -560,12 +560,8 @@ extern "C" int dfb200_emd_forward(int b, int n, const float* xyz1, const float* 
   DFB_REQUIRE(smem <= 200 * 1024, DFB200_ERR_UNSUPPORTED, "emd_forward: n=%d exceeds the shared-memory resident limit (10240)", n);
   DFB_CUDA(cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // cluster size: as many CTAs per cloud pair as keeps batch x C within one wave of the SMs (1 CTA per SM), at most 8
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    DFB_CUDA(cudaGetDevice(&dev));
-    DFB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int n_sm = current_device_sm_count();
+  DFB_REQUIRE(n_sm > 0, DFB200_ERR_CUDA, "emd_forward: cannot query the SM count of the current device");
   int C = 1;
   while (C < 8 && b * C * 2 <= n_sm && n / (C * 2) >= EMD_SOLO) C *= 2;
   cudaLaunchConfig_t cfg{};
@@ -577,8 +573,7 @@ extern "C" int dfb200_emd_forward(int b, int n, const float* xyz1, const float* 
   // very few, large cloud pairs (batch <= 4, n >= 4096): 8 SMs per pair leave the bid scan far behind the reference's
   // whole-GPU launches, so opt in to the non-portable 16-CTA cluster when the device can co-schedule one per pair
   if (C == 8 && b * 16 * 2 <= n_sm && n / 32 >= EMD_SOLO / 2) {
-    static bool np_ok = cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    if (np_ok) {
+    if (cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       attr[0].val.clusterDim.x = 16;
       cfg.gridDim = dim3(b * 16);
       int active = 0;
@@ -589,6 +584,8 @@ extern "C" int dfb200_emd_forward(int b, int n, const float* xyz1, const float* 
         attr[0].val.clusterDim.x = C;
         cfg.gridDim = dim3(b * C);
       }
+    } else {
+      (void)cudaGetLastError();
     }
   }
   DFB_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel, n, xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments,

@@ -1,4 +1,7 @@
 // tcgen05 building-block self-test and issue-rate microbenchmark (dfb200_selftest_umma, dfb200_bench_umma).
+// Diagnostics only: compiled into libdifffacto_b200_diag.so (-DDFB200_DIAGNOSTICS), never into the product library.
+#ifdef DFB200_DIAGNOSTICS
+#include "../../include/difffacto_b200_diag.h"
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -391,3 +394,4 @@ extern "C" int dfb200_bench_umma2(int mode, int N, int iters, int ksteps, long l
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }
+#endif  // DFB200_DIAGNOSTICS

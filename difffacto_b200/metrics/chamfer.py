@@ -25,6 +25,21 @@ def chamfer_forward(xyz1, xyz2):
     return dist1, dist2, idx1, idx2
 
 
+def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
+    """-> grad_xyz1 (B,n,3), grad_xyz2 (B,m,3)  (reference chamfer.backward, chamfer_cuda.cpp:27-34 / chamfer.cu:173-229)."""
+    require_cuda(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2)
+    xyz1 = xyz1.contiguous().float()
+    xyz2 = xyz2.contiguous().float()
+    g1 = torch.empty_like(xyz1)
+    g2 = torch.empty_like(xyz2)
+    B, n, _ = xyz1.shape
+    with _lib.on(xyz1.device):
+        check(_lib.load().dfb200_chamfer_backward(B, n, ptr(xyz1), xyz2.shape[1], ptr(xyz2), ptr(idx1.contiguous()),
+                                                  ptr(idx2.contiguous()), ptr(grad_dist1.contiguous().float()),
+                                                  ptr(grad_dist2.contiguous().float()), ptr(g1), ptr(g2), stream()))
+    return g1, g2
+
+
 class ChamferFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
@@ -37,14 +52,7 @@ class ChamferFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_dist1, grad_dist2):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        g1 = torch.empty_like(xyz1)
-        g2 = torch.empty_like(xyz2)
-        B, n, _ = xyz1.shape
-        with _lib.on(xyz1.device):
-            check(_lib.load().dfb200_chamfer_backward(B, n, ptr(xyz1), xyz2.shape[1], ptr(xyz2), ptr(idx1), ptr(idx2),
-                                                      ptr(grad_dist1.contiguous()), ptr(grad_dist2.contiguous()),
-                                                      ptr(g1), ptr(g2), stream()))
-        return g1, g2
+        return chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2)
 
 
 class _ChamferBase(torch.nn.Module):

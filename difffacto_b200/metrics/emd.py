@@ -10,6 +10,33 @@ from .._lib import check, ptr, require_cuda, stream
 from ..utils.registry import METRICS
 
 
+def emd_forward(xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments, max_increments, unass_idx, unass_cnt,
+                unass_cnt_sum, cnt_tmp, max_idx, eps, iters):
+    """The reference extension's `emd.forward` (emd.cpp:14-17): every buffer is caller-allocated, results land in `dist`
+    (squared matched distances) and `assignment`.  The kernel initialises its own scratch, so the caller's fill values
+    do not matter; `unass_cnt_sum` / `cnt_tmp` (>= batch int32 each) receive per-pair diagnostics (rounds run, round from
+    which one CTA finished alone)."""
+    require_cuda(xyz1, xyz2, dist, assignment)
+    b, n, _ = xyz1.shape
+    for t, dt, name in ((xyz1, torch.float32, "xyz1"), (xyz2, torch.float32, "xyz2"), (dist, torch.float32, "dist"),
+                        (assignment, torch.int32, "assignment")):
+        _lib.require(t, dt, name)
+    with _lib.on(xyz1.device):
+        check(_lib.load().dfb200_emd_forward(b, n, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(assignment), ptr(price), ptr(assignment_inv),
+                                             ptr(bid), ptr(bid_increments), ptr(max_increments), ptr(unass_idx), ptr(unass_cnt),
+                                             ptr(unass_cnt_sum), ptr(cnt_tmp), ptr(max_idx), float(eps), int(iters), stream()))
+    return 1
+
+
+def emd_backward(xyz1, xyz2, gradxyz, graddist, idx):
+    """The reference extension's `emd.backward` (emd.cpp:19-22, emd_cuda.cu:284-317): gradxyz (B,n,3) <- d(sum graddist*dist)/d xyz1."""
+    require_cuda(xyz1, xyz2, gradxyz, graddist, idx)
+    B, n, _ = xyz1.shape
+    with _lib.on(xyz1.device):
+        check(_lib.load().dfb200_emd_backward(B, n, ptr(xyz1), ptr(xyz2), ptr(gradxyz), ptr(graddist), ptr(idx), stream()))
+    return 1
+
+
 class emdFunction(Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2, eps, iters):
@@ -36,11 +63,8 @@ class emdFunction(Function):
         unass_cnt = torch.zeros(512, **i32)
         rounds = torch.zeros(512, **i32)      # diagnostics: auction rounds executed per pair ...
         solo_from = torch.zeros(512, **i32)   # ... and the round from which one CTA finished alone
-        with _lib.on(dev):
-            check(_lib.load().dfb200_emd_forward(batchsize, n, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(assignment), ptr(price),
-                                                 ptr(assignment_inv), ptr(bid), ptr(bid_increments), ptr(max_increments),
-                                                 ptr(unass_idx), ptr(unass_cnt), ptr(rounds), ptr(solo_from), ptr(max_idx), float(eps),
-                                                 int(iters), stream()))
+        emd_forward(xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments, max_increments, unass_idx, unass_cnt,
+                    rounds, solo_from, max_idx, eps, iters)
         emdFunction.last_stats = (rounds[:batchsize], solo_from[:batchsize], unass_cnt[:batchsize])
         ctx.save_for_backward(xyz1, xyz2, assignment)
         return dist, assignment
@@ -51,9 +75,7 @@ class emdFunction(Function):
         graddist = graddist.contiguous()
         gradxyz1 = torch.empty_like(xyz1)
         gradxyz2 = torch.zeros_like(xyz2)
-        B, n, _ = xyz1.shape
-        with _lib.on(xyz1.device):
-            check(_lib.load().dfb200_emd_backward(B, n, ptr(xyz1), ptr(xyz2), ptr(gradxyz1), ptr(graddist), ptr(assignment), stream()))
+        emd_backward(xyz1, xyz2, gradxyz1, graddist, assignment)
         return gradxyz1, gradxyz2, None, None
 
 

@@ -303,7 +303,10 @@ class AnchoredDiffusion(Module):
         if noise is None:
             noise = torch.randn_like(x_start)
         x_t = self.q_sample(x_start, t, anchors, noise=noise, variance=variance)
-        eps = self._eps(x_t, t, anchors, ctx, variance, anchor_assignment, valid_id)
+        # the conditional net only: classifier-free guidance is a SAMPLING-time mix (reference :263-266 sits in
+        # p_mean_variance; training_losses :787-797 calls self.model once), and the mix kernel has no autograd
+        eps = self.model(x_t, self._scale_timesteps(t), ctx, anchors=anchors.transpose(1, 2), anchor_assignment=anchor_assignment,
+                         variances=variance.transpose(1, 2), valid_id=valid_id)
         loss = (noise - eps) ** 2
         if flags is not None:
             loss = loss * flags

@@ -37,6 +37,16 @@ def gather_shapes(local, total, group=None):
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
 
 
-def rank_seed(seed, rank):
-    """Per-rank RNG stream, as the reference seeds `seed + local_rank` (runner/runner.py:39)."""
-    return int(seed) + int(rank)
+def rank_seed(seed, rank, world_size=None):
+    """Philox key of `rank` for the stream `seed` (the reference seeds `seed + local_rank`, runner/runner.py:39).
+    The Philox counter of the sampling kernels is the LOCAL element index plus the timestep, so two shards with equal
+    keys would draw identical noise.  `seed + rank` collides as soon as the caller's seeds are consecutive (batch index
+    + 1 on rank r-1 == batch index on rank r); with `world_size` the key is `seed * world_size + rank`, which is unique
+    per (seed, rank)."""
+    if world_size is None:
+        if dist.is_available() and dist.is_initialized():
+            world_size = dist.get_world_size()
+        else:
+            world_size = 1
+    assert 0 <= int(rank) < int(world_size)
+    return int(seed) * int(world_size) + int(rank)

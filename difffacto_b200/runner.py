@@ -86,7 +86,7 @@ class Runner:
             N = b["assign"].shape[1]
             out = self.diffusion.p_sample_loop([hi - lo, 3, N], b["anchors"], ctx=[b["code"], b["params"]], variance=b["variance"],
                                                anchor_assignment=b["assign"], valid_id=b["valid"], rng=rng,
-                                               seed=rank_seed(self.seed * 7919 + bi, self.rank),
+                                               seed=rank_seed(self.seed * 7919 + bi, self.rank, self.world),
                                                traj_interval=self.ret_interval if self.ret_traj else None)
             x0, traj = out if self.ret_traj else (out, None)
             res = {"pred": gather_shapes(x0.transpose(1, 2).contiguous(), B)}  # (B,N,3), as AnchorDiffAE.decode returns
@@ -123,7 +123,7 @@ class Runner:
             from .models.encoders.part_encoders import _exp_shift
             variance = _exp_shift(logvar_pp)
             x0 = self.diffusion.p_sample_loop(list(mean_pp.shape), mean_pp, ctx=ctx, variance=variance, anchor_assignment=seg, valid_id=vid,
-                                              rng=rng, seed=rank_seed(self.seed * 7919 + bi, self.rank))
+                                              rng=rng, seed=rank_seed(self.seed * 7919 + bi, self.rank, self.world))
             results["pred"].append(x0.transpose(1, 2).contiguous().cpu().numpy())
             results["seg_mask_ref"].append(seg.cpu().numpy())
         results = {k: np.concatenate(v, axis=0) for k, v in results.items()}

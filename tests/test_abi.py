@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    hdr = open(os.path.join(ROOT, "include", "difffacto_b200.h")).read()
+def header_symbols(name="difffacto_b200.h"):
+    hdr = open(os.path.join(ROOT, "include", name)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(dfb200_[a-z0-9_]+)\s*\(", hdr)))
 
@@ -24,6 +24,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
     assert lib.dfb200_abi_version() == 1
     assert isinstance(lib.dfb200_launch_count(), int)
+
+
+def test_diagnostics_are_not_in_the_product_library():
+    """Self-tests / microbenchmarks / the timeline hook live only in the -DDFB200_DIAGNOSTICS build."""
+    from difffacto_b200 import _lib
+    lib = _lib.load()
+    diag_names = header_symbols("difffacto_b200_diag.h")
+    assert sorted(_lib.DIAG_SIGNATURES) == diag_names and len(diag_names) == 5
+    for n in diag_names:
+        assert not hasattr(lib, n), f"{n} is a diagnostic and must not be exported by the product library"
+    dlib = _lib.load_diag()
+    for n in diag_names + header_symbols():
+        assert hasattr(dlib, n), f"{n} missing from the diagnostic build"
 
 
 def test_no_torch_in_abi():

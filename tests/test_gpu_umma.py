@@ -1,4 +1,5 @@
-"""-m gpu: the tcgen05 building blocks (dfb200_selftest_umma) against a bf16-operand fp32-accumulate reference."""
+"""-m gpu: the tcgen05 building blocks (dfb200_selftest_umma, diagnostic build of the library) against a bf16-operand
+fp32-accumulate reference."""
 import pytest
 import torch
 
@@ -17,7 +18,7 @@ def test_umma_selftest(variant, N, K):
     Cin = torch.randn(128, N, device="cuda")
     D = torch.empty(128, N, device="cuda")
     scratch = torch.zeros(N * K * 2 + 256, dtype=torch.uint8, device="cuda")
-    _lib.check(_lib.load().dfb200_selftest_umma(variant, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(Cin),
+    _lib.check(_lib.load_diag().dfb200_selftest_umma(variant, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(Cin),
                                                 _lib.ptr(D), _lib.ptr(scratch), _lib.stream()))
     torch.cuda.synchronize()
     assert (D - ref(A, W, bias, Cin)).abs().max().item() < 2e-4 * K ** 0.5 + 1e-4
@@ -36,7 +37,7 @@ def test_umma_cta_pair_selftest(variant, N, K):
     Cin = torch.randn(256, N, device="cuda")
     D = torch.empty(256, N, device="cuda")
     scratch = torch.zeros(N * K * 2 + 256, dtype=torch.uint8, device="cuda")
-    _lib.check(_lib.load().dfb200_selftest_umma2(variant, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(Cin),
+    _lib.check(_lib.load_diag().dfb200_selftest_umma2(variant, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(Cin),
                                                  _lib.ptr(D), _lib.ptr(scratch), _lib.stream()))
     torch.cuda.synchronize()
     assert (D - ref(A, W, bias, Cin)).abs().max().item() < 2e-4 * K ** 0.5 + 1e-4

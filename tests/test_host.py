@@ -140,7 +140,17 @@ def test_shard_range_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
-    assert rank_seed(5, 3) == 8
+
+
+def test_rank_seed_is_unique_per_batch_and_rank():
+    """Philox keys of (batch index, rank) must not collide: the kernels' counter is the LOCAL element index, so equal
+    keys on two shards would draw identical x_T and step noise (the round-1 `seed + rank` did for consecutive seeds)."""
+    assert rank_seed(5, 3, 4) == 23 and rank_seed(5, 0, 1) == 5
+    for W in (1, 2, 8):
+        keys = {rank_seed(7919 * s + bi, r, W) for s in range(3) for bi in range(50) for r in range(W)}
+        assert len(keys) == 3 * 50 * W
+    with pytest.raises(AssertionError):
+        rank_seed(1, 4, 4)
 
 
 def _gloo_worker(rank, world, total, port, q):

@@ -1,6 +1,7 @@
 """Diagnostic (GPU box): phase timeline (SM cycles) of CTA 0 of the fused bf16 denoiser kernel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("DFB200_DIAGNOSTICS", "1")  # the whole run goes through the diagnostic build of the library
 import torch
 import bench
 from difffacto_b200 import _lib

@@ -25,7 +25,7 @@ def run(variant, N, K, use_bias, use_cin):
     Cin = torch.randn(128, N, device="cuda") if use_cin else None
     D = torch.full((128, N), float("nan"), device="cuda")
     scratch = torch.zeros(N * K * 2 + 256, dtype=torch.uint8, device="cuda")
-    lib = _lib.load()
+    lib = _lib.load_diag()
     rc = lib.dfb200_selftest_umma(variant, N, K, _lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(Cin), _lib.ptr(D),
                                   _lib.ptr(scratch), _lib.stream())
     torch.cuda.synchronize()

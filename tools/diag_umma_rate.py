@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from difffacto_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_diag()
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 for layout in (0, 2, 1):
     for N in (64, 128, 256):
