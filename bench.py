@@ -3,7 +3,7 @@
 gen_chair denoiser) -- BASELINE.json `configs[1]` (batch 32 per B200; N GPUs = N x 32 shapes, weak scaling,
 one NCCL all-gather of the finished points).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32|fp32] [--suite all|headline]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch: x_T -> x_0 for 32 shapes per GPU.
@@ -98,6 +98,15 @@ def synthetic_batch(seed, B, N):
     return dict(code=code, params=params, anchors=anchors, variance=variance, assign=assign, valid=valid)
 
 
+def config_dict(world):
+    """The workload both arms run -- `--impl reference` prints the identical dict (the driver compares them)."""
+    return {"workload": WORKLOAD, "timesteps": T_STEPS, "points": NPTS, "parts": 4, "batch_per_gpu": B_PER_GPU,
+            "global_batch": B_PER_GPU * world,
+            "parallelism": f"GPU arm: batch-sharded x{world} (weak scaling), one all-gather of final points; reference arm: the per-GPU "
+                           "batch on the host cores of rank 0",
+            "l2": "GPU arm: flushed (256 MB write) between timed iterations; inputs of the e2e loop arrive from pinned host memory"}
+
+
 def run_reference(args):
     """The reference's CPU path (PyTorch fp32 port in oracle/) on all host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -108,7 +117,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = R.synthetic_state_dict(0)
-    B, N, S = B_PER_GPU, NPTS, 3  # bounded sample: S denoiser+update steps of the full batch, scaled to T
+    B, N, S = B_PER_GPU, NPTS, 10  # bounded sample: S denoiser+update steps of the full batch per timed step, scaled to T
     b = synthetic_batch(0, B, N)
     s = R.schedule(T_STEPS)
     x = torch.sqrt(b["variance"]) * torch.randn(B, 3, N) + b["anchors"]
@@ -121,20 +130,22 @@ def run_reference(args):
                                   torch.randn(B, 3, N))
         return xx
 
-    for _ in range(args.warmup):
-        sample_steps()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sample_steps()
-    dt = (time.perf_counter() - t0) / args.steps
-    per_step = dt / S
-    value = B / (per_step * T_STEPS)
-    sample = f"{S} denoiser+update steps of the batch-{B} workload per timed step, scaled to T={T_STEPS} (per-step cost is t-independent)"
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            sample_steps()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sample_steps()
+    dt = (time.perf_counter() - t0) / args.steps  # seconds per timed step = S sampling steps of the batch
+    value = B / (dt / S * T_STEPS)
+    sample = (f"each timed step = {S} denoiser+update steps of the batch-{B} workload ({S}/{T_STEPS} of one reverse process); value scaled "
+              f"to T={T_STEPS} (per-step cost does not depend on t); ms_per_step is the measured time of the bounded step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3 * T_STEPS / S, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "timesteps": T_STEPS, "points": N, "parts": 4, "batch_per_gpu": B},
+        "config": config_dict(max(1, args.gpus)),
+        "impl_detail": {"precision": "fp32", "rng": "torch.randn per step", "threads": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -151,15 +162,16 @@ def cpu_baseline(budget_s=15.0):
     s = R.schedule(T_STEPS)
     x = torch.sqrt(b["variance"]) * torch.randn(B, 3, N) + b["anchors"]
     n, t0 = 0, time.perf_counter()
-    while True:
-        t = torch.full((B,), T_STEPS - 1 - n, dtype=torch.long)
-        if n == 1:
-            t0 = time.perf_counter()  # first step = warm-up
-        x, _, _ = R.p_sample(sd, s, x, t, [b["code"], b["params"]], b["anchors"], b["variance"], b["assign"], b["valid"],
-                             torch.randn(B, 3, N))
-        n += 1
-        if n >= 3 and (time.perf_counter() - t0 > budget_s or n >= 40):
-            break
+    with torch.no_grad():
+        while True:
+            t = torch.full((B,), T_STEPS - 1 - n, dtype=torch.long)
+            if n == 1:
+                t0 = time.perf_counter()  # first step = warm-up
+            x, _, _ = R.p_sample(sd, s, x, t, [b["code"], b["params"]], b["anchors"], b["variance"], b["assign"], b["valid"],
+                                 torch.randn(B, 3, N))
+            n += 1
+            if n >= 3 and (time.perf_counter() - t0 > budget_s or n >= 40):
+                break
     per_step = (time.perf_counter() - t0) / (n - 1)
     return {"value": B / (per_step * T_STEPS), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n - 1} denoiser+update steps at batch {B} (oracle PyTorch port of the reference path), scaled to T={T_STEPS}"}
@@ -179,14 +191,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B, N, T = B_PER_GPU, NPTS, T_STEPS
     diff = build_model(T, args.precision).to(dev).eval()
-    host = {k: v.pin_memory() for k, v in synthetic_batch(100 + rank, B, N).items()}
-    res = {k: v.to(dev) for k, v in host.items()}
-    out_host = torch.empty(B, N, 3).pin_memory()
+    host = [{k: v.pin_memory() for k, v in synthetic_batch(100 + rank, B, N).items()} for _ in range(2)]  # double-buffered staging
+    res = {k: v.to(dev) for k, v in host[0].items()}
+    out_host = [torch.empty(B, N, 3).pin_memory() for _ in range(2)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def hot(step, resident=True):
-        """one pass of the hot path over one batch; returns the (B,N,3) points on this rank"""
-        d = res if resident else {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    def hot(step, d):
+        """one pass of the hot path over one batch; returns the (B*world,N,3) points"""
         x0 = diff.p_sample_loop([B, 3, N], d["anchors"], ctx=[d["code"], d["params"]], variance=d["variance"],
                                 anchor_assignment=d["assign"], valid_id=d["valid"], rng="philox",
                                 seed=rank_seed(1000 + step, rank, world))
@@ -198,36 +209,102 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, resident):
+    def max_over_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return tt.item()
+        return ms
+
+    def timed_resident(n):
+        """`value`: inputs resident in HBM; each iteration timed by CUDA events between barriers, L2 flushed in between."""
         evs, launches0 = [], _lib.launch_count()
         for s in range(n):
-            flush.fill_(s & 0xFF)  # L2 flush between timed iterations (outside the events)
+            flush.fill_(s & 0xFF)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            pts = hot(s, resident)
-            if not resident:
-                out_host.copy_(pts[rank * B:(rank + 1) * B] if world > 1 else pts, non_blocking=True)
+            hot(s, res)
             e1.record()
             barrier()
             evs.append(e0.elapsed_time(e1))
-        total_ms = sum(evs)
-        if world > 1:
-            tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            total_ms = tt.item()
-        return total_ms, _lib.launch_count() - launches0
+        return max_over_ranks(sum(evs)), _lib.launch_count() - launches0
+
+    def timed_e2e(n):
+        """`e2e`: the same call fed from PINNED HOST buffers, result read back to the host, every iteration, all inside ONE timed
+        region of n iterations.  Staging is double-buffered on side streams (inputs of iteration s+1 upload while s computes, the
+        points of s download while s+1 computes), as a serving loop would run it; the L2 flush stays between iterations."""
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+        in_ready = [None, None]
+        comp_done = [None, None]
+        out_done = [None, None]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        s_in.wait_stream(cur)
+        for s in range(n + 1):
+            k = s & 1
+            if s < n:  # upload inputs of iteration s (its device buffers were last read by iteration s-2)
+                with torch.cuda.stream(s_in):
+                    if comp_done[k] is not None:
+                        s_in.wait_event(comp_done[k])
+                    for name, v in host[k].items():
+                        dbuf[k][name].copy_(v, non_blocking=True)
+                    in_ready[k] = torch.cuda.Event()
+                    in_ready[k].record(s_in)
+            if s >= 1:  # compute iteration s-1 (its inputs were uploaded during iteration s-2's compute), then download
+                j = (s - 1) & 1
+                cur.wait_event(in_ready[j])
+                flush.fill_(s & 0xFF)
+                pts = hot(s - 1, dbuf[j])
+                comp_done[j] = torch.cuda.Event()
+                comp_done[j].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(comp_done[j])
+                    if out_done[j] is not None:
+                        out_done[j].synchronize()  # host buffer j is free again (a consumer would have taken it by now)
+                    out_host[j].copy_(pts[rank * B:(rank + 1) * B] if world > 1 else pts, non_blocking=True)
+                    pts.record_stream(s_out)
+                    out_done[j] = torch.cuda.Event()
+                    out_done[j].record(s_out)
+        cur.wait_stream(s_out)
+        e1.record(cur)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
 
     for s in range(args.warmup):
-        hot(s)
+        hot(s, res)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed(args.steps, True)
+    total_ms, launches = timed_resident(args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms, _ = timed(max(1, min(args.steps, 3)), False)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(10, min(args.steps, 20))
+    e2e_ms = timed_e2e(e2e_steps)
+
+    extra = {}
+    if args.suite == "all":
+        from tools import bench_blocks as BB
+        t_extra = time.perf_counter()
+        try:  # BASELINE configs[3], denoiser part: every rank takes part (DDP) -- at N=1 a single-GPU step
+            extra["train"] = BB.train_block(torch, dist, build_model, synthetic_batch, world, rank, local, FLOP_PER_POINT_STEP)
+        except Exception as e:
+            extra["train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1:
+            for name, fn in (
+                    ("e2e_generator", lambda: BB.generator_block(torch, diff, res, B, N)),
+                    ("precision_modes", lambda: BB.precision_block(torch, build_model, synthetic_batch, B, N, T, FLOP_PER_POINT_STEP)),
+                    ("ops", lambda: BB.ops_block(torch, flush)),
+                    ("eval", lambda: BB.eval_block(torch, flush)),
+                    ("gpu_eager_baseline", lambda: BB.gpu_eager_block(torch, synthetic_batch, B, N, T))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:
+                    extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        extra["extra_blocks_wall_s"] = round(time.perf_counter() - t_extra, 1)
     if rank == 0:
         value = B * world * args.steps / (total_ms * 1e-3)
         e2e = B * world * e2e_steps / (e2e_ms * 1e-3)
@@ -235,25 +312,26 @@ def run_ours(args):
         ms_per_net_step = total_ms / args.steps / T
         flop = B * N * FLOP_PER_POINT_STEP
         achieved = flop / (ms_per_net_step * 1e-3) / 1e12
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "timesteps": T, "points": N, "parts": 4, "batch_per_gpu": B,
-                       "global_batch": B * world, "parallelism": f"batch-sharded x{world}, one all-gather of final points",
-                       "precision": args.precision, "rng": "in-kernel philox", "l2": "flushed (256 MB write) between timed iterations"},
+            "dtype": {"bf16": "bf16", "tf32": "tf32"}.get(args.precision, "f32"), "data": "synthetic",
+            "config": config_dict(world),
+            "impl_detail": {"precision": args.precision, "rng": "in-kernel philox", "loop": "one persistent fused launch per reverse process"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_STEP * 1e-9,
                          "note": f"algorithmic {flop / 1e9:.1f} GFLOP per denoiser step (B*N*{FLOP_PER_POINT_STEP}) / mean time of one "
                                  f"sampling step ({ms_per_net_step * 1e3:.1f} us: context kernels + fused denoiser + update), CUDA events "
                                  f"over the timed region; peak {peak_src}; traffic = measured DRAM GB per sampling step (ncu), algorithmic "
                                  f"{B * N * 64 / 1e9:.4f} GB"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host[0].numel() * 4,
+                    "iterations": e2e_steps, "staging": "pinned host buffers, double-buffered H2D / D2H on side streams, one timed region"},
             "gpu_launches": launches,
             "clocks": clocks,
             "cpu_baseline": cpu_baseline() if world == 1 else None,
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -265,7 +343,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--suite", default="all", choices=["all", "headline"],
+                    help="all: headline + the secondary blocks (train, e2e_generator, precision_modes, ops, eval, gpu_eager_baseline); "
+                         "headline: the timed loop only (use under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

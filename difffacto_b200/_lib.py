@@ -20,6 +20,14 @@ class DenoiserCfg(ctypes.Structure):
                 ("depth", c_int), ("context_dim", c_int), ("n_class", c_int), ("flags", c_int)]
 
 
+class SampleOpts(ctypes.Structure):
+    """struct dfb200_sample_opts"""
+    _fields_ = [("timesteps", c_void_p), ("timesteps_host", ctypes.POINTER(c_int)), ("n_timesteps", c_int),
+                ("first_step", c_int), ("num_steps", c_int), ("tables_ready", c_int), ("ddim", c_int), ("ddim_eta", c_float),
+                ("alphas_cumprod_prev", c_void_p), ("xt_dir_coeff", c_void_p), ("guidance", c_int),
+                ("classifier_weight", c_float), ("step_sample", c_void_p), ("step_xstart", c_void_p)]
+
+
 NET_CLASS_COND, NET_CAT_PARAMS_TO_X, NET_CAT_CLASS_TO_X, NET_MASK_UNREFERENCED, NET_INCLUDE_STD = 1, 2, 4, 8, 16
 MODE_FP32, MODE_BF16 = 0, 1
 SCHED_ROWS = 8
@@ -83,6 +91,9 @@ SIGNATURES = {
     "dfb200_ddpm_sample_loop_workspace_bytes": (c_size_t, [_CFG, c_int, c_int, c_int, c_int]),
     "dfb200_ddpm_sample_loop": (c_int, [_CFG, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_u64, P,
                                          c_int, P, c_size_t, P]),
+    "dfb200_sample_loop_chunk": (c_int, [_CFG, c_int, c_int, c_int, c_int]),
+    "dfb200_sample_loop": (c_int, [_CFG, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_u64, P,
+                                    c_int, ctypes.POINTER(SampleOpts), P, c_size_t, P]),
 }
 
 # include/difffacto_b200_diag.h: exported only by the diagnostic build

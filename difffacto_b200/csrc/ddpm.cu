@@ -125,12 +125,7 @@ ddim_step_kernel(long long total, int per_sample, int T, const float* __restrict
   const StepCoef c = load_step_coef(sched, T, tt);
   const float x = __ldg(x_t + q), a = __ldg(anchors + q), v = __ldg(variance + q), e = __ldg(eps + q);
   const float x0 = ddpm_xstart(c, x, a, v, e);
-  const float L = __fsqrt_rn(v);
-  const float lhs = __fadd_rn(__fmul_rn(__fsub_rn(x0, a), __fsqrt_rn(__ldg(acp + tt))), a);
-  const float xt_dir = __fmul_rn(__fmul_rn(L, __ldg(dir_coeff + tt)), e);
-  const float sd = __fsqrt_rn(__fmul_rn(c.post_var, v));
-  const float nz = __fmul_rn(__fmul_rn(__fmul_rn(eta, c.nonzero), sd), noise != nullptr ? __ldg(noise + q) : 0.f);
-  x_prev[q] = __fadd_rn(__fadd_rn(lhs, xt_dir), nz);
+  x_prev[q] = ddim_prev(c, a, v, x0, e, noise != nullptr ? __ldg(noise + q) : 0.f, __fsqrt_rn(__ldg(acp + tt)), __ldg(dir_coeff + tt), eta);
   if (pred_xstart != nullptr) pred_xstart[q] = x0;
 }
 

@@ -41,4 +41,17 @@ __device__ __forceinline__ float ddpm_prev(const StepCoef& c, float x, float a, 
   return __fadd_rn(mean, __fmul_rn(__fmul_rn(c.nonzero, sd), z));
 }
 
+// DDIM variant (anchored_diffusion.py:368-374 xt_dir, :480-481 sample) in the reference's op order:
+//   sample = (((x0 - a) * sqrt(acp_t) + a) + (L * dir_t) * eps) + ((eta * nonzero) * sqrt(pv_t * var)) * z
+// sqrt_acp = sqrt(float32(alphas_cumprod_prev[t])), dir = float32(sqrt(1 - ac - eta^2 * posterior_variance))[t]
+__device__ __forceinline__ float ddim_prev(const StepCoef& c, float a, float var, float x0, float eps, float z, float sqrt_acp,
+                                           float dir, float eta) {
+  const float L = __fsqrt_rn(var);
+  const float lhs = __fadd_rn(__fmul_rn(__fsub_rn(x0, a), sqrt_acp), a);
+  const float xt_dir = __fmul_rn(__fmul_rn(L, dir), eps);
+  const float sd = __fsqrt_rn(__fmul_rn(c.post_var, var));
+  const float nz = __fmul_rn(__fmul_rn(__fmul_rn(eta, c.nonzero), sd), z);
+  return __fadd_rn(__fadd_rn(lhs, xt_dir), nz);
+}
+
 }  // namespace dfb200

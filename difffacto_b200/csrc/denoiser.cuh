@@ -72,20 +72,25 @@ int launch_context_kv_time(const PackLayout& L, const float* packed, int T, cons
 struct TcUpdate {
   const float* sched;  // device schedule table [DFB200_SCHED_ROWS][T]
   int T, t;            // first timestep of this launch (same for every sample of the batch)
-  int n_steps;         // timesteps t, t-1, ..., t-n_steps+1 run inside ONE persistent launch
+  int n_steps;         // timesteps t, t-1, ..., t-n_steps+1 (or step_t[0..n_steps)) run inside ONE persistent launch
+  const int* step_t;   // optional device list of this launch's timesteps in execution order (strided DDIM lists)
+  int step_base;       // sampling steps completed by earlier launches of the same loop (the `done` counters keep counting)
   size_t fold_step_bytes;  // distance between consecutive steps' fold packets
   const float* noise;  // (n_steps,B,3,N) N(0,1), first slice = step t, or NULL -> Philox(seed, offset = timestep)
   uint64_t seed;
   float* x_out;        // x_{t-1}; must alias x when n_steps > 1
   int* done;           // per 256-token unit: tile-steps completed since the loop began (zeroed by the caller); required if n_steps > 1
   float* traj; int traj_interval;  // optional trajectory slots (see dfb200_ddpm_sample_loop)
+  float* step_sample; float* step_xstart;  // optional (n_steps,B,3,N): sample / pred_xstart after each step of this launch
+  const float* ddim_acp; const float* ddim_dir; float ddim_eta;  // DDIM update when ddim_acp != NULL (device float32[T] tables)
+  int guidance; float guid_w;  // classifier-free guidance: `fold` holds 2B entries per step (conditional, then unconditional)
 };
 int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
                      const float* variances, const int* assign, const float* valid_id, const void* fold, float* eps_out,
                      const TcUpdate* upd, cudaStream_t st);
-// fold tiles for `steps` consecutive timesteps t_first, t_first-1, ...: fold[(s*B + b)*depth + l]
+// fold tiles for `steps` timesteps t_first, t_first-1, ... (or step_t[0..steps) when given): fold[(s*B + b)*depth + l]
 int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time,
-                        int t_first, int steps, void* fold, cudaStream_t st);
+                        int t_first, const int* step_t, int steps, void* fold, cudaStream_t st);
 size_t tc_fold_bytes_for(const NetDims& d, int B);
 
 int denoiser_forward_fp32(const PackLayout& L, const float* packed, int B, int N, const float* x,

@@ -35,8 +35,8 @@ using namespace tc;
 //   0, 1 : "fold" packets of tile 0 / tile 1 (per sample+block, rebuilt every step by context_fold_kernel):
 //          W_sim tile (32 x 128, 8 KB) | bias_sim slab (512 B) | W_pv tile (128 x 32, 8 KB)
 //   static stream, 24 packets per block at an 18 KB stride:
-//   s0: W1'_0 k[0,64) + b1'_0 slab     s1: W1'_0 k[64,128) + bo slab
-//   then for c = 0..6:  W2_c | W1'_{c+1} k[0,64) + b1'_{c+1} slab | W1'_{c+1} k[64,128)      and finally W2_7 + b2 slab
+//   s0: W1'_0 k[0,64)                  s1: W1'_0 k[64,128) + bo slab
+//   then for c = 0..6:  W2_c | W1'_{c+1} k[0,64) | W1'_{c+1} k[64,128)                      and finally W2_7 + b2 slab
 // W1'_c (128 x 128): rows [0,64) = value units 64c.. (scaled by 1/2, the GELU's 1/2), rows [64,128) = gate units
 // 512+64c..; W1' = W1.diag(norm3.w), b1' = b1 + W1.norm3.b.  W2_c: 128 rows x k[64c, 64c+64).
 // ---------------------------------------------------------------------------------------------
@@ -52,10 +52,7 @@ constexpr int FOLD_WSIM = 0, FOLD_BSIM = 8192, FOLD_WPV = 8704, FOLD_BYTES = 168
 __host__ __device__ inline int pkt_bytes(int p) {
   if (p < 2) return FOLD_BYTES;
   const int s = p - 2;
-  if (s == 0 || s == 1) return 16384 + 2048;
-  if (s == 23) return 16384 + 2048;
-  const int r = (s - 2) % 3;  // 0: W2_c, 1: W1 A-half (+slab), 2: W1 B-half
-  return r == 1 ? 16384 + 2048 : 16384;
+  return (s == 1 || s == 23) ? 16384 + 2048 : 16384;  // W1'_0 B-half carries the bo slab, W2_7 the b2 slab
 }
 __host__ __device__ inline int spkt_w1a(int c) { return c == 0 ? 0 : 3 + 3 * (c - 1); }  // static index of W1'_c k[0,64)
 __host__ __device__ inline int spkt_w1b(int c) { return spkt_w1a(c) + 1; }
@@ -70,11 +67,15 @@ __host__ __device__ inline int spkt_w2(int c) { return 2 + 3 * c; }
 //   fold kernel (fp32).
 constexpr uint32_t IH_INTILE = 0, IH_HEADTILE = 8192, IH_HEADSLAB = 12288, IH_CONST = 12544, INHEAD_BYTES = 13056;
 constexpr int IHC_GT = 0, IHC_GP = 45, IHC_CP = 81;  // float offsets inside IH_CONST (85 floats)
+//   then per block b1p (1024 fp32): the folded GEGLU-in bias b1' = b1 + W1.norm3.b in MMA column order -- per chunk c 128 floats,
+//   [0,64) = b1'[64c + k] / 2 (value units, the GELU's 1/2), [64,128) = b1'[512 + 64c + k] (gate units).  The feed-forward
+//   epilogue adds it on CUDA cores (it used to be a 14th K=16 MMA per tile-chunk against the ones tile).
 constexpr size_t HEAD_FLOATS = INHEAD_BYTES / 4;
 constexpr size_t FOLDW_FLOATS = (size_t)D_MODEL * D_MODEL * 2 + D_MODEL;
+constexpr size_t B1P_FLOATS = 2 * D_FF;
 
 size_t tc_stream_bytes_for(const NetDims& d) {
-  return (size_t)d.depth * STATIC_PER_LAYER * SLOT_BYTES + sizeof(float) * (HEAD_FLOATS + d.depth * FOLDW_FLOATS);
+  return (size_t)d.depth * STATIC_PER_LAYER * SLOT_BYTES + sizeof(float) * (HEAD_FLOATS + d.depth * (FOLDW_FLOATS + B1P_FLOATS));
 }
 size_t tc_fold_bytes_for(const NetDims& d, int B) { return (size_t)B * d.depth * FOLD_BYTES; }
 
@@ -111,6 +112,17 @@ __global__ void pack_bias_kernel(uint8_t* __restrict__ dst, int R, const float* 
   o[1] = lo;
 #pragma unroll
   for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
+}
+// b1p (see B1P_FLOATS): dst[c*128 + j] for chunk c, MMA column j
+__global__ void pack_b1p_kernel(float* __restrict__ dst, const float* __restrict__ b1, const float* __restrict__ W1,
+                                const float* __restrict__ beta3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * D_FF) return;
+  const int c = i >> 7, j = i & 127;
+  const int row = j < 64 ? 64 * c + j : D_FF + 64 * c + (j - 64);
+  float v = __ldg(b1 + row);
+  for (int k = 0; k < D_MODEL; ++k) v = fmaf(__ldg(W1 + (size_t)row * D_MODEL + k), __ldg(beta3 + k), v);
+  dst[i] = j < 64 ? 0.5f * v : v;
 }
 // proj_in (13 -> 128) + pre_norm as one MMA.  With h = W f + b (f = the 13 point features, of which f[9..12] is a one-hot
 // class p), LN(h)_n = rstd * ((W_n - wbar).f + (b_n - bbar)) * g_n + beta_n where wbar/bbar are the means over the 128
@@ -224,7 +236,6 @@ int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
     auto pk = [&](int p) { return base + (size_t)p * SLOT_BYTES; };
     for (int c = 0; c < FF_CHUNKS; ++c) {
       tile(pk(spkt_w1a(c)), 128, 64, P + o[B_W1], D_MODEL, 0, P + o[B_N3_W], c);
-      bias(pk(spkt_w1a(c)) + SLAB_OFF, 128, P + o[B_B1], P + o[B_W1], D_MODEL, P + o[B_N3_B], c);
       tile(pk(spkt_w1b(c)), 128, 64, P + o[B_W1], D_MODEL, 64, P + o[B_N3_W], c);
       tile(pk(spkt_w2(c)), 128, 64, P + o[B_W2], D_FF, 64 * c, nullptr, -1);
     }
@@ -232,6 +243,9 @@ int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
     bias(pk(spkt_w2(FF_CHUNKS - 1)) + SLAB_OFF, 128, P + o[B_B2], nullptr, 0, nullptr, -1);
     pack_foldw_kernel<<<D_MODEL, D_MODEL, 0, st>>>(extras + HEAD_FLOATS + (size_t)l * FOLDW_FLOATS, P + o[B_WQ], P + o[B_N2_W],
                                                    P + o[B_N2_B], P + o[B_WO]);
+    count_launch();
+    pack_b1p_kernel<<<cdiv(2 * D_FF, 256), 256, 0, st>>>(extras + HEAD_FLOATS + (size_t)L.d.depth * FOLDW_FLOATS + (size_t)l * B1P_FLOATS,
+                                                         P + o[B_B1], P + o[B_W1], P + o[B_N3_B]);
     count_launch();
   }
   pack_inhead_kernel<<<1, 128, 0, st>>>(reinterpret_cast<uint8_t*>(extras), P + L.g[P_IN_W], P + L.g[P_IN_B], P + L.g[P_PRE_W], P + L.g[P_PRE_B],
@@ -249,10 +263,12 @@ int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
 // written as bf16 UMMA tiles (the "fold" packet of (b, l)).  grid (B, depth), 256 threads.
 // ---------------------------------------------------------------------------------------------
 // kv: [B][depth][2][4][128] (full K/V, or their static half when kv_time != NULL);  kv_time: [T][depth][2][128] time half of
-// timestep (t_first - blockIdx.z), broadcast over the 4 tokens.  grid (B, depth, steps).
+// timestep step_t[blockIdx.z] (or t_first - blockIdx.z when step_t == NULL), broadcast over the 4 tokens.  grid (B, depth, steps).
+// W_sim and b_sim carry an extra factor log2(e): the softmax of the fused kernel is exp2(s' - max s') / sum, one MUFU.EX2 per logit.
+constexpr float LOG2E = 1.4426950408889634f;
 __global__ void __launch_bounds__(256)
 context_fold_kernel(int depth, const float* __restrict__ kv, const float* __restrict__ kv_time, int t_first,
-                    const float* __restrict__ extras, uint8_t* __restrict__ fold_all) {
+                    const int* __restrict__ step_t, const float* __restrict__ extras, uint8_t* __restrict__ fold_all) {
   __shared__ float K[MAX_TOKENS][D_MODEL], V[MAX_TOKENS][D_MODEL];
   // the packet is assembled in shared memory and leaves as coalesced 16-byte stores: the tile layout scatters a thread's
   // bf16 values 16..512 bytes apart, and 66 2-byte global stores per thread made this kernel store-issue bound
@@ -263,7 +279,8 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
   for (int i = t; i < 512; i += 256) {
     float kt = 0.f, vt = 0.f;
     if (kv_time != nullptr) {
-      const float* tt = kv_time + ((size_t)(t_first - (int)blockIdx.z) * depth + l) * 2 * D_MODEL;
+      const int tcur = step_t != nullptr ? __ldg(step_t + blockIdx.z) : t_first - (int)blockIdx.z;
+      const float* tt = kv_time + ((size_t)tcur * depth + l) * 2 * D_MODEL;
       kt = __ldg(tt + (i & 127));
       vt = __ldg(tt + D_MODEL + (i & 127));
     }
@@ -289,7 +306,7 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
     }
 #pragma unroll
     for (int j = 0; j < MAX_TOKENS; ++j)
-      *reinterpret_cast<__nv_bfloat16*>(out + FOLD_WSIM + tile_off(32, h * 4 + j, col)) = __float2bfloat16_rn(acc[j]);
+      *reinterpret_cast<__nv_bfloat16*>(out + FOLD_WSIM + tile_off(32, h * 4 + j, col)) = __float2bfloat16_rn(LOG2E * acc[j]);
   }
   // W_pv: thread = output channel c, columns r = (h,j)
   for (int hh = 0; hh < 4; ++hh) {
@@ -309,6 +326,7 @@ context_fold_kernel(int depth, const float* __restrict__ kv, const float* __rest
     const int h = t >> 2, j = t & 3;
     float v = 0.f;
     for (int d = 0; d < 16; ++d) v = fmaf(K[j][16 * h + d], __ldg(bqG + 16 * h + d), v);
+    v *= LOG2E;
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out + FOLD_BSIM + t * 16);
@@ -353,12 +371,21 @@ struct TcParams {
   long long* dbg;  // optional timeline buffer: CTA 0 records clock64() at the phase boundaries of its dbg_item-th work item
   int dbg_item;
   // persistent work list: item idx = step_local * n_units + unit, CTA c takes idx = c, c + gridDim.x, ...
-  int n_units, n_steps, t_first;  // units of 2 tiles; timesteps t_first, t_first-1, ... (n_steps of them)
+  int n_units, n_steps, t_first;  // units of 2 tiles; timesteps t_first, t_first-1, ... (n_steps of them) unless step_t is given
+  const int* step_t;              // optional device list of this launch's timesteps in execution order (DDIM strides)
+  int step_base;                  // sampling steps completed by earlier launches of the loop (base of the `done` counters)
   size_t fold_step_bytes;         // distance between the fold packets of consecutive steps
   int* done;                      // per unit: number of tile-steps completed since the loop began (cross-CTA dependency), or NULL
+  const float* b1p;               // folded GEGLU-in biases, [depth][8][128] fp32 (see B1P_FLOATS)
   // fused eps -> x_{t-1} update (sampling loop): active when upd_sched != NULL
   const float* upd_sched; int upd_T; const float* upd_noise; size_t noise_step_elems; uint64_t upd_seed; float* x_out;
   float* traj; int traj_interval;
+  float* step_sample; float* step_xstart;  // optional (n_steps,B,3,N): `sample` / `pred_xstart` of every step of this launch
+  const float* ddim_acp; const float* ddim_dir; float ddim_eta;  // DDIM update instead of the ancestral one when ddim_acp != NULL
+  // classifier-free guidance (anchored_diffusion.py:263-266): a unit is ONE 128-token tile run twice -- tile slot 0 with the
+  // conditional fold packets, slot 1 with the unconditional ones (fold entries [B, 2B) of a step) -- and the head mixes
+  // eps = (1 - w) * eps_uncond + w * eps_cond before the update.
+  int guidance; float guid_w; int B;
 };
 
 // Packed fp32x2 math (FFMA2 on sm_100): the CUDA-core epilogues are the bottleneck of this kernel (the
@@ -370,10 +397,17 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // GEGLU for two columns: (a/2 arrives from the MMA) * g * (1 + tanh(g*(c0 + c1 g^2))).
 // tanh-form GELU with (c0, c1) refit against the exact erf GELU (max abs error 2.7e-4 over R, below the bf16
 // rounding of the result); 5 packed FMA-pipe instructions + 2 MUFU.TANH per column pair (erff costs ~45/column).
-__device__ __forceinline__ float2 geglu2(float2 a_half, float2 g) {
+__device__ __forceinline__ float2 geglu2(float2 a_half, float2 g, float2 ba_half, float2 bg) {
+  a_half = __fadd2_rn(a_half, ba_half);  // the GEGLU-in bias b1' (value half pre-scaled by 1/2), added here instead of by an MMA
+  g = __fadd2_rn(g, bg);
   const float2 g2 = __fmul2_rn(g, g);
   const float2 in = __fmul2_rn(g, __ffma2_rn(g2, f2s(0.034700932528f), f2s(0.800156991001f)));
   const float2 t = f2(tanh_approx(in.x), tanh_approx(in.y));
@@ -437,7 +471,13 @@ __device__ __forceinline__ void row_normalize_to_tile(uint32_t taddr, float mean
     }
   }
 }
-
+// LayerNorm of the row -> bf16 A-operand row.  (A one-pass form that keeps the row in 128 registers was measured slower: the phase
+// is bound by the ~190 FMA-pipe instructions per row, not by the TMEM round trips, and the registers pushed state to local memory.)
+__device__ __forceinline__ void row_layernorm_to_tile(uint32_t taddr, uint8_t* tile, int r) {
+  float mean, rstd;
+  row_stats(taddr, mean, rstd);
+  row_normalize_to_tile(taddr, mean, rstd, tile, r);
+}
 
 // D[128 x NB] (+)= A[128 x 16*KSTEPS] . B[NB x 16*KSTEPS]^T.  A tiles have 128 rows (k-slab = 2048 B), B tiles NB rows
 // (k-slab = NB*16 B).  Fully unrolled so that descriptors are (uniform base + immediate).
@@ -492,14 +532,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     uint8_t* a_tile = smem + SM_A + T * 32768;
     const bool tl_on = tid == 0;
     uint32_t ph_acc = 0, ph_acc_oth = 0, ph_x = 0;  // ph_acc_oth: BAR_ACC of the OTHER tile (FF phase works on both)
+    const bool upd = P.upd_sched != nullptr;
     int item_n = 0;
 #pragma unroll 1
     for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++item_n) {
     const int unit = (int)(idx % P.n_units), step_local = (int)(idx / P.n_units);
-    const int t_cur = P.t_first - step_local;
-    const long long tile_id0 = (long long)unit * 2;
-    const bool tile_ok = tile_id0 + T < n_tiles;
-    const long long tok = (tile_ok ? tile_id0 + T : n_tiles - 1) * 128 + r;
+    const int t_cur = P.step_t != nullptr ? __ldg(P.step_t + step_local) : P.t_first - step_local;
+    const long long tile_id = P.guidance ? (long long)unit : (long long)unit * 2 + T;  // guidance: both slots run the same tile
+    const bool tile_ok = tile_id < n_tiles;
+    const long long tok = (tile_ok ? tile_id : n_tiles - 1) * 128 + r;
     const long long b = tok / P.N;
     const int p = (int)(tok - b * P.N);
     uint32_t vmask = 0;  // bit j set = part token j is valid
@@ -515,10 +556,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       P.dbg[220] = (long long)ns;
     }
 #endif
+    // Per-token operands that do not change over the sampling steps are requested BEFORE the cross-step dependency wait.
+    float f[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f[3 + c] = __ldg(P.anchors + (b * 3 + c) * P.N + p);
+      const float v = __ldg(P.variances + (b * 3 + c) * P.N + p);
+      f[6 + c] = (P.flags & DFB200_NET_INCLUDE_STD) ? sqrtf(v) : v;
+    }
+    const int part = __ldg(P.assign + tok);
     if (P.done != nullptr) {
-      // x of this unit at this timestep is produced by the item (unit, previous step), possibly on another SM
+      // x of this unit at this step is produced by the item (unit, previous step), possibly on another SM
       if (r == 0) {
-        const int need = 2 * (P.upd_T - 1 - t_cur);
+        const int need = 2 * (P.step_base + step_local);
         int have;
         do {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(P.done + unit) : "memory");
@@ -534,15 +584,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     // ---- proj_in (13 -> 128) + pre_norm on the tensor core: analytic variance -> scaled K=32 A row -> one MMA into X ----
     {
       const float* cst = reinterpret_cast<const float*>(smem + SM_INHEAD + IH_CONST);
-      float f[9];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        f[c] = __ldcg(P.x + (b * 3 + c) * P.N + p);  // x is rewritten every step by other SMs: read through L2
-        f[3 + c] = __ldg(P.anchors + (b * 3 + c) * P.N + p);
-        const float v = __ldg(P.variances + (b * 3 + c) * P.N + p);
-        f[6 + c] = (P.flags & DFB200_NET_INCLUDE_STD) ? sqrtf(v) : v;
-      }
-      const int part = __ldg(P.assign + tok);
+      for (int c = 0; c < 3; ++c) f[c] = __ldcg(P.x + (b * 3 + c) * P.N + p);  // x is rewritten every step by other SMs: read through L2
       TL(0, 211);
       float var = cst[IHC_CP + part];
       {
@@ -592,15 +635,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     for (int l = 0; l < P.depth; ++l) {
       TL(0, 2 + l * 40);
       // ---- LN2 -> A ----
-      float mean, rstd;
-      row_stats(X, mean, rstd);
-      row_normalize_to_tile(X, mean, rstd, a_tile, r);
+      row_layernorm_to_tile(X, a_tile, r);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[BAR_A + T]);
       TL(0, 3 + l * 40);
 
-      // ---- folded cross-attention: logits S[(h,j)] arrive from the MMA; softmax over the 4 part tokens per head ----
+      // ---- folded cross-attention: logits S[(h,j)] (x log2 e) arrive from the MMA; softmax over the 4 part tokens per head ----
       mbar_wait(&bars[BAR_ACC + T], ph_acc);
       ph_acc ^= 1;
       tc_fence_after();
@@ -615,7 +656,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           float s0 = (vmask & 1u) ? sv[4 * h] : -FLT_MAX, s1 = (vmask & 2u) ? sv[4 * h + 1] : -FLT_MAX;  // masked_fill(~mask, -finfo.max)
           float s2 = (vmask & 4u) ? sv[4 * h + 2] : -FLT_MAX, s3 = (vmask & 8u) ? sv[4 * h + 3] : -FLT_MAX;
           const float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
-          s0 = __expf(s0 - mx); s1 = __expf(s1 - mx); s2 = __expf(s2 - mx); s3 = __expf(s3 - mx);
+          s0 = ex2_approx(s0 - mx); s1 = ex2_approx(s1 - mx); s2 = ex2_approx(s2 - mx); s3 = ex2_approx(s3 - mx);
           const float inv = __fdividef(1.f, (s0 + s1) + (s2 + s3));
           pw[2 * h] = pack_bf16(s0 * inv, s1 * inv);
           pw[2 * h + 1] = pack_bf16(s2 * inv, s3 * inv);
@@ -635,8 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       ph_x ^= 1;
       tc_fence_after();
       TL(0, 6 + l * 40);
-      row_stats(X, mean, rstd);
-      row_normalize_to_tile(X, mean, rstd, a_tile, r);
+      row_layernorm_to_tile(X, a_tile, r);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[BAR_A + T]);
@@ -652,8 +692,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       // which the MMA warp issued after both logits MMAs), and it must NOT be waited for here: the barrier may already be
       // two phases on (the other tile's H_0 does not depend on this thread), where a parity wait would never return.
       ph_acc_oth ^= 1;
+      const float4* b1p = reinterpret_cast<const float4*>(P.b1p + (size_t)l * B1P_FLOATS) + T * 8;  // this column half's biases
 #pragma unroll 1
       for (int c = 0; c < FF_CHUNKS; ++c) {
+        // the chunk's folded biases (uniform addresses, L2-resident), requested before the accumulator wait; both tiles use them
+        float ba[32], bg[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 va = __ldg(b1p + c * 32 + k), vg = __ldg(b1p + c * 32 + 16 + k);
+          ba[4 * k] = va.x; ba[4 * k + 1] = va.y; ba[4 * k + 2] = va.z; ba[4 * k + 3] = va.w;
+          bg[4 * k] = vg.x; bg[4 * k + 1] = vg.y; bg[4 * k + 2] = vg.z; bg[4 * k + 3] = vg.w;
+        }
 #pragma unroll
         for (int TT = 0; TT < 2; ++TT) {
           const uint32_t ACCt = lane_base + 256 + TT * 128 + T * 32;
@@ -668,7 +717,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           uint32_t u[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float2 y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]));
+            const float2 y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]), f2(ba[2 * k], ba[2 * k + 1]),
+                                    f2(bg[2 * k], bg[2 * k + 1]));
             u[k] = pack_bf16(y.x, y.y);
           }
           tmem_st16(ACCt, u);
@@ -686,16 +736,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     TL(0, 2 + P.depth * 40);
     // ---- post_norm (folded) + proj_out (128 -> 3) on the tensor core (N = 16 MMA, 3 live columns) ----
     {
-      float mean, rstd;
-      row_stats(X, mean, rstd);
       TL(0, 204);
-      row_normalize_to_tile(X, mean, rstd, a_tile, r);
+      row_layernorm_to_tile(X, a_tile, r);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[BAR_A + T]);
       ph_acc_oth ^= 1;  // the other tile's head phase of BAR_ACC (never waited for here; see the FF loop)
-      // While the head MMA runs: everything of the anchored DDPM update that does not depend on eps (operand loads, noise).
-      const bool upd = P.upd_sched != nullptr;
+      // While the head MMA runs: everything of the update that does not depend on eps (operand loads, noise).
       StepCoef cf{};
       float xv[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f}, zq[3] = {0.f, 0.f, 0.f};
       if (upd) {
@@ -730,24 +777,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       float ev[16];
       tmem_ld16(ACC, ev);
       tmem_wait_ld();
-      const float eps3[3] = {ev[0], ev[1], ev[2]};
+      float eps3[3] = {ev[0], ev[1], ev[2]};
       TL(0, 205);
-      if (tile_ok && P.eps_out != nullptr) {
+      if (P.guidance) {
+        // slot 1 (unconditional pass) hands its eps to slot 0 through its A tile (the head MMA has finished reading it)
+        float* xch = reinterpret_cast<float*>(smem + SM_A + 32768);
+        if (T == 1) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) xch[c * 128 + r] = eps3[c];
+        }
+        named_bar_sync(3, 256);
+        if (T == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) eps3[c] = __fadd_rn(__fmul_rn(1.f - P.guid_w, xch[c * 128 + r]), __fmul_rn(P.guid_w, eps3[c]));
+        }
+        named_bar_sync(3, 256);  // slot 1 must not start its next item's A row before slot 0 has read the exchange
+      }
+      const bool writer = tile_ok && (!P.guidance || T == 0);
+      if (writer && P.eps_out != nullptr) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) P.eps_out[(b * 3 + c) * P.N + p] = eps3[c];
       }
       if (upd) {
-        // anchored DDPM update fused into the epilogue (same arithmetic as dfb200_ddpm_step; every sample shares t)
+        // anchored DDPM (or DDIM) update fused into the epilogue (same arithmetic as dfb200_ddpm_step / dfb200_ddim_step; every
+        // sample shares t); x, anchors, variances and the noise are already in registers
         const bool keep = P.traj != nullptr && t_cur > 0 && t_cur % P.traj_interval == 0;
         float* tr = keep ? P.traj + (size_t)(t_cur / P.traj_interval - 1) * (size_t)P.M * 3 : nullptr;
+        float* ss = P.step_sample != nullptr ? P.step_sample + (size_t)step_local * (size_t)P.M * 3 : nullptr;
+        float* sx = P.step_xstart != nullptr ? P.step_xstart + (size_t)step_local * (size_t)P.M * 3 : nullptr;
+        float acp_s = 0.f, dir_c = 0.f;
+        if (P.ddim_acp != nullptr) {
+          acp_s = __fsqrt_rn(__ldg(P.ddim_acp + t_cur));
+          dir_c = __ldg(P.ddim_dir + t_cur);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const long long e = (b * 3 + c) * P.N + p;
           const float x0 = ddpm_xstart(cf, xv[c], av[c], vv[c], eps3[c]);
-          const float xp = ddpm_prev(cf, xv[c], av[c], vv[c], x0, zq[c]);
-          if (tile_ok) {
+          const float xp = P.ddim_acp != nullptr ? ddim_prev(cf, av[c], vv[c], x0, eps3[c], zq[c], acp_s, dir_c, P.ddim_eta)
+                                                 : ddpm_prev(cf, xv[c], av[c], vv[c], x0, zq[c]);
+          if (writer) {
             P.x_out[e] = xp;
             if (keep) tr[e] = xp;
+            if (ss != nullptr) ss[e] = xp;
+            if (sx != nullptr) sx[e] = x0;
           }
         }
       }
@@ -755,8 +828,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     TL(0, 206);
     if (P.done != nullptr) {
       named_bar_sync(1 + T, 128);      // all 128 rows of the tile have stored x_{t-1} (CTA-scope order) ...
-      if (r == 0)                      // ... and ONE gpu-scope release publishes the tile-step (cumulative over the barrier)
-        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(P.done + unit), "r"(1) : "memory");
+      if (r == 0 && (!P.guidance || T == 0))  // ... and ONE gpu-scope release publishes the tile-step (cumulative over the barrier)
+        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(P.done + unit), "r"(P.guidance ? 2 : 1) : "memory");
     }
     TL(0, 3 + P.depth * 40);
 #ifdef DFB200_DIAGNOSTICS
@@ -792,12 +865,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
       if (T == 0) { mbar_wait(&bars[BAR_UREADY + 0], ph_u0); ph_u0 ^= 1; }
       else { mbar_wait(&bars[BAR_UREADY + 1], ph_u1); ph_u1 ^= 1; }
     };
-    // H_c(T) = LN3(x_T) W1'_c^T + b1'_c -> ACC_T (128 columns: 64 value | 64 gate)
+    // H_c(T) = LN3(x_T) W1'_c^T -> ACC_T (128 columns: 64 value | 64 gate); the bias b1'_c is added by the GEGLU epilogue
     auto ff_in = [&](int T, uint32_t pa, uint32_t pb) {
       const uint32_t d = 256 + T * 128, at = a_base + T * 32768;
       umma_gemm<128, 4>(d, at, pa, idesc128, 0u);
       umma_gemm<128, 4>(d, at + 4 * 4096, pb, idesc128, 1u);
-      umma_bf16(d, ones_desc, make_smem_desc(pa + SLAB_OFF, 0, TILE_SBO), idesc128, 1u);
       umma_commit(&bars[BAR_ACC + T]);
     };
     int item_n = 0;
@@ -922,9 +994,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
 #pragma unroll 1
     for (long long idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
       const int unit = (int)(idx % P.n_units), step_local = (int)(idx / P.n_units);
-      const long long tile_id0 = (long long)unit * 2;
-      const long long t0 = tile_id0 < n_tiles ? tile_id0 : n_tiles - 1, t1 = tile_id0 + 1 < n_tiles ? tile_id0 + 1 : n_tiles - 1;
-      const long long b0 = t0 * 128 / P.N, b1 = t1 * 128 / P.N;
+      const long long tile_id0 = P.guidance ? (long long)unit : (long long)unit * 2, tile_id1 = P.guidance ? (long long)unit : tile_id0 + 1;
+      const long long t0 = tile_id0 < n_tiles ? tile_id0 : n_tiles - 1, t1 = tile_id1 < n_tiles ? tile_id1 : n_tiles - 1;
+      const long long b0 = t0 * 128 / P.N, b1 = t1 * 128 / P.N + (P.guidance ? P.B : 0);
       const uint8_t* fold = P.fold + (size_t)step_local * P.fold_step_bytes;
       for (int lp = 0; lp < P.depth * PKT_PER_LAYER; ++lp, ++G) {
         const int slot = G % NSLOT;
@@ -959,9 +1031,9 @@ static const float* tc_extras(const PackLayout& L, const void* packed) {
 }
 
 int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time, int t_first,
-                        int steps, void* fold, cudaStream_t st) {
+                        const int* step_t, int steps, void* fold, cudaStream_t st) {
   if (B == 0 || steps == 0) return DFB200_OK;
-  context_fold_kernel<<<dim3(B, L.d.depth, steps), 256, 0, st>>>(L.d.depth, kv_static, kv_time, t_first, tc_extras(L, packed),
+  context_fold_kernel<<<dim3(B, L.d.depth, steps), 256, 0, st>>>(L.d.depth, kv_static, kv_time, t_first, step_t, tc_extras(L, packed),
                                                                   reinterpret_cast<uint8_t*>(fold));
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
@@ -978,6 +1050,7 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   p.stream = reinterpret_cast<const uint8_t*>(packed) + L.tc_stream_off;
   p.fold = reinterpret_cast<const uint8_t*>(fold);
   p.inhead = reinterpret_cast<const uint8_t*>(tc_extras(L, packed));
+  p.b1p = tc_extras(L, packed) + HEAD_FLOATS + (size_t)L.d.depth * FOLDW_FLOATS;
   p.x = x; p.anchors = anchors; p.variances = variances; p.assign = assign; p.valid = valid_id;
   p.eps_out = eps_out;
   p.N = N; p.depth = L.d.depth; p.flags = L.d.flags;
@@ -986,13 +1059,20 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
   p.dbg = g_tc_timeline;
   p.dbg_item = g_tc_timeline_item;
 #endif
-  p.n_units = cdiv(p.M, 256);
+  p.B = B;
+  p.guidance = upd != nullptr && upd->guidance;
+  p.guid_w = upd != nullptr ? upd->guid_w : 0.f;
+  p.n_units = p.guidance ? (int)(p.M / 128) : cdiv(p.M, 256);
   p.n_steps = 1;
   p.t_first = 0;
   if (upd != nullptr) {
     p.upd_sched = upd->sched; p.upd_T = upd->T; p.t_first = upd->t; p.upd_noise = upd->noise; p.upd_seed = upd->seed; p.x_out = upd->x_out;
     p.n_steps = upd->n_steps; p.fold_step_bytes = upd->fold_step_bytes; p.noise_step_elems = (size_t)p.M * 3;
     p.done = upd->done; p.traj = upd->traj; p.traj_interval = upd->traj_interval;
+    p.step_t = upd->step_t; p.step_base = upd->step_base;
+    p.step_sample = upd->step_sample; p.step_xstart = upd->step_xstart;
+    p.ddim_acp = upd->ddim_acp; p.ddim_dir = upd->ddim_dir; p.ddim_eta = upd->ddim_eta;
+    DFB_REQUIRE(p.n_steps == 1 || p.done != nullptr, DFB200_ERR_INVALID_ARG, "denoiser (bf16 mode): multi-step launch without dependency counters");
   }
   // the spin-wait on P.done assumes every CTA of the grid is resident: size it by the LAUNCHING device's SM count
   const int n_sm = current_device_sm_count();
@@ -1009,7 +1089,7 @@ int denoiser_forward_tc(const PackLayout& L, const void* packed, int B, int N, c
                         const float* variances, const int* assign, const float* valid_id, float* eps_out, Workspace& ws,
                         cudaStream_t st) {
   // K/V (ws.kv, from launch_context_kv) -> per-(sample, block) folded attention tiles -> fused kernel
-  int rc = launch_context_fold(L, packed, B, ws.kv, nullptr, 0, 1, ws.fold, st);
+  int rc = launch_context_fold(L, packed, B, ws.kv, nullptr, 0, nullptr, 1, ws.fold, st);
   if (rc != DFB200_OK) return rc;
   return denoiser_step_tc(L, packed, B, N, x, anchors, variances, assign, valid_id, ws.fold, eps_out, nullptr, st);
 }

@@ -206,11 +206,62 @@ class AnchoredDiffusion(Module):
                                                    ptr(pred_xstart), stream()))
         return {"sample": sample, "pred_xstart": pred_xstart}
 
+    # ---- the fused loop (dfb200_sample_loop) -------------------------------------------------
+    def _fused_ok(self):
+        return not (self.use_beta or self.rescale_timesteps)  # the fused loop feeds the raw integer timestep to the net
+
+    def _loop_state(self, B, N, anchors, ctx, variance, anchor_assignment, valid_id, device):
+        """Everything one reverse process needs on the device, built once: operands, step list, tables, workspace."""
+        anchors, variance = self._prep(anchors, variance)
+        assert variance.shape == anchors.shape == (B, 3, N)
+        if isinstance(ctx, (list, tuple)):
+            ctx = torch.cat(list(ctx), dim=1)
+        net, lib = self.model, _lib.load()
+        st = dict(anchors=anchors, variance=variance, ctx=ctx.to(torch.float32).contiguous(),
+                  assign=anchor_assignment.to(torch.int32).contiguous(),
+                  valid=None if valid_id is None else valid_id.to(torch.float32).contiguous(),
+                  cfg=net.c_cfg(), mode=net.mode(), packed=net.packed_weights(), sched=self._sched(device))
+        steps = [int(i) for i in self.steps[::-1]]
+        st["steps"] = steps
+        strided = steps != list(range(self.num_timesteps - 1, -1, -1))
+        st["steps_host"] = (_lib.c_int * len(steps))(*steps) if strided else None
+        st["steps_dev"] = torch.tensor(steps, dtype=torch.int32, device=device) if strided else None
+        st["ddim"] = self._ddim_tables(device) if self.ddim_sampling else None
+        nws = lib.dfb200_ddpm_sample_loop_workspace_bytes(st["cfg"], st["mode"], B, N, self.num_timesteps)
+        st["ws"], st["nws"] = torch.empty(nws, dtype=torch.uint8, device=device), nws
+        st["chunk"] = max(1, lib.dfb200_sample_loop_chunk(st["cfg"], st["mode"], B, N, self.num_timesteps))
+        return st
+
+    def _run_steps(self, st, B, N, x, from_noise, first, count, noise, seed, traj, traj_interval, step_sample=None, step_xstart=None):
+        o = _lib.SampleOpts()
+        if st["steps_dev"] is not None:
+            o.timesteps, o.timesteps_host, o.n_timesteps = st["steps_dev"].data_ptr(), st["steps_host"], len(st["steps"])
+        o.first_step, o.num_steps, o.tables_ready = first, count, int(first > 0)
+        if st["ddim"] is not None:
+            o.ddim, o.ddim_eta = 1, float(self.ddim_eta)
+            o.alphas_cumprod_prev, o.xt_dir_coeff = st["ddim"][0].data_ptr(), st["ddim"][1].data_ptr()
+        o.guidance, o.classifier_weight = int(bool(self.guidance)), float(self.classifier_weight)
+        o.step_sample = None if step_sample is None else step_sample.data_ptr()
+        o.step_xstart = None if step_xstart is None else step_xstart.data_ptr()
+        with _lib.on(x.device):
+            check(_lib.load().dfb200_sample_loop(st["cfg"], ptr(st["packed"]), st["mode"], B, N, self.num_timesteps, ptr(st["sched"]),
+                                                 ptr(x), from_noise, ptr(st["ctx"]), ptr(st["anchors"]), ptr(st["variance"]),
+                                                 ptr(st["assign"]), ptr(st["valid"]), ptr(noise), int(seed), ptr(traj),
+                                                 int(traj_interval or 1), o, ptr(st["ws"]), st["nws"], stream()))
+
     def p_sample_loop_progressive(self, shape, anchors, ctx=None, variance=None, anchor_assignment=None, valid_id=None,
-                                  noise=None, device=None, progress=False):
+                                  noise=None, device=None, progress=False, fused=True, chunk=None):
         """Generator protocol of the reference (:528-588): yields (T, {'sample': x_T}) first, then
-        (i, {'sample', 'pred_xstart'}) for i = T-1 .. 0.  Every yielded tensor is a fresh buffer
-        (callers such as AnchorDiffAE.decode keep views of them)."""
+        (i, {'sample', 'pred_xstart'}) for i = T-1 .. 0 (or the DDIM step list).  Every yielded tensor is a buffer that is
+        never written again (callers such as AnchorDiffAE.decode keep views of them).
+
+        The steps are served from the FUSED loop, one persistent-kernel launch per chunk of steps (24 at the BASELINE size):
+        the kernel stores `sample` and `pred_xstart` of every step of the chunk into fresh buffers that the generator then
+        hands out one by one, so a caller that iterates the generator runs at the speed of `p_sample_loop` instead of
+        paying ~10 launches per step.  torch's generator is consumed exactly as by the reference (x_T first, then one
+        randn per step incl. t=0); a consumer that stops early has computed at most one chunk more than it used.
+        `fused=False` (or use_beta / rescale_timesteps) steps through `p_sample` as the reference does; `chunk` overrides the
+        number of steps per launch (default: dfb200_sample_loop_chunk, 37 at the BASELINE size)."""
         if device is None:
             device = next(self.model.parameters()).device
         assert isinstance(shape, (tuple, list))
@@ -224,46 +275,51 @@ class AnchoredDiffusion(Module):
             from tqdm.auto import tqdm
             indices = tqdm(indices)
         yield self.num_timesteps, dict(sample=pcd)
-        for i in indices:
-            t = torch.full((shape[0],), i, dtype=torch.long, device=device)
-            with torch.no_grad():
-                out = self.p_sample(pcd, t, anchors, ctx=ctx, variance=variance, anchor_assignment=anchor_assignment,
-                                    valid_id=valid_id)
-                yield i, out
-                pcd = out["sample"]
+        if not (fused and self._fused_ok() and pcd.is_cuda):
+            for i in indices:
+                t = torch.full((shape[0],), i, dtype=torch.long, device=device)
+                with torch.no_grad():
+                    out = self.p_sample(pcd, t, anchors, ctx=ctx, variance=variance, anchor_assignment=anchor_assignment,
+                                        valid_id=valid_id)
+                    yield i, out
+                    pcd = out["sample"]
+            return
+        B, C, N = shape
+        with torch.no_grad():
+            st = self._loop_state(B, N, anchors, ctx, variance, anchor_assignment, valid_id, pcd.device)
+            x = pcd.to(torch.float32).contiguous().clone()  # running state; the yielded x_T stays untouched
+            steps, chunk = st["steps"], int(chunk or st["chunk"])
+            it = iter(indices)
+            for k0 in range(0, len(steps), chunk):
+                n = min(chunk, len(steps) - k0)
+                z = torch.empty(n, B, C, N, device=pcd.device)
+                for k in range(n):  # one draw per step, as p_sample's torch.randn_like (:476)
+                    torch.randn(B, C, N, device=pcd.device, out=z[k])
+                out = torch.empty(2, n, B, C, N, device=pcd.device)  # fresh per chunk: yielded views are never overwritten
+                self._run_steps(st, B, N, x, 0, k0, n, z, 0, None, None, step_sample=out[0], step_xstart=out[1])
+                for k in range(n):
+                    yield next(it), dict(sample=out[0, k], pred_xstart=out[1, k])
 
     @torch.no_grad()
     def p_sample_loop(self, shape, anchors, ctx=None, noise=None, variance=None, anchor_assignment=None, valid_id=None,
                       device=None, progress=False, rng="torch", seed=0, traj_interval=None):
-        """Whole reverse process in ONE C call (dfb200_ddpm_sample_loop); returns x_0 (B,3,N)
-        (reference p_sample_loop :486-526), or (x_0, traj) when traj_interval is given.
+        """Whole reverse process in ONE C call (dfb200_sample_loop); returns x_0 (B,3,N)
+        (reference p_sample_loop :486-526), or (x_0, traj) when traj_interval is given: traj[s] is the sample at
+        t = (s+1)*traj_interval (x_T itself when that equals T), the keys AnchorDiffAE.decode keeps under ret_traj.
+        DDIM step lists and classifier-free guidance run inside the same fused kernel.
           rng="torch":  noise drawn up front with torch.randn in the reference's call order
                         (x_T first unless `noise` supplies it, then one draw per step)
           rng="philox": noise generated inside the kernels from `seed` (no HBM noise traffic)."""
         if device is None:
             device = next(self.model.parameters()).device
+        device = torch.device(device)
         B, C, N = shape
         T = self.num_timesteps
-        if self.ddim_sampling or self.guidance:
-            # DDIM (a few strided steps) / guidance (two denoiser passes per step): stepwise kernels, no generator overhead
-            assert rng == "torch" and not traj_interval, "DDIM/guidance sampling draws its noise with torch and keeps no trajectory"
-            x = noise if noise is not None else torch.sqrt(variance) * torch.randn(B, C, N, device=device) + anchors
-            for i in self.steps[::-1]:
-                t = torch.full((B,), i, dtype=torch.long, device=device)
-                x = self.p_sample(x, t, anchors, ctx=ctx, variance=variance, anchor_assignment=anchor_assignment,
-                                  valid_id=valid_id)["sample"]
-            return x
-        anchors, variance = self._prep(anchors, variance)
-        assert variance.shape == anchors.shape == (B, C, N)
-        if isinstance(ctx, (list, tuple)):
-            ctx = torch.cat(list(ctx), dim=1)
-        ctx = ctx.to(torch.float32).contiguous()
-        net = self.model
-        assign = anchor_assignment.to(torch.int32).contiguous()
-        valid = None if valid_id is None else valid_id.to(torch.float32).contiguous()
-        if self.use_beta or self.rescale_timesteps:
+        if not self._fused_ok():
             raise NotImplementedError("fused sample loop feeds the raw integer timestep to the net (use_beta=False, "
                                       "rescale_timesteps=False); use p_sample_loop_progressive")
+        st = self._loop_state(B, N, anchors, ctx, variance, anchor_assignment, valid_id, device)
+        n_steps = len(st["steps"])
         step_noise = None
         if noise is not None:
             x, from_noise = noise.to(torch.float32).contiguous().clone(), 0
@@ -272,23 +328,21 @@ class AnchoredDiffusion(Module):
         else:
             x, from_noise = torch.empty(B, C, N, device=device), 2
         if rng == "torch":
-            step_noise = torch.empty(T, B, C, N, device=device)
-            for k in range(T):
+            step_noise = torch.empty(n_steps, B, C, N, device=device)
+            for k in range(n_steps):
                 torch.randn(B, C, N, device=device, out=step_noise[k])
-        lib = _lib.load()
-        cfg, mode = net.c_cfg(), net.mode()
-        packed = net.packed_weights()
-        nws = lib.dfb200_ddpm_sample_loop_workspace_bytes(cfg, mode, B, N, T)
-        ws = torch.empty(nws, dtype=torch.uint8, device=device)
         traj = None
         if traj_interval:
-            traj = torch.empty(max((T - 1) // traj_interval, 0), B, C, N, device=device)
-        with _lib.on(device):
-            check(lib.dfb200_ddpm_sample_loop(cfg, ptr(packed), mode, B, N, T, ptr(self._sched(device)), ptr(x), from_noise,
-                                              ptr(ctx), ptr(anchors), ptr(variance), ptr(assign), ptr(valid),
-                                              ptr(step_noise), int(seed), ptr(traj), int(traj_interval or 1), ptr(ws), nws,
-                                              stream()))
+            traj = torch.empty(T // traj_interval, B, C, N, device=device)
+        self._run_steps(st, B, N, x, from_noise, 0, n_steps, step_noise, seed, traj, traj_interval)
         return (x, traj) if traj_interval else x
+
+    def traj_keys(self, traj_interval):
+        """Timesteps whose slot of `p_sample_loop(..., traj_interval=)`'s trajectory is filled, with the slot index: the t > 0
+        of the step list with t % interval == 0, plus T itself (x_T) when T % interval == 0 (anchor_gen.py:164-165)."""
+        T = self.num_timesteps
+        ts = sorted({int(t) for t in self.steps if t > 0 and t % traj_interval == 0} | ({T} if T % traj_interval == 0 else set()))
+        return [(t, t // traj_interval - 1) for t in ts]
 
     def forward(self, x_start, t, **kw):
         """nn.Module entry (used under DistributedDataParallel): the training loss dict."""

@@ -90,9 +90,9 @@ class Runner:
                                                traj_interval=self.ret_interval if self.ret_traj else None)
             x0, traj = out if self.ret_traj else (out, None)
             res = {"pred": gather_shapes(x0.transpose(1, 2).contiguous(), B)}  # (B,N,3), as AnchorDiffAE.decode returns
-            if traj is not None:
-                for s in range(traj.shape[0]):
-                    res[(s + 1) * self.ret_interval] = gather_shapes(traj[s].transpose(1, 2).contiguous(), B)
+            if traj is not None:  # the keys AnchorDiffAE.decode keeps (anchor_gen.py:160-167), x_T under T included
+                for t_key, slot in self.diffusion.traj_keys(self.ret_interval):
+                    res[t_key] = gather_shapes(traj[slot].transpose(1, 2).contiguous(), B)
             results.append({k: v.cpu().numpy() for k, v in res.items()})
         torch.cuda.synchronize(self.device)
         if self.rank == 0:
@@ -116,17 +116,26 @@ class Runner:
         torch.manual_seed(self.seed + self.rank)
         results = dict(pred=[], seg_mask_ref=[])
         npoints = int(self.cfg.model.npoints or 2048)
-        for bi in range(max(1, num_gen // B)):
-            valid_id = valid_ids[torch.multinomial(probs, B, replacement=True).to(self.device)]
-            ctx, mean_pp, logvar_pp, seg, vid, _ = self.encoder.sample_latents(B, npoints, self.device, fixed_id=torch.zeros(4, device=self.device),
+        # the num_gen shapes are sharded over the ranks (contiguous, balanced), generated in batches of <= B, gathered once
+        lo, hi = shard_range(num_gen, self.rank, self.world)
+        from .models.encoders.part_encoders import _exp_shift
+        for bi, b0 in enumerate(range(lo, hi, B)):
+            nb = min(B, hi - b0)
+            valid_id = valid_ids[torch.multinomial(probs, nb, replacement=True).to(self.device)]
+            ctx, mean_pp, logvar_pp, seg, vid, _ = self.encoder.sample_latents(nb, npoints, self.device, fixed_id=torch.zeros(4, device=self.device),
                                                                               valid_id=valid_id, K=param_sample_num)
-            from .models.encoders.part_encoders import _exp_shift
             variance = _exp_shift(logvar_pp)
             x0 = self.diffusion.p_sample_loop(list(mean_pp.shape), mean_pp, ctx=ctx, variance=variance, anchor_assignment=seg, valid_id=vid,
                                               rng=rng, seed=rank_seed(self.seed * 7919 + bi, self.rank, self.world))
-            results["pred"].append(x0.transpose(1, 2).contiguous().cpu().numpy())
-            results["seg_mask_ref"].append(seg.cpu().numpy())
-        results = {k: np.concatenate(v, axis=0) for k, v in results.items()}
+            results["pred"].append(x0.transpose(1, 2).contiguous())
+            results["seg_mask_ref"].append(seg)
+        n_local = (hi - lo) * param_sample_num
+        pred = torch.cat(results["pred"], dim=0) if results["pred"] else torch.empty(0, npoints, 3, device=self.device)
+        seg = torch.cat(results["seg_mask_ref"], dim=0) if results["seg_mask_ref"] else torch.empty(0, npoints, dtype=torch.int32, device=self.device)
+        assert pred.shape[0] == n_local
+        if self.world > 1 and param_sample_num == 1:
+            pred, seg = gather_shapes(pred, num_gen), gather_shapes(seg.int(), num_gen)
+        results = {"pred": pred.cpu().numpy(), "seg_mask_ref": seg.cpu().numpy()}
         if self.rank == 0:
             os.makedirs(os.path.join(self.work_dir, "val"), exist_ok=True)
             path = os.path.join(self.work_dir, "val", "gen_fixed0000.npz")

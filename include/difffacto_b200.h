@@ -306,7 +306,7 @@ int dfb200_coupling_reverse(int B, int d, const float* s_t, float* target, int l
 int dfb200_token_attention(int Bt, int n_tok, int heads, int d_head, const float* q, const float* k, const float* v,
                            const float* valid, float* out, dfb200_stream_t stream);
 
-/* Scratch bytes for dfb200_ddpm_sample_loop. */
+/* Scratch bytes for dfb200_ddpm_sample_loop / dfb200_sample_loop (one size serves every option set). */
 size_t dfb200_ddpm_sample_loop_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B,
                                                int N, int T);
 /* Full reverse process x_T -> x_0 for a batch: T x (denoiser + fused eps->x_{t-1} update).
@@ -315,9 +315,10 @@ size_t dfb200_ddpm_sample_loop_workspace_bytes(const dfb200_denoiser_cfg* cfg, i
  *                Philox(seed) draw number T); out: x_0.
  *   noise      : (T,B,3,N) per-step N(0,1) noise, index [T-1-i] for step i counting down from
  *                T-1 (step order of the loop), or NULL to use Philox(seed).
- *   traj       : optional (n_traj,B,3,N) buffer; x after step t is stored for every t>0 with
- *                t % traj_interval == 0 at slot t/traj_interval - 1 (AnchorDiffAE.decode's
- *                ret_traj/ret_interval, python/difffacto/models/networks/anchor_gen.py:160-167).
+ *   traj       : optional (T / traj_interval, B,3,N) buffer; x after step t is stored for every t>0 with
+ *                t % traj_interval == 0 at slot t/traj_interval - 1, and x_T itself in the last slot when
+ *                T % traj_interval == 0 (AnchorDiffAE.decode's ret_traj/ret_interval keys, T included,
+ *                python/difffacto/models/networks/anchor_gen.py:160-167).
  * Replaces AnchoredDiffusion.p_sample_loop_progressive, anchored_diffusion.py:528-588. */
 int dfb200_ddpm_sample_loop(const dfb200_denoiser_cfg* cfg, const void* packed, int mode, int B,
                             int N, int T, const float* sched, float* x, int x_T_from_noise,
@@ -325,6 +326,43 @@ int dfb200_ddpm_sample_loop(const dfb200_denoiser_cfg* cfg, const void* packed, 
                             const int* anchor_assignment, const float* valid_id,
                             const float* noise, uint64_t seed, float* traj, int traj_interval,
                             void* workspace, size_t workspace_bytes, dfb200_stream_t stream);
+
+/* Variants of the loop, all inside the same persistent fused kernel in bf16 mode (all-zero / NULL = the call above):
+ *   timesteps      strided step lists (DDIM, anchored_diffusion.py:114-126): DEVICE int32[n_timesteps], strictly
+ *                  decreasing, execution order, plus the same values on the HOST (the launch sequence is host-driven);
+ *   first_step /   run only steps [first_step, first_step + num_steps) of the list (num_steps 0 = to the end): a caller
+ *   num_steps      that consumes the loop as a generator (AnchorDiffAE.decode over p_sample_loop_progressive) asks for
+ *                  it chunk by chunk; `noise`, `step_sample`, `step_xstart` then index from this call's first step.
+ *                  The x_T initialisation, the trajectory's x_T slot and the loop tables belong to the call with
+ *                  first_step == 0; later calls on the SAME workspace set tables_ready = 1;
+ *   ddim           the DDIM update (:368-374, :480-481) with eta and the two float32[T] DEVICE tables
+ *                  float32(alphas_cumprod_prev), float32(sqrt(1 - ac - eta^2 posterior_variance));
+ *   guidance       classifier-free guidance (:263-266): a second, zero-context denoiser pass per step,
+ *                  eps = (1 - w) eps_uncond + w eps_cond;
+ *   step_sample /  optional (num_steps,B,3,N) outputs: `sample` and `pred_xstart` of EVERY executed step (the dict the
+ *   step_xstart    reference's generator yields, :587). */
+typedef struct dfb200_sample_opts {
+  const int* timesteps;
+  const int* timesteps_host;
+  int n_timesteps;
+  int first_step, num_steps, tables_ready;
+  int ddim;
+  float ddim_eta;
+  const float* alphas_cumprod_prev;
+  const float* xt_dir_coeff;
+  int guidance;
+  float classifier_weight;
+  float* step_sample;
+  float* step_xstart;
+} dfb200_sample_opts;
+/* Steps one persistent launch of the fused kernel covers for these sizes: the natural num_steps of a chunked caller. */
+int dfb200_sample_loop_chunk(const dfb200_denoiser_cfg* cfg, int mode, int B, int N, int T);
+int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* packed, int mode, int B, int N, int T,
+                       const float* sched, float* x, int x_T_from_noise, const float* ctx, const float* anchors,
+                       const float* variance, const int* anchor_assignment, const float* valid_id,
+                       const float* noise, uint64_t seed, float* traj, int traj_interval,
+                       const dfb200_sample_opts* opts, void* workspace, size_t workspace_bytes,
+                       dfb200_stream_t stream);
 
 #ifdef __cplusplus
 }

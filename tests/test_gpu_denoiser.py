@@ -158,7 +158,7 @@ def test_fused_sample_loop_matches_stepwise_and_reference(golden, precision):
     cfg, mode = d.model.c_cfg(), d.model.mode()
     nws = lib.dfb200_ddpm_sample_loop_workspace_bytes(cfg, mode, 2, 128, 6)
     ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
-    traj = torch.empty(2, 2, 3, 128, device="cuda")
+    traj = torch.empty(3, 2, 3, 128, device="cuda")  # T // interval slots: t = 2, 4 and x_T itself (6 % 2 == 0)
     cc = torch.cat(ctx, 1).contiguous()
     step_noise = noises[1:].contiguous()
     _lib.check(lib.dfb200_ddpm_sample_loop(cfg, _lib.ptr(d.model.packed_weights()), mode, 2, 128, 6, _lib.ptr(d._sched(x.device)),
@@ -170,6 +170,7 @@ def test_fused_sample_loop_matches_stepwise_and_reference(golden, precision):
     # traj slots: t=2 -> slot 0, t=4 -> slot 1 (x after step t)
     assert np.abs(traj[0].cpu().numpy() - golden["loop_samples"][6 - 2]).max() < tol
     assert np.abs(traj[1].cpu().numpy() - golden["loop_samples"][6 - 4]).max() < tol
+    assert np.abs(traj[2].cpu().numpy() - golden["loop_samples"][0]).max() < 1e-5  # x_T, kept under key T by decode (anchor_gen.py:164)
 
 
 def test_philox_loop_equals_explicit_noise_loop():
@@ -316,7 +317,7 @@ def test_bf16_fused_loop_odd_shapes_track_the_stepwise_fp32_path(B, N, T):
                               valid_id=i["valid"], rng="philox", seed=seed, traj_interval=2)
     d32 = build(T, "fp32")
     x = torch.sqrt(i["variance"]) * draws[T] + i["anchors"]
-    kept = {}
+    kept = {T: x}
     for step in range(T - 1, -1, -1):
         tt = torch.full((B,), step, dtype=torch.long, device="cuda")
         x = d32.p_sample(x, tt, i["anchors"], ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"],

@@ -6,7 +6,8 @@ import torch
 import bench
 from difffacto_b200 import _lib
 from oracle import denoiser_ref as R
-d = bench.build_model(30, "bf16").cuda().eval()
+TLEN = int(sys.argv[2]) if len(sys.argv) > 2 else 30   # length of the sampling loop the item is taken from
+d = bench.build_model(TLEN, "bf16").cuda().eval()
 inp = R.synthetic_inputs(5, 32, 2048, False)
 i = {k: v.cuda() for k, v in inp.items()}
 f = lambda: d.model(i["x"], i["t"], [i["code"], i["params"]], anchors=i["anchors"].transpose(1, 2),
