@@ -29,7 +29,7 @@ class SampleOpts(ctypes.Structure):
 
 
 NET_CLASS_COND, NET_CAT_PARAMS_TO_X, NET_CAT_CLASS_TO_X, NET_MASK_UNREFERENCED, NET_INCLUDE_STD = 1, 2, 4, 8, 16
-MODE_FP32, MODE_BF16 = 0, 1
+MODE_FP32, MODE_BF16, MODE_TF32 = 0, 1, 2
 SCHED_ROWS = 8
 P = c_void_p
 _CFG = ctypes.POINTER(DenoiserCfg)

@@ -37,6 +37,8 @@ struct PackLayout {
   size_t fp32_floats;    // end of the fp32 region
   size_t tc_stream_off;  // byte offset of the bf16 packet stream (16 B aligned)
   size_t tc_stream_bytes;
+  size_t tf32_stream_off;  // byte offset of the tf32 packet stream (denoiser_tf32.cu)
+  size_t tf32_stream_bytes;
   size_t total_bytes;
 };
 
@@ -92,6 +94,12 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
 int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time,
                         int t_first, const int* step_t, int steps, void* fold, cudaStream_t st);
 size_t tc_fold_bytes_for(const NetDims& d, int B);
+
+// DFB200_MODE_TF32 (denoiser_tf32.cu): kind::tf32 tensor-core path at reference tolerance; ws.kv must hold the K/V of this call
+int denoiser_forward_tf32(const PackLayout& L, const void* packed, int B, int N, const float* x, const float* anchors,
+                          const float* variances, const int* assign, const float* valid_id, float* eps_out, Workspace& ws,
+                          cudaStream_t st);
+size_t tf32_fold_bytes_for(const NetDims& d, int B);
 
 int denoiser_forward_fp32(const PackLayout& L, const float* packed, int B, int N, const float* x,
                           const float* anchors, const float* variances, const int* assign,

@@ -58,7 +58,9 @@ size_t param_numel(const NetDims& d, bool global, int which) {
   return 0;
 }
 
-size_t tc_stream_bytes_for(const NetDims& d);  // denoiser_tc.cu
+size_t tc_stream_bytes_for(const NetDims& d);    // denoiser_tc.cu
+size_t tf32_stream_bytes_for(const NetDims& d);  // denoiser_tf32.cu
+int tf32_pack_stream(const PackLayout& L, void* packed, cudaStream_t st);
 
 int make_pack_layout(const dfb200_denoiser_cfg* cfg, PackLayout* L) {
   int rc = make_net_dims(cfg, &L->d);
@@ -72,7 +74,9 @@ int make_pack_layout(const dfb200_denoiser_cfg* cfg, PackLayout* L) {
   L->fp32_floats = off;
   L->tc_stream_off = (off * sizeof(float) + 1023) & ~(size_t)1023;
   L->tc_stream_bytes = tc_stream_bytes_for(L->d);
-  L->total_bytes = L->tc_stream_off + L->tc_stream_bytes;
+  L->tf32_stream_off = (L->tc_stream_off + L->tc_stream_bytes + 1023) & ~(size_t)1023;
+  L->tf32_stream_bytes = tf32_stream_bytes_for(L->d);
+  L->total_bytes = L->tf32_stream_off + L->tf32_stream_bytes;
   return DFB200_OK;
 }
 
@@ -92,6 +96,8 @@ Workspace carve_workspace(const NetDims& d, int mode, int B, int N, void* base) 
     w.x = take(M * D_MODEL);
     w.q = take(M * D_MODEL);
     w.u = take(M * D_FF);
+  } else if (mode == DFB200_MODE_TF32) {
+    w.fold = take((tf32_fold_bytes_for(d, B) + 3) / 4);
   } else {
     w.fold = take((tc_fold_bytes_for(d, B) + 3) / 4);
   }
@@ -367,7 +373,9 @@ extern "C" int dfb200_denoiser_pack(const dfb200_denoiser_cfg* cfg, const float*
     DFB_CUDA(cudaMemcpyAsync(P + L.freqs, fr.data(), sizeof(float) * fr.size(), cudaMemcpyHostToDevice, st));
     DFB_CUDA(cudaStreamSynchronize(st));  // fr is a stack-lifetime host buffer
   }
-  return tc_pack_stream(L, packed, st);
+  rc = tc_pack_stream(L, packed, st);
+  if (rc != DFB200_OK) return rc;
+  return tf32_pack_stream(L, packed, st);
 }
 
 extern "C" size_t dfb200_denoiser_workspace_bytes(const dfb200_denoiser_cfg* cfg, int mode, int B, int N) {
@@ -384,7 +392,8 @@ extern "C" int dfb200_denoiser_forward(const dfb200_denoiser_cfg* cfg, const voi
   int rc = make_pack_layout(cfg, &L);
   if (rc != DFB200_OK) return rc;
   DFB_REQUIRE(B >= 0 && N >= 0, DFB200_ERR_INVALID_ARG, "denoiser_forward: negative size");
-  DFB_REQUIRE(mode == DFB200_MODE_FP32 || mode == DFB200_MODE_BF16, DFB200_ERR_INVALID_ARG, "denoiser_forward: unknown mode %d", mode);
+  DFB_REQUIRE(mode == DFB200_MODE_FP32 || mode == DFB200_MODE_BF16 || mode == DFB200_MODE_TF32, DFB200_ERR_INVALID_ARG,
+              "denoiser_forward: unknown mode %d", mode);
   if (B == 0 || N == 0) return DFB200_OK;
   Workspace ws = carve_workspace(L.d, mode, B, N, workspace);
   DFB_REQUIRE(workspace != nullptr && workspace_bytes >= ws.bytes, DFB200_ERR_WORKSPACE,
@@ -396,5 +405,7 @@ extern "C" int dfb200_denoiser_forward(const dfb200_denoiser_cfg* cfg, const voi
   const float* valid = (L.d.flags & DFB200_NET_MASK_UNREFERENCED) ? valid_id : nullptr;
   if (mode == DFB200_MODE_FP32)
     return denoiser_forward_fp32(L, P, B, N, x, anchors, variances, anchor_assignment, valid, eps_out, ws, st);
+  if (mode == DFB200_MODE_TF32)
+    return denoiser_forward_tf32(L, packed, B, N, x, anchors, variances, anchor_assignment, valid, eps_out, ws, st);
   return denoiser_forward_tc(L, packed, B, N, x, anchors, variances, anchor_assignment, valid, eps_out, ws, st);
 }

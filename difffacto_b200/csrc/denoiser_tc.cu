@@ -1030,6 +1030,15 @@ static const float* tc_extras(const PackLayout& L, const void* packed) {
   return reinterpret_cast<const float*>(S + (size_t)L.d.depth * STATIC_PER_LAYER * SLOT_BYTES);
 }
 
+// shared with the tf32 kernel (denoiser_tf32.cu): the per-block fold weights (WqG | bqG | WoT) and the folded GEGLU-in biases
+const float* tc_foldw_base(const PackLayout& L, const void* packed, size_t* stride_floats) {
+  *stride_floats = FOLDW_FLOATS;
+  return tc_extras(L, packed) + HEAD_FLOATS;
+}
+const float* tc_b1p_base(const PackLayout& L, const void* packed) {
+  return tc_extras(L, packed) + HEAD_FLOATS + (size_t)L.d.depth * FOLDW_FLOATS;
+}
+
 int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time, int t_first,
                         const int* step_t, int steps, void* fold, cudaStream_t st) {
   if (B == 0 || steps == 0) return DFB200_OK;

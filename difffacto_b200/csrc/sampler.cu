@@ -66,7 +66,7 @@ static LoopWorkspace carve_loop(const NetDims& d, int mode, int B, int N, int T,
   };
   // sized for the largest variant (guidance doubles the per-sample tables), so one workspace serves every option set
   w.ctx0 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * (d.c_ctx_static - d.n_tok) * d.n_tok));
-  if (mode == DFB200_MODE_FP32) {
+  if (mode != DFB200_MODE_BF16) {
     w.eps = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * 3 * N));
     w.eps_u = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * 3 * N));
     w.t_f = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B));
@@ -145,7 +145,8 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
   dfb200_sample_opts o{};
   if (opts != nullptr) o = *opts;
   DFB_REQUIRE(B >= 0 && N >= 0 && T >= 1, DFB200_ERR_INVALID_ARG, "sample_loop: bad sizes B=%d N=%d T=%d", B, N, T);
-  DFB_REQUIRE(mode == DFB200_MODE_FP32 || mode == DFB200_MODE_BF16, DFB200_ERR_INVALID_ARG, "sample_loop: unknown mode %d", mode);
+  DFB_REQUIRE(mode == DFB200_MODE_FP32 || mode == DFB200_MODE_BF16 || mode == DFB200_MODE_TF32, DFB200_ERR_INVALID_ARG,
+              "sample_loop: unknown mode %d", mode);
   DFB_REQUIRE(traj == nullptr || traj_interval >= 1, DFB200_ERR_INVALID_ARG, "sample_loop: traj_interval must be >= 1");
   // the step list: every timestep T-1 .. 0, or the caller's strictly decreasing device list (DDIM strides)
   const int n_list = o.timesteps != nullptr ? o.n_timesteps : T;
@@ -183,8 +184,13 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
   const size_t ctx_floats = (size_t)B * (L.d.c_ctx_static - L.d.n_tok) * L.d.n_tok;
   if (o.guidance && prepare) DFB_CUDA(cudaMemsetAsync(lw.ctx0, 0, sizeof(float) * ctx_floats, st));
 
-  if (mode == DFB200_MODE_FP32) {
+  if (mode != DFB200_MODE_BF16) {  // fp32 (CUDA cores) and tf32 (tensor cores): step-wise launches, same update kernels
     Workspace ws = carve_workspace(L.d, mode, B, N, lw.net);
+    auto forward = [&](float* eps_dst) {
+      return mode == DFB200_MODE_TF32
+                 ? denoiser_forward_tf32(L, packed, B, N, x, anchors, variance, anchor_assignment, valid, eps_dst, ws, st)
+                 : denoiser_forward_fp32(L, P, B, N, x, anchors, variance, anchor_assignment, valid, eps_dst, ws, st);
+    };
     for (int k = first; k < first + count; ++k) {
       const int i = step_time(k);
       fill_step_kernel<<<cdiv(B, 256), 256, 0, st>>>(B, i, lw.t_f, lw.t_i);
@@ -193,12 +199,12 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
       if (o.guidance) {  // unconditional pass first (its K/V workspace is overwritten by the conditional one)
         rc = launch_context_kv(L, P, B, lw.t_f, lw.ctx0, ws, st);
         if (rc != DFB200_OK) return rc;
-        rc = denoiser_forward_fp32(L, P, B, N, x, anchors, variance, anchor_assignment, valid, lw.eps_u, ws, st);
+        rc = forward(lw.eps_u);
         if (rc != DFB200_OK) return rc;
       }
       rc = launch_context_kv(L, P, B, lw.t_f, ctx, ws, st);
       if (rc != DFB200_OK) return rc;
-      rc = denoiser_forward_fp32(L, P, B, N, x, anchors, variance, anchor_assignment, valid, lw.eps, ws, st);
+      rc = forward(lw.eps);
       if (rc != DFB200_OK) return rc;
       if (o.guidance) {
         rc = dfb200_guidance_mix((size_t)total, o.classifier_weight, lw.eps_u, lw.eps, lw.eps, stream);

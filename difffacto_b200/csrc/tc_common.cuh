@@ -115,6 +115,29 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- kind::tf32: fp32 containers in shared memory, the tensor core reads the top 19 bits (1+8+10) -------------------------
+// Same canonical K-major no-swizzle layout with 32-bit elements: a 16-byte chunk holds 4 k-values, one MMA covers K = 8
+// (two chunks): offset(r, k) = (k/4)*R*16 + r*16 + (k%4)*4, LBO = R*16, SBO = 128 -- the byte geometry of the bf16 tiles.
+// idesc: c_format = F32 (1), a_format = b_format = TF32 (2), K-major both.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t tile_off32(int R, int r, int k) { return (uint32_t)((k >> 2) * R * 16 + r * 16 + (k & 3) * 4); }
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa; the tensor core would otherwise TRUNCATE the fp32 container
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return __uint_as_float(y);
+}
+
 // Arrive on `bar` when every MMA issued so far by this thread has completed (implies
 // tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

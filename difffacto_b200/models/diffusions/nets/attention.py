@@ -108,7 +108,8 @@ class TransformerNet(nn.Module):
             [_Block(self.inner_dim, n_heads, d_head, dropout, self.context_dim) for _ in range(depth)])
         self.proj_out = nn.Linear(self.inner_dim, out_channels)
 
-        # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulation); "fp32": CUDA-core path
+        # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulation), the throughput mode; "tf32": tcgen05 kind::tf32 with
+        # every non-GEMM op in fp32, the tensor-core mode at reference tolerance; "fp32": CUDA-core path (reference numerics)
         self.precision = precision or os.environ.get("DFB200_PRECISION", "bf16")
         # training path: "fp32" (CUDA-core GEMMs, bit-faithful gradients) or "bf16" (tcgen05 GEMMs, mixed precision)
         self.train_precision = os.environ.get("DFB200_TRAIN_PRECISION", "fp32")
@@ -127,9 +128,9 @@ class TransformerNet(nn.Module):
                            self.raw_context_dim, self.n_class, flags)
 
     def mode(self):
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
-        return _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
+        if self.precision not in ("fp32", "bf16", "tf32"):
+            raise ValueError(f"precision must be 'fp32', 'tf32' or 'bf16', got {self.precision!r}")
+        return {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "tf32": _lib.MODE_TF32}[self.precision]
 
     def packed_weights(self):
         """Device weight image for the kernels; rebuilt whenever a parameter was modified."""

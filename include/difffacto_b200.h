@@ -148,6 +148,8 @@ typedef struct dfb200_denoiser_cfg {
 /* Precision mode of the denoiser GEMMs. */
 #define DFB200_MODE_FP32 0 /* CUDA-core FFMA, fp32 everywhere (reference numerics)          */
 #define DFB200_MODE_BF16 1 /* tcgen05 tensor cores: bf16 operands, fp32 accumulate in TMEM  */
+#define DFB200_MODE_TF32 2 /* tcgen05 kind::tf32: fp32 operands rounded to 10 mantissa bits, fp32 accumulate; LayerNorm, softmax,
+                              erf-GELU, proj_in/out and every bias in fp32 -- the tensor-core mode at reference tolerance (<= 2e-3) */
 
 /* Number of fp32 parameter tensors dfb200_denoiser_pack expects: 12 + 13*depth, in this order
  * (names as in the reference state_dict under `diffusion.model.`):

@@ -165,6 +165,7 @@ def precision_block(torch, build_model, synthetic_batch, B, N, T, flop_per_point
     ref_model = None
     for mode in modes:
         try:
+            torch.manual_seed(0)  # the same random-init weights in every mode
             diff = build_model(T, mode).cuda().eval()
             if ref_model is None:
                 torch.set_num_threads(os.cpu_count() or 1)
