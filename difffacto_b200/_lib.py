@@ -25,7 +25,8 @@ class SampleOpts(ctypes.Structure):
     _fields_ = [("timesteps", c_void_p), ("timesteps_host", ctypes.POINTER(c_int)), ("n_timesteps", c_int),
                 ("first_step", c_int), ("num_steps", c_int), ("tables_ready", c_int), ("ddim", c_int), ("ddim_eta", c_float),
                 ("alphas_cumprod_prev", c_void_p), ("xt_dir_coeff", c_void_p), ("guidance", c_int),
-                ("classifier_weight", c_float), ("step_sample", c_void_p), ("step_xstart", c_void_p)]
+                ("classifier_weight", c_float), ("step_sample", c_void_p), ("step_xstart", c_void_p),
+                ("step_sample_list", ctypes.POINTER(c_void_p)), ("step_xstart_list", ctypes.POINTER(c_void_p))]
 
 
 NET_CLASS_COND, NET_CAT_PARAMS_TO_X, NET_CAT_CLASS_TO_X, NET_MASK_UNREFERENCED, NET_INCLUDE_STD = 1, 2, 4, 8, 16

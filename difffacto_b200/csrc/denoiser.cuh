@@ -70,6 +70,7 @@ int launch_context_kv_static(const PackLayout& L, const float* packed, int B, co
 int launch_context_kv_time(const PackLayout& L, const float* packed, int T, const float* t_values, float* temb_h, float* temb,
                            float* kv_time, cudaStream_t st);
 
+constexpr int TC_MAX_LIST_STEPS = 64;  // per-step output pointers travel in the kernel parameters (power of two)
 // fused-update arguments of the bf16 kernel (all-zero = plain forward writing eps)
 struct TcUpdate {
   const float* sched;  // device schedule table [DFB200_SCHED_ROWS][T]
@@ -84,6 +85,7 @@ struct TcUpdate {
   int* done;           // per 256-token unit: tile-steps completed since the loop began (zeroed by the caller); required if n_steps > 1
   float* traj; int traj_interval;  // optional trajectory slots (see dfb200_ddpm_sample_loop)
   float* step_sample; float* step_xstart;  // optional (n_steps,B,3,N): sample / pred_xstart after each step of this launch
+  float* const* step_sample_list; float* const* step_xstart_list;  // or HOST arrays of n_steps (B,3,N) device buffers (n_steps <= TC_MAX_LIST_STEPS)
   const float* ddim_acp; const float* ddim_dir; float ddim_eta;  // DDIM update when ddim_acp != NULL (device float32[T] tables)
   int guidance; float guid_w;  // classifier-free guidance: `fold` holds 2B entries per step (conditional, then unconditional)
 };

@@ -381,6 +381,7 @@ struct TcParams {
   const float* upd_sched; int upd_T; const float* upd_noise; size_t noise_step_elems; uint64_t upd_seed; float* x_out;
   float* traj; int traj_interval;
   float* step_sample; float* step_xstart;  // optional (n_steps,B,3,N): `sample` / `pred_xstart` of every step of this launch
+  float* step_s[TC_MAX_LIST_STEPS]; float* step_x[TC_MAX_LIST_STEPS];  // or one (B,3,N) buffer per step (NULL entries = not wanted)
   const float* ddim_acp; const float* ddim_dir; float ddim_eta;  // DDIM update instead of the ancestral one when ddim_acp != NULL
   // classifier-free guidance (anchored_diffusion.py:263-266): a unit is ONE 128-token tile run twice -- tile slot 0 with the
   // conditional fold packets, slot 1 with the unconditional ones (fold entries [B, 2B) of a step) -- and the head mixes
@@ -803,8 +804,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
         // sample shares t); x, anchors, variances and the noise are already in registers
         const bool keep = P.traj != nullptr && t_cur > 0 && t_cur % P.traj_interval == 0;
         float* tr = keep ? P.traj + (size_t)(t_cur / P.traj_interval - 1) * (size_t)P.M * 3 : nullptr;
-        float* ss = P.step_sample != nullptr ? P.step_sample + (size_t)step_local * (size_t)P.M * 3 : nullptr;
-        float* sx = P.step_xstart != nullptr ? P.step_xstart + (size_t)step_local * (size_t)P.M * 3 : nullptr;
+        float* ss = P.step_sample != nullptr ? P.step_sample + (size_t)step_local * (size_t)P.M * 3 : P.step_s[step_local & (TC_MAX_LIST_STEPS - 1)];
+        float* sx = P.step_xstart != nullptr ? P.step_xstart + (size_t)step_local * (size_t)P.M * 3 : P.step_x[step_local & (TC_MAX_LIST_STEPS - 1)];
         float acp_s = 0.f, dir_c = 0.f;
         if (P.ddim_acp != nullptr) {
           acp_s = __fsqrt_rn(__ldg(P.ddim_acp + t_cur));
@@ -1080,6 +1081,14 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
     p.done = upd->done; p.traj = upd->traj; p.traj_interval = upd->traj_interval;
     p.step_t = upd->step_t; p.step_base = upd->step_base;
     p.step_sample = upd->step_sample; p.step_xstart = upd->step_xstart;
+    if (upd->step_sample_list != nullptr || upd->step_xstart_list != nullptr) {
+      DFB_REQUIRE(p.n_steps <= TC_MAX_LIST_STEPS, DFB200_ERR_INVALID_ARG, "denoiser (bf16 mode): at most %d steps per launch with per-step output buffers",
+                  TC_MAX_LIST_STEPS);
+      for (int k = 0; k < p.n_steps; ++k) {
+        if (upd->step_sample_list != nullptr) p.step_s[k] = upd->step_sample_list[k];
+        if (upd->step_xstart_list != nullptr) p.step_x[k] = upd->step_xstart_list[k];
+      }
+    }
     p.ddim_acp = upd->ddim_acp; p.ddim_dir = upd->ddim_dir; p.ddim_eta = upd->ddim_eta;
     DFB_REQUIRE(p.n_steps == 1 || p.done != nullptr, DFB200_ERR_INVALID_ARG, "denoiser (bf16 mode): multi-step launch without dependency counters");
   }

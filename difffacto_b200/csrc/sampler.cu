@@ -129,6 +129,7 @@ extern "C" int dfb200_sample_loop_chunk(const dfb200_denoiser_cfg* cfg, int mode
   const long long full = carve_loop(d, mode, B, N, T, nullptr).chunk;
   const long long period = balance_period(cdiv((long long)B * N, 256));
   long long c = period * ((24 + period - 1) / period);
+  if (c > TC_MAX_LIST_STEPS) c = TC_MAX_LIST_STEPS;  // per-step output buffers: at most this many steps per launch
   if (c > full) c = full;
   return (int)c;
 }
@@ -211,7 +212,8 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
         if (rc != DFB200_OK) return rc;
       }
       const float* z = philox ? nullptr : noise + (size_t)(k - first) * total;
-      float* xs = o.step_xstart != nullptr ? o.step_xstart + (size_t)(k - first) * total : nullptr;
+      float* xs = o.step_xstart != nullptr ? o.step_xstart + (size_t)(k - first) * total
+                                           : o.step_xstart_list != nullptr ? o.step_xstart_list[k - first] : nullptr;
       if (o.ddim) {
         float* zbuf = nullptr;
         if (philox) {  // DDIM with in-kernel noise: draw this step's Philox normals into the (now free) unconditional buffer
@@ -225,8 +227,9 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
         rc = launch_ddpm_step(B, N, T, sched, lw.t_i, x, eps, anchors, variance, z, philox, seed, (uint64_t)i, x, xs, st);
       }
       if (rc != DFB200_OK) return rc;
-      if (o.step_sample != nullptr)
-        DFB_CUDA(cudaMemcpyAsync(o.step_sample + (size_t)(k - first) * total, x, sizeof(float) * total, cudaMemcpyDeviceToDevice, st));
+      float* ssd = o.step_sample != nullptr ? o.step_sample + (size_t)(k - first) * total
+                                            : o.step_sample_list != nullptr ? o.step_sample_list[k - first] : nullptr;
+      if (ssd != nullptr) DFB_CUDA(cudaMemcpyAsync(ssd, x, sizeof(float) * total, cudaMemcpyDeviceToDevice, st));
       if (traj != nullptr && i > 0 && i % traj_interval == 0)
         DFB_CUDA(cudaMemcpyAsync(traj + (size_t)(i / traj_interval - 1) * total, x, sizeof(float) * total, cudaMemcpyDeviceToDevice, st));
     }
@@ -251,7 +254,9 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
     DFB_CUDA(cudaMemsetAsync(lw.done, 0, sizeof(int) * (size_t)cdiv((long long)B * N, 128), st));
   }
   const size_t per_step = tc_fold_bytes_for(L.d, nb);
-  const int chunk = o.guidance ? (lw.chunk > 1 ? lw.chunk / 2 : 1) : lw.chunk;  // guidance: 2B fold entries per step
+  int chunk = o.guidance ? (lw.chunk > 1 ? lw.chunk / 2 : 1) : lw.chunk;  // guidance: 2B fold entries per step
+  const bool lists = o.step_sample_list != nullptr || o.step_xstart_list != nullptr;
+  if (lists && chunk > TC_MAX_LIST_STEPS) chunk = TC_MAX_LIST_STEPS;  // per-step output pointers travel in the kernel parameters
   for (int k0 = first; k0 < first + count; k0 += chunk) {
     const int steps = first + count - k0 < chunk ? first + count - k0 : chunk;
     const int* list = o.timesteps != nullptr ? o.timesteps + k0 : nullptr;
@@ -269,6 +274,8 @@ extern "C" int dfb200_sample_loop(const dfb200_denoiser_cfg* cfg, const void* pa
     u.traj = traj; u.traj_interval = traj_interval;
     u.step_sample = o.step_sample != nullptr ? o.step_sample + (size_t)(k0 - first) * total : nullptr;
     u.step_xstart = o.step_xstart != nullptr ? o.step_xstart + (size_t)(k0 - first) * total : nullptr;
+    u.step_sample_list = o.step_sample_list != nullptr ? o.step_sample_list + (k0 - first) : nullptr;
+    u.step_xstart_list = o.step_xstart_list != nullptr ? o.step_xstart_list + (k0 - first) : nullptr;
     if (o.ddim) { u.ddim_acp = o.alphas_cumprod_prev; u.ddim_dir = o.xt_dir_coeff; u.ddim_eta = o.ddim_eta; }
     u.guidance = o.guidance; u.guid_w = o.classifier_weight;
     rc = denoiser_step_tc(L, packed, B, N, x, anchors, variance, anchor_assignment, valid, lw.fold, nullptr, &u, st);

@@ -233,6 +233,7 @@ class AnchoredDiffusion(Module):
         return st
 
     def _run_steps(self, st, B, N, x, from_noise, first, count, noise, seed, traj, traj_interval, step_sample=None, step_xstart=None):
+        """step_sample / step_xstart: lists of `count` separate (B,3,N) tensors (one per executed step)."""
         o = _lib.SampleOpts()
         if st["steps_dev"] is not None:
             o.timesteps, o.timesteps_host, o.n_timesteps = st["steps_dev"].data_ptr(), st["steps_host"], len(st["steps"])
@@ -241,8 +242,10 @@ class AnchoredDiffusion(Module):
             o.ddim, o.ddim_eta = 1, float(self.ddim_eta)
             o.alphas_cumprod_prev, o.xt_dir_coeff = st["ddim"][0].data_ptr(), st["ddim"][1].data_ptr()
         o.guidance, o.classifier_weight = int(bool(self.guidance)), float(self.classifier_weight)
-        o.step_sample = None if step_sample is None else step_sample.data_ptr()
-        o.step_xstart = None if step_xstart is None else step_xstart.data_ptr()
+        if step_sample is not None:
+            o.step_sample_list = (_lib.c_void_p * count)(*[t.data_ptr() for t in step_sample])
+        if step_xstart is not None:
+            o.step_xstart_list = (_lib.c_void_p * count)(*[t.data_ptr() for t in step_xstart])
         with _lib.on(x.device):
             check(_lib.load().dfb200_sample_loop(st["cfg"], ptr(st["packed"]), st["mode"], B, N, self.num_timesteps, ptr(st["sched"]),
                                                  ptr(x), from_noise, ptr(st["ctx"]), ptr(st["anchors"]), ptr(st["variance"]),
@@ -258,7 +261,7 @@ class AnchoredDiffusion(Module):
         The steps are served from the FUSED loop, one persistent-kernel launch per chunk of steps (24 at the BASELINE size):
         the kernel stores `sample` and `pred_xstart` of every step of the chunk into fresh buffers that the generator then
         hands out one by one, so a caller that iterates the generator runs at the speed of `p_sample_loop` instead of
-        paying ~10 launches per step.  torch's generator is consumed exactly as by the reference (x_T first, then one
+        paying ~10 launches per step (at most 64 steps per launch: the per-step output pointers travel in the kernel parameters).  torch's generator is consumed exactly as by the reference (x_T first, then one
         randn per step incl. t=0); a consumer that stops early has computed at most one chunk more than it used.
         `fused=False` (or use_beta / rescale_timesteps) steps through `p_sample` as the reference does; `chunk` overrides the
         number of steps per launch (default: dfb200_sample_loop_chunk, 37 at the BASELINE size)."""
@@ -295,10 +298,12 @@ class AnchoredDiffusion(Module):
                 z = torch.empty(n, B, C, N, device=pcd.device)
                 for k in range(n):  # one draw per step, as p_sample's torch.randn_like (:476)
                     torch.randn(B, C, N, device=pcd.device, out=z[k])
-                out = torch.empty(2, n, B, C, N, device=pcd.device)  # fresh per chunk: yielded views are never overwritten
-                self._run_steps(st, B, N, x, 0, k0, n, z, 0, None, None, step_sample=out[0], step_xstart=out[1])
+                # one fresh tensor per step and output: never overwritten, and a caller that keeps a few steps pins only those
+                outs = [torch.empty(B, C, N, device=pcd.device) for _ in range(n)]
+                xss = [torch.empty(B, C, N, device=pcd.device) for _ in range(n)]
+                self._run_steps(st, B, N, x, 0, k0, n, z, 0, None, None, step_sample=outs, step_xstart=xss)
                 for k in range(n):
-                    yield next(it), dict(sample=out[0, k], pred_xstart=out[1, k])
+                    yield next(it), dict(sample=outs[k], pred_xstart=xss[k])
 
     @torch.no_grad()
     def p_sample_loop(self, shape, anchors, ctx=None, noise=None, variance=None, anchor_assignment=None, valid_id=None,

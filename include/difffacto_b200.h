@@ -342,7 +342,9 @@ int dfb200_ddpm_sample_loop(const dfb200_denoiser_cfg* cfg, const void* packed, 
  *   guidance       classifier-free guidance (:263-266): a second, zero-context denoiser pass per step,
  *                  eps = (1 - w) eps_uncond + w eps_cond;
  *   step_sample /  optional (num_steps,B,3,N) outputs: `sample` and `pred_xstart` of EVERY executed step (the dict the
- *   step_xstart    reference's generator yields, :587). */
+ *   step_xstart    reference's generator yields, :587);
+ *   step_sample_list / step_xstart_list   the same outputs as HOST arrays of num_steps separate (B,3,N) device buffers (entries
+ *                  may be NULL), so that a caller who keeps only some steps does not pin the others' memory. */
 typedef struct dfb200_sample_opts {
   const int* timesteps;
   const int* timesteps_host;
@@ -356,6 +358,8 @@ typedef struct dfb200_sample_opts {
   float classifier_weight;
   float* step_sample;
   float* step_xstart;
+  float* const* step_sample_list;
+  float* const* step_xstart_list;
 } dfb200_sample_opts;
 /* Steps one persistent launch of the fused kernel covers for these sizes: the natural num_steps of a chunked caller. */
 int dfb200_sample_loop_chunk(const dfb200_denoiser_cfg* cfg, int mode, int B, int N, int T);

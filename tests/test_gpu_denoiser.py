@@ -2,7 +2,7 @@
 the golden vectors minted from the real reference (tests/golden) and the oracle port.
 
 Stated tolerances (abs, on eps ~ O(0.5)):
-  fp32 mode (CUDA-core FFMA):  1e-4   (fp32 accumulation order only)
+  fp32 mode (CUDA-core FFMA):  1e-5   (fp32 accumulation order only, measured 1.3e-6 at B=32, N=2048)
   tf32 mode (tcgen05 kind::tf32, everything that is not a GEMM operand in fp32): 2e-3 (SURVEY.md 8c)
   bf16 mode (tcgen05, bf16 operands, fp32 accumulate): 1e-2 per step (measured max 3.2e-3 at B=32, N=2048)
 DDPM update arithmetic: bit-exact with the reference's torch op sequence evaluated on the same GPU given eps and
@@ -15,7 +15,7 @@ from oracle import denoiser_ref as R
 
 pytestmark = pytest.mark.gpu
 CASES = {"a": (11, 3, 64, False), "b": (12, 2, 128, True)}
-TOL = {"fp32": 1e-4, "tf32": 2e-3, "bf16": 1e-2}
+TOL = {"fp32": 1e-5, "tf32": 2e-3, "bf16": 1e-2}
 NET_CFG = dict(type="TransformerNet", in_channels=3, out_channels=3, n_heads=8, d_head=16, depth=5, dropout=0.2,
                context_dim=262, n_class=4, class_cond=True, use_linear=True, cat_params_to_x=True, use_checkpoint=False,
                single_attn=True, cat_class_to_x=True)
