@@ -195,18 +195,29 @@ struct Tf32Params {
   long long M;
 };
 
-// erf GELU of the reference (F.gelu default): Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7; returns g * (1 + erf(g / sqrt 2))
-__device__ __forceinline__ float gelu2x(float g) {
-  const float z = fabsf(g) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  const float erf_abs = fmaf(-p * t, e, 1.f);
-  return g * (1.f + copysignf(erf_abs, g));
+// erf GELU of the reference (F.gelu default) for two columns: Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7; returns
+// (a_half + ba) * (g + bg) * (1 + erf((g + bg) / sqrt 2)), rounded to tf32.  Packed fp32x2 math (FFMA2): the GEGLU epilogue is
+// the bottleneck of this kernel (ncu: tensor pipe 29 % busy, issue slots 49 %), MUFU.RCP / MUFU.EX2 stay scalar.
+__device__ __forceinline__ float2 geglu_erf2(float2 a_half, float2 g, float2 ba, float2 bg) {
+  const float2 one = make_float2(1.f, 1.f);
+  g = __fadd2_rn(g, bg);
+  a_half = __fadd2_rn(a_half, ba);
+  const float2 z = __fmul2_rn(make_float2(fabsf(g.x), fabsf(g.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 den = __ffma2_rn(z, make_float2(0.3275911f, 0.3275911f), one);
+  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 zz = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float ex, ey;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(zz.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(zz.y));
+  // erf(|z|) = 1 - p t e;  1 + erf(z) = 1 + sign(g) erf(|z|)
+  const float2 erf_abs = __ffma2_rn(__fmul2_rn(p, t), make_float2(-ex, -ey), one);
+  const float2 onep = __fadd2_rn(one, make_float2(copysignf(erf_abs.x, g.x), copysignf(erf_abs.y, g.y)));
+  const float2 u = __fmul2_rn(__fmul2_rn(a_half, g), onep);
+  return make_float2(to_tf32(u.x), to_tf32(u.y));
 }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -406,7 +417,11 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
           tmem_ld32(ACC + 64, gt);
           tmem_wait_ld();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) a[k] = to_tf32((a[k] + ba[k]) * gelu2x(gt[k] + bg[k]));
+          for (int k = 0; k < 16; ++k) {
+            const float2 u = geglu_erf2(make_float2(a[2 * k], a[2 * k + 1]), make_float2(gt[2 * k], gt[2 * k + 1]),
+                                        make_float2(ba[2 * k], ba[2 * k + 1]), make_float2(bg[2 * k], bg[2 * k + 1]));
+            a[2 * k] = u.x; a[2 * k + 1] = u.y;
+          }
           tc_fence_before();
           mbar_wait(&bars[BAR_UFREE], ph_ufree);  // FF-out of the previous chunk has finished reading the U tile
           ph_ufree ^= 1;
