@@ -266,78 +266,82 @@ int tc_pack_stream(const PackLayout& L, void* packed, cudaStream_t st) {
 // timestep step_t[blockIdx.z] (or t_first - blockIdx.z when step_t == NULL), broadcast over the 4 tokens.  grid (B, depth, steps).
 // W_sim and b_sim carry an extra factor log2(e): the softmax of the fused kernel is exp2(s' - max s') / sum, one MUFU.EX2 per logit.
 constexpr float LOG2E = 1.4426950408889634f;
-__global__ void __launch_bounds__(256)
+constexpr int FOLD_SPB = 8;  // sampling steps folded per CTA: its 128 + 128 weight columns are read once (registers) for all of them
+__global__ void __launch_bounds__(512)
 context_fold_kernel(int depth, const float* __restrict__ kv, const float* __restrict__ kv_time, int t_first,
-                    const int* __restrict__ step_t, const float* __restrict__ extras, uint8_t* __restrict__ fold_all) {
+                    const int* __restrict__ step_t, int steps, const float* __restrict__ extras, uint8_t* __restrict__ fold_all) {
   __shared__ float K[MAX_TOKENS][D_MODEL], V[MAX_TOKENS][D_MODEL];
   // the packet is assembled in shared memory and leaves as coalesced 16-byte stores: the tile layout scatters a thread's
   // bf16 values 16..512 bytes apart, and 66 2-byte global stores per thread made this kernel store-issue bound
   __shared__ __align__(16) uint8_t img[FOLD_BYTES];
   const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
   const float* src = kv + ((size_t)b * depth + l) * 1024;
-  uint8_t* fold = fold_all + (size_t)blockIdx.z * gridDim.x * depth * FOLD_BYTES;
-  for (int i = t; i < 512; i += 256) {
-    float kt = 0.f, vt = 0.f;
-    if (kv_time != nullptr) {
-      const int tcur = step_t != nullptr ? __ldg(step_t + blockIdx.z) : t_first - (int)blockIdx.z;
-      const float* tt = kv_time + ((size_t)tcur * depth + l) * 2 * D_MODEL;
-      kt = __ldg(tt + (i & 127));
-      vt = __ldg(tt + D_MODEL + (i & 127));
-    }
-    (&K[0][0])[i] = __ldg(src + i) + kt;
-    (&V[0][0])[i] = __ldg(src + 512 + i) + vt;
-  }
-  __syncthreads();
   const float* WqG = extras + HEAD_FLOATS + (size_t)l * FOLDW_FLOATS;
   const float* bqG = WqG + D_MODEL * D_MODEL;
   const float* WoT = bqG + D_MODEL;
-  uint8_t* gout = fold + ((size_t)b * depth + l) * FOLD_BYTES;
-  uint8_t* out = img;
-  const int col = t & 127, half = t >> 7;
-  // W_sim: thread = column k, rows r = (h,j) with h in this half's 4 heads
+  // 512 threads: threads [0,256) build W_sim, [256,512) W_pv; within a role thread = (column, half of the heads)
+  const int col = t & 127, half = (t >> 7) & 1, role = t >> 8;
+  // Every step of a (sample, block) multiplies the SAME weight columns: one L2 read per CTA instead of one per step (the kernel
+  // was L2-bound on these 128 KB per packet: 2.7 ms per 1000-step loop at the BASELINE size).
+  float w[4][16];
+#pragma unroll
   for (int hh = 0; hh < 4; ++hh) {
-    const int h = half * 4 + hh;
-    float acc[MAX_TOKENS] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float w = __ldg(WqG + (16 * h + d) * D_MODEL + col);
-#pragma unroll
-      for (int j = 0; j < MAX_TOKENS; ++j) acc[j] = fmaf(K[j][16 * h + d], w, acc[j]);
+    for (int d = 0; d < 16; ++d) w[hh][d] = __ldg((role == 0 ? WqG : WoT) + (16 * (half * 4 + hh) + d) * D_MODEL + col);
+  }
+  const int s_lo = blockIdx.z * FOLD_SPB, s_hi = min(steps, s_lo + FOLD_SPB);
+  for (int sidx = s_lo; sidx < s_hi; ++sidx) {
+    uint8_t* fold = fold_all + (size_t)sidx * gridDim.x * depth * FOLD_BYTES;
+    __syncthreads();  // the previous step's packet has left `img`, K / V are free
+    for (int i = t; i < 512; i += 512) {
+      float kt = 0.f, vt = 0.f;
+      if (kv_time != nullptr) {
+        const int tcur = step_t != nullptr ? __ldg(step_t + sidx) : t_first - sidx;
+        const float* tt = kv_time + ((size_t)tcur * depth + l) * 2 * D_MODEL;
+        kt = __ldg(tt + (i & 127));
+        vt = __ldg(tt + D_MODEL + (i & 127));
+      }
+      (&K[0][0])[i] = __ldg(src + i) + kt;
+      (&V[0][0])[i] = __ldg(src + 512 + i) + vt;
     }
+    __syncthreads();
+    uint8_t* gout = fold + ((size_t)b * depth + l) * FOLD_BYTES;
+    uint8_t* out = img;
+    // role 0, W_sim: thread = column k, rows r = (h,j) with h in this half's 4 heads;  role 1, W_pv: thread = output channel c,
+    // columns r = (h,j)
+    const float (*KV)[D_MODEL] = role == 0 ? K : V;
 #pragma unroll
-    for (int j = 0; j < MAX_TOKENS; ++j)
-      *reinterpret_cast<__nv_bfloat16*>(out + FOLD_WSIM + tile_off(32, h * 4 + j, col)) = __float2bfloat16_rn(LOG2E * acc[j]);
-  }
-  // W_pv: thread = output channel c, columns r = (h,j)
-  for (int hh = 0; hh < 4; ++hh) {
-    const int h = half * 4 + hh;
-    float acc[MAX_TOKENS] = {0.f, 0.f, 0.f, 0.f};
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      float acc[MAX_TOKENS] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float w = __ldg(WoT + (16 * h + d) * D_MODEL + col);
+      for (int d = 0; d < 16; ++d) {
 #pragma unroll
-      for (int j = 0; j < MAX_TOKENS; ++j) acc[j] = fmaf(V[j][16 * h + d], w, acc[j]);
+        for (int j = 0; j < MAX_TOKENS; ++j) acc[j] = fmaf(KV[j][16 * h + d], w[hh][d], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < MAX_TOKENS; ++j) {
+        if (role == 0) *reinterpret_cast<__nv_bfloat16*>(out + FOLD_WSIM + tile_off(32, h * 4 + j, col)) = __float2bfloat16_rn(LOG2E * acc[j]);
+        else *reinterpret_cast<__nv_bfloat16*>(out + FOLD_WPV + tile_off(128, col, h * 4 + j)) = __float2bfloat16_rn(acc[j]);
+      }
     }
+    if (t < 32) {  // bias slab of the logits
+      const int h = t >> 2, j = t & 3;
+      float v = 0.f;
+      for (int d = 0; d < 16; ++d) v = fmaf(K[j][16 * h + d], __ldg(bqG + 16 * h + d), v);
+      v *= LOG2E;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out + FOLD_BSIM + t * 16);
+      o[0] = hi; o[1] = lo;
 #pragma unroll
-    for (int j = 0; j < MAX_TOKENS; ++j)
-      *reinterpret_cast<__nv_bfloat16*>(out + FOLD_WPV + tile_off(128, col, h * 4 + j)) = __float2bfloat16_rn(acc[j]);
+      for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    static_assert(FOLD_BYTES % 16 == 0, "fold packet must be a whole number of 16-byte chunks");
+    for (int i = t; i < FOLD_BYTES / 16; i += 512)
+      __stcs(reinterpret_cast<uint4*>(gout) + i, reinterpret_cast<const uint4*>(img)[i]);
   }
-  if (t < 32) {  // bias slab of the logits
-    const int h = t >> 2, j = t & 3;
-    float v = 0.f;
-    for (int d = 0; d < 16; ++d) v = fmaf(K[j][16 * h + d], __ldg(bqG + 16 * h + d), v);
-    v *= LOG2E;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out + FOLD_BSIM + t * 16);
-    o[0] = hi; o[1] = lo;
-#pragma unroll
-    for (int k = 2; k < 8; ++k) o[k] = __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
-  static_assert(FOLD_BYTES % 16 == 0, "fold packet must be a whole number of 16-byte chunks");
-  for (int i = t; i < FOLD_BYTES / 16; i += 256)
-    reinterpret_cast<uint4*>(gout)[i] = reinterpret_cast<const uint4*>(img)[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1043,8 +1047,8 @@ const float* tc_b1p_base(const PackLayout& L, const void* packed) {
 int launch_context_fold(const PackLayout& L, const void* packed, int B, const float* kv_static, const float* kv_time, int t_first,
                         const int* step_t, int steps, void* fold, cudaStream_t st) {
   if (B == 0 || steps == 0) return DFB200_OK;
-  context_fold_kernel<<<dim3(B, L.d.depth, steps), 256, 0, st>>>(L.d.depth, kv_static, kv_time, t_first, step_t, tc_extras(L, packed),
-                                                                  reinterpret_cast<uint8_t*>(fold));
+  context_fold_kernel<<<dim3(B, L.d.depth, cdiv(steps, FOLD_SPB)), 512, 0, st>>>(L.d.depth, kv_static, kv_time, t_first, step_t, steps,
+                                                                                  tc_extras(L, packed), reinterpret_cast<uint8_t*>(fold));
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

@@ -1150,11 +1150,12 @@ three_interpolate_kernel(int c, int m, int n, int c_per_block, const float* __re
 // LDS.128 for 4 channels and the gathers never leave the SM; a thread owns TI_PPT query points (idx / weights in registers
 // for the whole channel tile) and the 4 output rows are written with coalesced streaming stores.  (A variant with 4
 // consecutive points per thread and STG.128 stores measured slower: its idx/weight loads are 48-byte strided.)
-constexpr int TI_THREADS = 256, TI_PPT = 4;
+constexpr int TI_THREADS = 256;
+template <int TI_PPT, int TI_STAGE>  // TI_STAGE float4 slots staged per thread and quad: m <= TI_THREADS * TI_STAGE
 __global__ void __launch_bounds__(TI_THREADS)
 three_interpolate_c4_kernel(int c, int m, int n, int quads_per_block, const float* __restrict__ points,
                             const int* __restrict__ idx, const float* __restrict__ weight, float* __restrict__ out) {
-  extern __shared__ float4 ti_tile[];  // [m]
+  extern __shared__ float4 ti_tile[];  // [2][m]
   const int b = blockIdx.z, tid = threadIdx.x;
   const int nquad = (c + 3) >> 2;
   const int q0 = blockIdx.y * quads_per_block, q1 = min(nquad, q0 + quads_per_block);
@@ -1172,27 +1173,51 @@ three_interpolate_c4_kernel(int c, int m, int n, int quads_per_block, const floa
     i1[u] = __ldg(ii); i2[u] = __ldg(ii + 1); i3[u] = __ldg(ii + 2);
     w1[u] = __ldg(ww); w2[u] = __ldg(ww + 1); w3[u] = __ldg(ww + 2);
   }
-  for (int q = q0; q < q1; ++q) {
+  // The source tile is DOUBLE-BUFFERED: the 4 rows of quad q+1 are fetched into registers before quad q is computed and stored to
+  // the other buffer after it, so the global-load latency of the staging overlaps the gathers / stores and a quad costs one
+  // barrier instead of two (the kernel is HBM-bound on its output stream; the barriers were its bubbles).
+  float4 st[TI_STAGE];
+  auto fetch = [&](int q) {
     const int l0 = q * 4, nl = min(4, c - l0);
     const float* r0 = pts + (size_t)l0 * m;
     const float* r1 = r0 + (nl > 1 ? m : 0);
     const float* r2 = r0 + (nl > 2 ? 2 * (size_t)m : 0);
     const float* r3 = r0 + (nl > 3 ? 3 * (size_t)m : 0);
-    __syncthreads();
-    for (int i = tid; i < m; i += TI_THREADS) ti_tile[i] = make_float4(__ldg(r0 + i), __ldg(r1 + i), __ldg(r2 + i), __ldg(r3 + i));
-    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < TI_STAGE; ++s) {
+      const int i = tid + s * TI_THREADS;
+      if (i < m) st[s] = make_float4(__ldg(r0 + i), __ldg(r1 + i), __ldg(r2 + i), __ldg(r3 + i));
+    }
+  };
+  auto stash = [&](float4* buf) {
+#pragma unroll
+    for (int s = 0; s < TI_STAGE; ++s) {
+      const int i = tid + s * TI_THREADS;
+      if (i < m) buf[i] = st[s];
+    }
+  };
+  fetch(q0);
+  stash(ti_tile);
+  __syncthreads();
+  for (int q = q0; q < q1; ++q) {
+    const int l0 = q * 4, nl = min(4, c - l0);
+    const float4* cur = ti_tile + ((q - q0) & 1) * m;
+    float4* nxt = ti_tile + (((q - q0) & 1) ^ 1) * m;
+    if (q + 1 < q1) fetch(q + 1);
     float* o0 = o + (size_t)l0 * n;
 #pragma unroll
     for (int u = 0; u < TI_PPT; ++u) {
       if (!ok[u]) continue;
       const int j = (blockIdx.x * TI_PPT + u) * TI_THREADS + tid;
-      const float4 a = ti_tile[i1[u]], bq = ti_tile[i2[u]], cq = ti_tile[i3[u]];
+      const float4 a = cur[i1[u]], bq = cur[i2[u]], cq = cur[i3[u]];
       // fma(p3,w3, fma(p1,w1, mul(p2,w2))) per channel, as in the plain kernel
       __stcs(o0 + j, __fmaf_rn(cq.x, w3[u], __fmaf_rn(a.x, w1[u], __fmul_rn(bq.x, w2[u]))));
       if (nl > 1) __stcs(o0 + (size_t)n + j, __fmaf_rn(cq.y, w3[u], __fmaf_rn(a.y, w1[u], __fmul_rn(bq.y, w2[u]))));
       if (nl > 2) __stcs(o0 + 2 * (size_t)n + j, __fmaf_rn(cq.z, w3[u], __fmaf_rn(a.z, w1[u], __fmul_rn(bq.z, w2[u]))));
       if (nl > 3) __stcs(o0 + 3 * (size_t)n + j, __fmaf_rn(cq.w, w3[u], __fmaf_rn(a.w, w1[u], __fmul_rn(bq.w, w2[u]))));
     }
+    if (q + 1 < q1) stash(nxt);  // the other buffer was last read in iteration q-1, before that iteration's barrier
+    __syncthreads();
   }
 }
 
@@ -1408,9 +1433,10 @@ extern "C" int dfb200_three_interpolate(int b, int c, int m, int n, const float*
   DFB_REQUIRE(m > 0, DFB200_ERR_INVALID_ARG, "three_interpolate: empty source cloud");
   {
     // staged path: the interleaved source tile fits in shared memory and is reused by enough outputs
-    const size_t smem = sizeof(float4) * (size_t)m;
-    if (smem <= 48 * 1024 && n >= 4 * m && c >= 4 && b <= 65535) {
-      const int gx4 = cdiv(n, TI_THREADS * TI_PPT);
+    const size_t smem = 2 * sizeof(float4) * (size_t)m;  // double-buffered source tile
+    if (m <= TI_THREADS * 4 && n >= 4 * m && c >= 4 && b <= 65535) {
+      const int ppt = (n >= TI_THREADS * 8 && getenv("DFB200_TI_PPT4") == nullptr) ? 8 : 4;  // points per thread (idx / weights in registers)
+      const int gx4 = cdiv(n, TI_THREADS * ppt);
       const int nquad = (c + 3) / 4;
       int qpb = nquad;
       while (qpb > 1 && (long long)gx4 * b * cdiv(nquad, qpb) < 148 * 8) qpb = (qpb + 1) / 2;
@@ -1418,7 +1444,12 @@ extern "C" int dfb200_three_interpolate(int b, int c, int m, int n, const float*
       if (grid4.y <= 65535) {
         // (a variant with 4 consecutive points per thread -- 128-bit idx/weight loads, one STG.128 per channel -- was
         //  measured slower: 224 vs 191 us at batch 256, 69 registers and less gather parallelism per warp)
-        three_interpolate_c4_kernel<<<grid4, TI_THREADS, smem, as_stream(stream)>>>(c, m, n, qpb, points, idx, weight, out);
+#define TI_LAUNCH(P, S) three_interpolate_c4_kernel<P, S><<<grid4, TI_THREADS, smem, as_stream(stream)>>>(c, m, n, qpb, points, idx, weight, out)
+        if (ppt == 8 && m <= TI_THREADS * 2) TI_LAUNCH(8, 2);
+        else if (ppt == 8) TI_LAUNCH(8, 4);
+        else if (m <= TI_THREADS * 2) TI_LAUNCH(4, 2);
+        else TI_LAUNCH(4, 4);
+#undef TI_LAUNCH
         DFB_LAUNCH_CHECK();
         return DFB200_OK;
       }
