@@ -719,7 +719,8 @@ static size_t bqg_smem_bytes(int n) {
 }
 static size_t bqg_keys_offset(int n) { return bqg_smem_bytes(n) - 4 * (size_t)BQG_MAXSORT; }
 
-__global__ void __launch_bounds__(BQG_T)
+template <bool WPC>  // WPC: one warp per centre over a flattened candidate stream (A/B experiment); default: 8 lanes per centre
+__global__ void __launch_bounds__(BQG_T, 3)
 ball_query_grid_kernel(int nb, int n, int m, int mpad, int keys_off, int min_occupied, float radius, float radius2,
                        int nsample, int scan_tile,
                        const float* __restrict__ new_xyz, const float* __restrict__ xyz,
@@ -858,6 +859,112 @@ ball_query_grid_kernel(int nb, int n, int m, int mpad, int keys_off, int min_occ
       if (j % scan_tile == 0) idx[((size_t)b * m + j) * nsample] = -1;
     }
     __syncthreads();  // the next cloud's build reuses shared memory
+    continue;
+  }
+
+  if (WPC) {
+    // ---- ONE WARP per centre over a FLATTENED candidate stream (round 2) ------------------------------------------------
+    // The 9 x-contiguous runs of the 3x3x3 neighbourhood hold ~9 candidates each at r = 0.2: with 8 lanes per centre and one
+    // run at a time the pair-test loop ran at 35 % lane utilisation and a centre cost 775 warp-instructions.  Here lanes 0..8
+    // fetch the 9 run bounds, a 9-wide prefix sum lays the runs end to end, and lane L tests flat positions L, L+32, ...: every
+    // lane keeps a cursor (current run, its flat end) that it advances past finished / empty runs, so all 32 lanes test
+    // candidates until the stream is exhausted (~7 iterations for ~216 candidates).  Hits set bits in the warp's n-bit map
+    // (shared-memory atomicOr: candidates arrive in cell order), which the warp reads back in ascending index order -- lane L
+    // owns words [L*wpl, (L+1)*wpl) -- with ONE 32-lane popcount prefix scan: bit-identical to the ordered scan.  No centre
+    // sorting (no inter-centre divergence inside a warp), no group shuffles.
+    __shared__ int2 s_runs[NW][10];
+    const int wstride = ((n + 1023) / 1024) * 32;  // words of one warp's map (multiple of 32)
+    const int wpl = wstride / 32;                  // words per lane, <= 8 (n <= 8192)
+    unsigned* BMw = U + (size_t)warp * wstride;
+    for (int i = lane; i < wstride; i += 32) BMw[i] = 0u;
+    __syncwarp();
+    const int npass = (jhi - jlo + NW * GPW - 1) / (NW * GPW);
+    for (int pass = 0; pass < npass; ++pass) {
+#pragma unroll 1
+      for (int cc = 0; cc < GPW; ++cc) {
+        const int j = jlo + pass * NW * GPW + warp * GPW + cc;
+        if (j >= jhi) break;  // warp-uniform
+        const float* cq = new_xyz + ((size_t)b * m + j) * 3;
+        const float cx = __ldg(cq), cy = __ldg(cq + 1), cz = __ldg(cq + 2);
+        const int icx = (int)fminf(fmaxf(floorf((cx - lx) * ivx), -1.f), (float)gx);
+        const int icy = (int)fminf(fmaxf(floorf((cy - ly) * ivy), -1.f), (float)gy);
+        const int icz = (int)fminf(fmaxf(floorf((cz - lz) * ivz), -1.f), (float)gz);
+        const int x0 = max(icx - 1, 0), x1 = min(icx + 1, gx - 1);
+        int kb = 0, len = 0;
+        if (lane < 9) {
+          const int dz = lane / 3, dy = lane - 3 * dz;
+          const int yy = icy - 1 + dy, zz = icz - 1 + dz;
+          if (x0 <= x1 && yy >= 0 && yy < gy && zz >= 0 && zz < gz) {
+            const int row = (zz * gy + yy) * gx;
+            kb = E[row + x0];
+            len = (int)E[row + x1 + 1] - kb;
+          }
+        }
+        int incl = len;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+          const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 8);
+        if (lane < 9) s_runs[warp][lane] = make_int2(kb, incl);  // (start in S, flat END of the run)
+        __syncwarp();
+        {
+          int rcur = 0, obeg = 0;
+          int2 cur = s_runs[warp][0];
+          for (int p = lane; p - lane < total; p += 32) {  // warp-uniform trip count
+            if (p < total) {
+              while (p >= cur.y) {  // past the current run (or an empty one): total = s_runs[8].y > p bounds rcur by 8
+                obeg = cur.y;
+                cur = s_runs[warp][++rcur];
+              }
+              const float4 pt = S[cur.x + (p - obeg)];
+              if (sq3(cx - pt.x, cy - pt.y, cz - pt.z) < radius2) {
+                const int q = __float_as_int(pt.w);
+                atomicOr(&BMw[q >> 5], 1u << (q & 31));
+              }
+            }
+          }
+        }
+        __syncwarp();
+        // read-back in ascending index order
+        int* o = idx + ((size_t)b * m + j) * nsample;
+        unsigned wv[8];
+        int c = 0, myfirst = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          wv[i] = i < wpl ? BMw[lane * wpl + i] : 0u;
+          if (c == 0 && wv[i] != 0u) myfirst = (lane * wpl + i) * 32 + __ffs(wv[i]) - 1;
+          c += __popc(wv[i]);
+        }
+        int inc2 = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+          if (lane >= d) inc2 += v;
+        }
+        const int cnt = __shfl_sync(0xFFFFFFFFu, inc2, 31);
+        const unsigned nz = __ballot_sync(0xFFFFFFFFu, c != 0);
+        const int ffirst = __shfl_sync(0xFFFFFFFFu, myfirst, nz != 0u ? __ffs(nz) - 1 : 0);
+        const int first = cnt > 0 ? ffirst : 0;
+        int pos = inc2 - c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          unsigned v = wv[i];
+          if (v != 0u) {
+            BMw[lane * wpl + i] = 0u;  // ready for the warp's next centre
+            const int base = (lane * wpl + i) * 32;
+            while (v != 0u && pos < nsample) {
+              o[pos++] = base + __ffs(v) - 1;
+              v &= v - 1u;
+            }
+          }
+        }
+        for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) o[l] = first;
+        __syncwarp();
+      }
+    }
+    __syncthreads();  // the next cloud's build overwrites the maps / sorted array
     continue;
   }
 
@@ -1355,10 +1462,18 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
   if (!force_scan && n >= 1024 && n <= 8192 && m >= 32) {
     const size_t gsm = bqg_smem_bytes(n);
     // persistent CTAs (as many as fit: shared memory or 8 x 256 threads per SM), balanced static partition
-    int per_sm = (int)((227 * 1024) / (gsm + 1024));
+    // DFB200_BQ_QUERY=wpc: the warp-per-centre query over a flattened candidate stream (round-2 experiment, measured SLOWER than
+    // the default 8-lanes-per-centre query: 180 vs 132 us at batch 256, r = 0.2 -- 804 vs 633 warp-instructions per centre, the
+    // per-lane run cursor and the 32-lane read-back cost more than the idle lanes they remove; profiles/ncu_ball_query_r2.csv)
+    static const bool wpc = [] { const char* e = getenv("DFB200_BQ_QUERY"); return e != nullptr && e[0] == 'w'; }();
+    auto kernel = wpc ? ball_query_grid_kernel<true> : ball_query_grid_kernel<false>;
+    DFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    int per_sm = 0;  // resident CTAs per SM (registers AND shared memory): more CTAs than that would run as a second, unbalanced wave
+    DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BQG_T, gsm));
     per_sm = per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm);
     const int ppc = cdiv(m, BQG_T / BQG_LPC);  // passes of 32 centres per cloud
-    const long long items = (long long)b * ppc, slots = 148LL * per_sm;
+    const int n_sm = current_device_sm_count();
+    const long long items = (long long)b * ppc, slots = (long long)(n_sm > 0 ? n_sm : 148) * per_sm;
     int ctas;
     if (2LL * b <= slots) {  // few clouds: k CTAs per cloud (slices never straddle two clouds -> one build each)
       const int k = (int)(slots / b < ppc ? slots / b : ppc);
@@ -1366,7 +1481,6 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
     } else {
       ctas = (int)(items < slots ? items : slots);
     }
-    DFB_CUDA(cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
     int scpw = 8;
     while (scpw > 1 && (long long)b * cdiv(m, 8 * scpw) < 148 * 4) scpw /= 2;
     int mpad = 0;  // centres are sorted by cell when they fit the key array
@@ -1375,8 +1489,8 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
       while (mpad < m) mpad <<= 1;
     }
     static const int min_occ = [] { const char* e = getenv("DFB200_BQ_MIN_OCCUPIED"); return e != nullptr ? atoi(e) : BQG_MIN_OCCUPIED; }();
-    ball_query_grid_kernel<<<ctas, BQG_T, gsm, st>>>(b, n, m, mpad, (int)bqg_keys_offset(n), min_occ, radius, radius2, nsample,
-                                                    8 * scpw, new_xyz, xyz, idx);
+    if (wpc) mpad = 0;  // no centre sorting: a warp works on one centre at a time
+    kernel<<<ctas, BQG_T, gsm, st>>>(b, n, m, mpad, (int)bqg_keys_offset(n), min_occ, radius, radius2, nsample, 8 * scpw, new_xyz, xyz, idx);
     DFB_LAUNCH_CHECK();
     const size_t ssm = sizeof(float) * 3 * (size_t)((n + 3) & ~3);
     if (ssm > 48 * 1024)
