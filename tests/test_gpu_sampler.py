@@ -157,3 +157,56 @@ def test_philox_normals_are_standard_normal():
     assert abs((a[:-1] * a[1:]).mean().item()) < 2e-3 and abs((a[0::2] * a[1::2]).mean().item()) < 2e-3  # lag-1 / in-pair correlation
     assert abs((z[0] * z[1]).double().mean().item()) < 2e-3 and abs((z[0] * z[2]).double().mean().item()) < 2e-3
     assert not torch.equal(z[0], z[1]) and not torch.equal(z[0], z[2])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_guidance_and_ddim_generator_at_odd_shapes(precision):
+    """Units that straddle samples (N = 384: a 128-token tile per unit in guidance mode, 256-token units otherwise), an odd batch,
+    a strided DDIM list served through the chunked generator (chunk = 3 steps -> several launches with tables_ready), all against
+    the step-wise generator from the same torch seed."""
+    T, B, N = 40, 3, 384
+    d = build_variant(T, precision, guidance=True, classifier_weight=1.5, ddim_sampling=True, ddim_nsteps=7, ddim_discretize="uniform",
+                      ddim_eta=0.7)
+    i = dev(R.synthetic_inputs(33, B, N, False))
+    kw = dict(anchors=i["anchors"], ctx=[i["code"], i["params"]], variance=i["variance"], anchor_assignment=i["assign"], valid_id=i["valid"])
+    torch.manual_seed(8)
+    slow = list(d.p_sample_loop_progressive([B, 3, N], fused=False, **kw))
+    torch.manual_seed(8)
+    fast = list(d.p_sample_loop_progressive([B, 3, N], chunk=3, **kw))
+    assert [t for t, _ in fast] == [t for t, _ in slow] == [T] + list(d.steps[::-1])
+    tol = 1e-6 if precision == "fp32" else 5e-3 if precision == "tf32" else 5e-2  # tensor-core modes: hoisted K/V tables (see above), x |w|+|1-w| = 2
+    for (_, a), (_, b) in zip(fast, slow):
+        for k in a:
+            assert (a[k] - b[k]).abs().max().item() <= tol, (k, (a[k] - b[k]).abs().max().item())
+
+
+def test_sample_loop_rejects_bad_arguments():
+    """Status codes instead of undefined behaviour: unsorted step lists, ranges outside the list, DDIM without its tables,
+    a workspace that is too small."""
+    from difffacto_b200 import _lib
+    lib = _lib.load()
+    T, B, N = 10, 1, 128
+    d = build(T, "bf16")
+    i = dev(R.synthetic_inputs(1, B, N, True))
+    st = d._loop_state(B, N, i["anchors"], [i["code"], i["params"]], i["variance"], i["assign"], i["valid"], torch.device("cuda"))
+    x = torch.zeros(B, 3, N, device="cuda")
+
+    def call(o, ws_bytes=None):
+        return lib.dfb200_sample_loop(st["cfg"], _lib.ptr(st["packed"]), st["mode"], B, N, T, _lib.ptr(st["sched"]), _lib.ptr(x), 0,
+                                      _lib.ptr(st["ctx"]), _lib.ptr(st["anchors"]), _lib.ptr(st["variance"]), _lib.ptr(st["assign"]),
+                                      _lib.ptr(st["valid"]), None, 1, None, 1, o, _lib.ptr(st["ws"]), st["nws"] if ws_bytes is None else ws_bytes,
+                                      _lib.stream())
+    bad = torch.tensor([5, 7, 2], dtype=torch.int32, device="cuda")
+    o = _lib.SampleOpts()
+    o.timesteps, o.timesteps_host, o.n_timesteps = bad.data_ptr(), (_lib.c_int * 3)(5, 7, 2), 3
+    assert call(o) == 1 and b"strictly decreasing" in lib.dfb200_last_error()
+    o = _lib.SampleOpts()
+    o.first_step, o.num_steps = 8, 5
+    assert call(o) == 1 and b"outside the list" in lib.dfb200_last_error()
+    o = _lib.SampleOpts()
+    o.ddim = 1
+    assert call(o) == 1 and b"DDIM" in lib.dfb200_last_error()
+    assert call(_lib.SampleOpts(), ws_bytes=16) == 4 and b"workspace too small" in lib.dfb200_last_error()
+    assert call(_lib.SampleOpts()) == 0  # and the all-defaults call runs
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
