@@ -374,6 +374,7 @@ struct TcParams {
   long long M;
   long long* dbg;  // optional timeline buffer: CTA 0 records clock64() at the phase boundaries of its dbg_item-th work item
   int dbg_item;
+  int abl;  // diagnostic build only: ablation bits (timing experiments, results invalid): 1 no GEGLU math, 2 no FF LDTM, 4 no ring copies, 8 no FF-in MMAs, 16 no FF-out MMAs
   // persistent work list: item idx = step_local * n_units + unit, CTA c takes idx = c, c + gridDim.x, ...
   int n_units, n_steps, t_first;  // units of 2 tiles; timesteps t_first, t_first-1, ... (n_steps of them) unless step_t is given
   const int* step_t;              // optional device list of this launch's timesteps in execution order (DDIM strides)
@@ -423,11 +424,13 @@ __device__ __forceinline__ float2 geglu2(float2 a_half, float2 g, float2 ba_half
 // timeline instrumentation (diagnostic build only, and off unless a buffer is supplied): slot layout [who][event],
 // who 0 = tile-0 row 0, 1 = MMA lane
 #ifdef DFB200_DIAGNOSTICS
+#define ABL(bit) ((P.abl & (bit)) != 0)
 #define TL(who, ev)                                                                                  \
   do {                                                                                               \
     if (P.dbg != nullptr && blockIdx.x == 0 && item_n == P.dbg_item && tl_on) P.dbg[(who) * 512 + (ev)] = clock64(); \
   } while (0)
 #else
+#define ABL(bit) false
 #define TL(who, ev) do { (void)tl_on; } while (0)
 #endif
 
@@ -716,14 +719,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           tc_fence_after();
           if (TT == 0) TL(0, 8 + l * 40 + c * 2);
           float a[32], gt[32];
-          tmem_ld32(ACCt, a);
-          tmem_ld32(ACCt + 64, gt);
+#ifdef DFB200_DIAGNOSTICS
+#pragma unroll
+          for (int k = 0; k < 32; ++k) a[k] = gt[k] = 0.f;
+          if (!ABL(2))
+#endif
+          {
+            tmem_ld32(ACCt, a);
+            tmem_ld32(ACCt + 64, gt);
+          }
           tmem_wait_ld();
           uint32_t u[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float2 y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]), f2(ba[2 * k], ba[2 * k + 1]),
-                                    f2(bg[2 * k], bg[2 * k + 1]));
+            float2 y;
+            if (ABL(1))  // diagnostic build: no GEGLU math (timing experiment, results invalid)
+              y = f2(a[2 * k] + ba[2 * k] + bg[2 * k + 1], gt[2 * k + 1] + a[2 * k + 1] + gt[2 * k] + ba[2 * k + 1] + bg[2 * k]);
+            else
+              y = geglu2(f2(a[2 * k], a[2 * k + 1]), f2(gt[2 * k], gt[2 * k + 1]), f2(ba[2 * k], ba[2 * k + 1]), f2(bg[2 * k], bg[2 * k + 1]));
             u[k] = pack_bf16(y.x, y.y);
           }
           tmem_st16(ACCt, u);
@@ -873,8 +886,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
     // H_c(T) = LN3(x_T) W1'_c^T -> ACC_T (128 columns: 64 value | 64 gate); the bias b1'_c is added by the GEGLU epilogue
     auto ff_in = [&](int T, uint32_t pa, uint32_t pb) {
       const uint32_t d = 256 + T * 128, at = a_base + T * 32768;
+      if (!ABL(8)) {
       umma_gemm<128, 4>(d, at, pa, idesc128, 0u);
       umma_gemm<128, 4>(d, at + 4 * 4096, pb, idesc128, 1u);
+      }
       umma_commit(&bars[BAR_ACC + T]);
     };
     int item_n = 0;
@@ -952,10 +967,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           if (T == 0) TL(1, 8 + l * 40 + c * 2);
           wait_u(T);
           if (T == 0) TL(1, 9 + l * 40 + c * 2);
+#ifdef DFB200_DIAGNOSTICS
+          if (ABL(32) || ABL(64)) {  // idle cycles on the critical chain (no work, ~no energy): is the sustained rate cycle- or power-bound?
+            const long long t_end = clock64() + (ABL(64) ? 300 : 150);
+            while (clock64() < t_end) __nanosleep(20);
+          }
+#endif
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d = T * 128;
             // x_T += U_T W2_c^T with U read from TMEM (8 columns per K=16 step; k [0,32) at columns [0,16), k [32,64) at [32,48))
+            if (!ABL(16))
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_bf16_ts(d, 256 + T * 128 + (ks >> 1) * 32 + (ks & 1) * 8, make_smem_desc(pw2 + ks * 4096, 2048, TILE_SBO), idesc128, 1u);
@@ -1011,8 +1033,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) denoiser_tc_kernel(const TcPara
           const uint32_t bytes = (uint32_t)pkt_bytes(p);
           const uint8_t* src = p < 2 ? fold + ((size_t)(p == 0 ? b0 : b1) * P.depth + l) * FOLD_BYTES
                                      : P.stream + ((size_t)l * STATIC_PER_LAYER + (p - 2)) * SLOT_BYTES;
+          if (ABL(4) && p >= 2 && G >= NSLOT) {
+            mbar_arrive(&bars[BAR_WFULL + slot]);
+          } else {
           mbar_arrive_expect_tx(&bars[BAR_WFULL + slot], bytes);
           bulk_g2s(smem + SM_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_WFULL + slot]);
+          }
         }
         __syncwarp();
       }
@@ -1072,6 +1098,7 @@ int denoiser_step_tc(const PackLayout& L, const void* packed, int B, int N, cons
 #ifdef DFB200_DIAGNOSTICS
   p.dbg = g_tc_timeline;
   p.dbg_item = g_tc_timeline_item;
+  { const char* e = getenv("DFB200_TC_ABLATE"); p.abl = e != nullptr ? atoi(e) : 0; }
 #endif
   p.B = B;
   p.guidance = upd != nullptr && upd->guidance;
