@@ -126,8 +126,9 @@ def load():
     DFB200_DIAGNOSTICS=1 in the environment makes the whole package run on the diagnostic build (tools/diag_*.py)."""
     global _lib
     if _lib is None:
+        # DFB200_LIB_PATH: A/B measurements of two builds of THIS library on one box (tools/); never a fallback
         _lib = load_diag() if os.environ.get("DFB200_DIAGNOSTICS") == "1" else \
-            _open(LIB_PATH, SIGNATURES, "python -m difffacto_b200.build")
+            _open(os.environ.get("DFB200_LIB_PATH") or LIB_PATH, SIGNATURES, "python -m difffacto_b200.build")
     return _lib
 
 
