@@ -7,7 +7,8 @@
 // One CTA (256 threads) owns a 128 x 128 output tile.  Operands are read as fp32 from global memory in either layout
 // (k-contiguous or row-contiguous), converted to bf16 in registers and written as canonical K-major no-swizzle UMMA tiles
 // (16-byte chunks, conflict-free) into a 2-stage shared-memory ring of 64-deep k-slices; one thread issues the 4 K=16 MMAs
-// of a slice and commits to the slice's mbarrier, so staging of slice i+1 overlaps the MMAs of slice i.  gridDim.z > 1
+// of a slice and commits to the slice's mbarrier.  Round 2: the operands of slice i+1 are requested into registers (64 per thread)
+// before slice i's barrier, so their global-memory latency overlaps the MMAs and the other resident CTAs.  gridDim.z > 1
 // splits K (wgrad reduces over the B*N token rows) with an atomicAdd epilogue.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -18,36 +19,53 @@ using namespace tc;
 constexpr int GT_M = 128, GT_N = 128, GT_K = 64, GT_THREADS = 256;
 constexpr uint32_t GT_TILE_BYTES = GT_M * GT_K * 2;  // 16 KB per operand per stage
 
-// Stage rows [r0, r0+128) x k [k0, k0+64) of an operand as a bf16 UMMA tile (R = 128).  KC: element (r,k) = P[r*ld + k];
-// else P[k*ld + r].  256 threads: thread -> (row = tid % 128, k-half = tid / 128) handles 4 chunks of 8 k-values.
+// Staging of rows [r0, r0+128) x k [k0, k0+64) of an operand as a bf16 UMMA tile (R = 128), in TWO phases so that all global
+// loads of a k-slice (both operands) are in flight together: gt_load fetches the thread's 4 chunks of 8 k-values into
+// registers, gt_store converts and writes them.  (Round 1 fetched, converted and stored chunk by chunk: 16 dependent
+// global-memory round trips per slice -- ncu showed 62 % of the stall samples on the first F2FP after each load pair.)
+// KC: element (r,k) = P[r*ld + k]; else P[k*ld + r].
+//   KC mapping: thread -> rows rblk*16 + rsub + 8j (rsub = tid % 8), chunks kq + 4i (kq = (tid / 8) % 4): a warp-wide LDG.128
+//     touches 8 rows x 128 contiguous bytes (8 cache lines; the row-per-lane mapping of round 1 touched 32), and a quarter warp
+//     stores 8 consecutive rows of one chunk (conflict-free STS.128).
+//   row-contiguous mapping: thread -> row tid % 128, chunks (tid / 128) * 4 + ch; lanes read consecutive rows of one k (coalesced).
 template <bool KC>
-__device__ __forceinline__ void gt_stage(uint8_t* tile, const float* __restrict__ P, int ld, int r0, int rows, int k0, int kend) {
-  const int r = threadIdx.x & 127, kh = threadIdx.x >> 7;
-  const int gr = r0 + r;
+__device__ __forceinline__ void gt_load(float (&v)[4][8], const float* __restrict__ P, int ld, int r0, int rows, int k0, int kend, bool vec_ok) {
+  const int t = threadIdx.x;
+  if (KC) {
+    const int rsub = t & 7, kq = (t >> 3) & 3, rblk = t >> 5;
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    const int kc = kh * 4 + ch;          // chunk (k-slab) index inside the slice: k = k0 + 8*kc .. +8
-    const int gk = k0 + kc * 8;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (gr < rows) {
-      if (KC) {
-        const float* p = P + (size_t)gr * ld + gk;
-        if (gk + 7 < kend && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) if (gk + e < kend) v[e] = __ldg(p + e);
-        }
+    for (int c = 0; c < 4; ++c) {
+      const int j = c >> 1, i = c & 1;
+      const int gr = r0 + rblk * 16 + rsub + 8 * j, gk = k0 + (kq + 4 * i) * 8;
+      const float* p = P + (size_t)gr * ld + gk;
+      if (vec_ok && gr < rows && gk + 7 < kend) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) if (gk + e < kend) v[e] = __ldg(P + (size_t)(gk + e) * ld + gr);  // coalesced over rows
+        for (int e = 0; e < 8; ++e) v[c][e] = (gr < rows && gk + e < kend) ? __ldg(p + e) : 0.f;
       }
     }
+  } else {
+    const int r = t & 127, kh = t >> 7, gr = r0 + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int gk = k0 + (kh * 4 + c) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[c][e] = (gr < rows && gk + e < kend) ? __ldg(P + (size_t)(gk + e) * ld + gr) : 0.f;
+    }
+  }
+}
+template <bool KC>
+__device__ __forceinline__ void gt_store(uint8_t* tile, const float (&v)[4][8]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int r, kc;
+    if (KC) { r = (t >> 5) * 16 + (t & 7) + 8 * (c >> 1); kc = ((t >> 3) & 3) + 4 * (c & 1); }
+    else { r = t & 127; kc = (t >> 7) * 4 + c; }
     *reinterpret_cast<uint4*>(tile + kc * (GT_M * 16) + r * 16) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        make_uint4(pack_bf16(v[c][0], v[c][1]), pack_bf16(v[c][2], v[c][3]), pack_bf16(v[c][4], v[c][5]), pack_bf16(v[c][6], v[c][7]));
   }
 }
 
@@ -72,14 +90,26 @@ gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const 
   const uint32_t idesc = make_idesc_bf16(GT_M, GT_N);
   uint32_t ph[2] = {0, 0};
   int it = 0;
+  // 16-byte loads need k-contiguous rows that start on 16-byte boundaries (uniform per launch)
+  const bool a_vec = A_KC && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (kbeg % 4 == 0);
+  const bool b_vec = B_KC && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (kbeg % 4 == 0);
+  float va[4][8], vb[4][8];
+  if (kbeg < kend) {
+    gt_load<A_KC>(va, A, lda, i0, M, kbeg, kend, a_vec);
+    gt_load<B_KC>(vb, B, ldb, j0, N, kbeg, kend, b_vec);
+  }
   for (int k0 = kbeg; k0 < kend; k0 += GT_K, ++it) {
     const int s = it & 1;
     if (it >= 2) {  // the MMAs that read this stage two slices ago have completed
       mbar_wait(&bars[s], ph[s]);
       ph[s] ^= 1;
     }
-    gt_stage<A_KC>(a_tiles + s * GT_TILE_BYTES, A, lda, i0, M, k0, kend);
-    gt_stage<B_KC>(b_tiles + s * GT_TILE_BYTES, B, ldb, j0, N, k0, kend);
+    gt_store<A_KC>(a_tiles + s * GT_TILE_BYTES, va);
+    gt_store<B_KC>(b_tiles + s * GT_TILE_BYTES, vb);
+    if (k0 + GT_K < kend) {  // the next slice's operands fly while this slice's MMAs run
+      gt_load<A_KC>(va, A, lda, i0, M, k0 + GT_K, kend, a_vec);
+      gt_load<B_KC>(vb, B, ldb, j0, N, k0 + GT_K, kend, b_vec);
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {

@@ -326,11 +326,12 @@ timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__
 // Inverted dropout with a counter-based mask (Philox, one draw per 4 elements): y = (keep ? x / (1 - p) : 0) (+ residual).  The backward
 // pass calls the same kernel on the incoming gradient with the same (seed, offset).
 __global__ void __launch_bounds__(256)
-dropout_kernel(long long total, float p, float scale, uint64_t seed, uint64_t offset, const float* __restrict__ x,
-               const float* __restrict__ residual, float* __restrict__ y) {
+dropout_kernel(long long total, float p, float scale, uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ step,
+               const float* __restrict__ x, const float* __restrict__ residual, float* __restrict__ y) {
   const long long q4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long e = q4 * 4;
   if (e >= total) return;
+  if (step != nullptr) seed += (uint64_t)__ldg(step) * 0x9E3779B97F4A7C15ull;  // device-side step counter (CUDA-graph replays)
   uint32_t r[4];
   philox4x32_10((uint64_t)q4, offset, seed, r);
 #pragma unroll
@@ -458,7 +459,17 @@ extern "C" int dfb200_dropout(size_t count, float p, uint64_t seed, uint64_t off
   DFB_REQUIRE(p >= 0.f && p < 1.f, DFB200_ERR_INVALID_ARG, "dropout: p must be in [0, 1)");
   if (count == 0) return DFB200_OK;
   dropout_kernel<<<(unsigned)cdiv((long long)((count + 3) / 4), 256LL), 256, 0, as_stream(stream)>>>((long long)count, p, 1.f / (1.f - p), seed,
-                                                                                                     offset, x, residual, y);
+                                                                                                     offset, nullptr, x, residual, y);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_dropout_stepped(size_t count, float p, uint64_t seed, uint64_t offset, const unsigned long long* step, const float* x,
+                                      const float* residual, float* y, dfb200_stream_t stream) {
+  DFB_REQUIRE(p >= 0.f && p < 1.f, DFB200_ERR_INVALID_ARG, "dropout: p must be in [0, 1)");
+  if (count == 0) return DFB200_OK;
+  dropout_kernel<<<(unsigned)cdiv((long long)((count + 3) / 4), 256LL), 256, 0, as_stream(stream)>>>((long long)count, p, 1.f / (1.f - p), seed,
+                                                                                                     offset, step, x, residual, y);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

@@ -213,6 +213,14 @@ class TransformerNet(nn.Module):
         u = T.dropout(T.geglu(h), self.dropout, self.training)
         return T.linear(u, ff.net[2].weight, ff.net[2].bias, residual)
 
+    def _freqs_on(self, dev):
+        """The 128 sinusoid frequencies of timestep_embedding (nets/utils.py:7-24), resident per device (a host-side build +
+        upload inside the forward would not be capturable in a CUDA graph)."""
+        cache = self.__dict__.setdefault("_freqs_cache", {})
+        if dev not in cache:
+            cache[dev] = torch.exp(-math.log(10000) * torch.arange(start=0, end=128, dtype=torch.float32) / 128).to(dev)
+        return cache[dev]
+
     def _forward_train(self, x, t, ctx, anchors, variances, valid_id, anchor_assignment):
         """Reference attention.py:385-440 (+ :296-306, :179-204) on the differentiable primitives; fp32."""
         _lib.require_cuda(x, ctx, anchors, variances, anchor_assignment, valid_id)
@@ -221,12 +229,13 @@ class TransformerNet(nn.Module):
         B, C, N = x.shape
         f32 = torch.float32
         dev = x.device
+        T.begin_step()
         if torch.is_grad_enabled():  # one zero fill for all atomically accumulated gradients of this step's backward pass
             T.begin_zero_arena(dev, sum(p.numel() for p in self.parameters()) + 2 * self.depth * B * self.n_class * 128 + 64 * 160)
         # context (B,4,522) = [part code | mean, var | one-hot class | t_embed]  (:389-398)
         ctx = ctx.to(f32).transpose(1, 2)
         class_embed = torch.eye(self.n_class, device=dev, dtype=f32).unsqueeze(0).expand(B, -1, -1)
-        freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=128, dtype=f32) / 128).to(dev)
+        freqs = self._freqs_on(dev)
         t_embed = self._ff(self.time_embed, T.timestep_embedding(t, freqs))
         ctx = torch.cat([ctx, class_embed, t_embed.unsqueeze(1).expand(-1, self.n_class, -1)], dim=-1).contiguous()
         ctx2d = ctx.reshape(B * self.n_class, self.context_dim)

@@ -216,19 +216,43 @@ def part_attention(q, k, v, valid, B, N):
 
 
 _dropout_calls = 0
+_step_counter = None   # device int64 tensor (1,) while a training step is captured / replayed as a CUDA graph (train_graph.py)
+_step_seed = 0
+
+
+def set_step_counter(counter, seed=0):
+    """counter: a (1,) int64 CUDA tensor that the caller increments once per training step, or None (default).  While it is
+    set, dropout() keys its masks by (seed, call index within the step, *counter) and touches neither the host generator nor
+    the process-wide call count: the launch sequence is identical on every step, as a CUDA-graph replay needs."""
+    global _step_counter, _step_seed, _step_calls
+    _step_counter, _step_seed, _step_calls = counter, int(seed), 0
+
+
+_step_calls = 0
+
+
+def begin_step():
+    """Resets the per-step dropout call index (called by TransformerNet._forward_train at the start of a forward pass)."""
+    global _step_calls
+    _step_calls = 0
 
 
 class DropoutFn(Function):
-    """y = dropout(x) (+ residual): inverted dropout with a Philox mask keyed by (seed, offset)."""
+    """y = dropout(x) (+ residual): inverted dropout with a Philox mask keyed by (seed, offset[, *step counter])."""
 
     @staticmethod
-    def forward(ctx, x, p, seed, offset, residual):
+    def forward(ctx, x, p, seed, offset, residual, counter):
         x = _c(x)
         y = torch.empty_like(x)
         with _lib.on(x.device):
-            check(_lib.load().dfb200_dropout(x.numel(), float(p), int(seed), int(offset), ptr(x), ptr(None if residual is None else _c(residual)),
-                                             ptr(y), stream()))
+            if counter is None:
+                check(_lib.load().dfb200_dropout(x.numel(), float(p), int(seed), int(offset), ptr(x),
+                                                 ptr(None if residual is None else _c(residual)), ptr(y), stream()))
+            else:
+                check(_lib.load().dfb200_dropout_stepped(x.numel(), float(p), int(seed), int(offset), ptr(counter), ptr(x),
+                                                         ptr(None if residual is None else _c(residual)), ptr(y), stream()))
         ctx.args = (float(p), int(seed), int(offset))
+        ctx.counter = counter
         ctx.has_res = residual is not None
         return y
 
@@ -238,20 +262,26 @@ class DropoutFn(Function):
         dx = torch.empty_like(dy)
         p, seed, offset = ctx.args
         with _lib.on(dy.device):
-            check(_lib.load().dfb200_dropout(dy.numel(), p, seed, offset, ptr(dy), None, ptr(dx), stream()))
-        return dx, None, None, None, (dy if ctx.has_res else None)
+            if ctx.counter is None:
+                check(_lib.load().dfb200_dropout(dy.numel(), p, seed, offset, ptr(dy), None, ptr(dx), stream()))
+            else:  # the counter is incremented after the optimizer step: forward and backward of a step see the same value
+                check(_lib.load().dfb200_dropout_stepped(dy.numel(), p, seed, offset, ptr(ctx.counter), ptr(dy), None, ptr(dx), stream()))
+        return dx, None, None, None, (dy if ctx.has_res else None), None
 
 
 def dropout(x, p, training, residual=None):
     """nn.Dropout (optionally fused with the residual add that follows it): identity in eval mode or for p == 0; the mask
     seed comes from torch's CPU generator (so torch.manual_seed makes a run reproducible), the offset counts the dropout
-    calls of the process."""
-    global _dropout_calls
+    calls of the process.  With a step counter set (CUDA-graph training, set_step_counter) the key is (seed, call index, *counter)."""
+    global _dropout_calls, _step_calls
     if not training or p == 0.0:
         return x if residual is None else x + residual
+    if _step_counter is not None:
+        _step_calls += 1
+        return DropoutFn.apply(x, p, _step_seed, _step_calls, residual, _step_counter)
     _dropout_calls += 1
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-    return DropoutFn.apply(x, p, seed, _dropout_calls, residual)
+    return DropoutFn.apply(x, p, seed, _dropout_calls, residual, None)
 
 
 def timestep_embedding(t, freqs):

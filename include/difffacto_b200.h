@@ -260,6 +260,10 @@ int dfb200_timestep_embedding(int B, const float* t, const float* freqs128, floa
  * NULL).  The backward pass applies the same call (without residual) to the incoming gradient. */
 int dfb200_dropout(size_t count, float p, uint64_t seed, uint64_t offset, const float* x, const float* residual, float* y,
                    dfb200_stream_t stream);
+/* The same with the mask additionally keyed by a DEVICE-resident step counter (*step is read by the kernel): a training step
+ * captured in a CUDA graph draws a fresh mask on every replay when the graph increments the counter (train_graph.py). */
+int dfb200_dropout_stepped(size_t count, float p, uint64_t seed, uint64_t offset, const unsigned long long* step, const float* x,
+                           const float* residual, float* y, dfb200_stream_t stream);
 /* Backward of dfb200_q_sample: any of the three outputs may be NULL. */
 int dfb200_q_sample_backward(int B, int N, int T, const float* sched, const int* t, const float* variance,
                              const float* noise, const float* grad_x_t, float* grad_x_start, float* grad_anchors,

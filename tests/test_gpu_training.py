@@ -151,3 +151,59 @@ def test_bf16_training_gradients_close_to_fp32():
     assert abs(res["bf16"][0] - res["fp32"][0]) < 2e-3 * max(1.0, abs(res["fp32"][0]))
     worst = max((_rel(res["bf16"][1][k], res["fp32"][1][k]), k) for k in res["fp32"][1])
     assert worst[0] < 5e-2, worst
+
+
+def _graph_inputs(seed, B, N):
+    inp = R.synthetic_inputs(seed, B, N, False)
+    return dict(x0=inp["x"].cuda(), t=inp["t"].cuda(), anchors=inp["anchors"].cuda(), variance=inp["variance"].cuda(), code=inp["code"].cuda(),
+                params=inp["params"].cuda(), assign=inp["assign"].cuda(), valid=inp["valid"].cuda(), flags=torch.ones(B, 1, N).cuda(),
+                noise=inp["noise"].cuda())
+
+
+def _loss_fn(d):
+    def f(x0, t, anchors, variance, code, params, assign, valid, flags, noise):
+        return d.training_losses(x0, t, anchors=anchors, variance=variance, ctx=[code, params], anchor_assignment=assign, valid_id=valid,
+                                 flags=flags, noise=noise)["mse_loss"]
+    return f
+
+
+def test_cuda_graph_training_step_equals_the_eager_step():
+    """difffacto_b200/train_graph.py: forward + backward + Adam replayed as ONE CUDA graph gives the losses and the weights of
+    the eager loop (dropout off so both draw no masks; the warm-up steps of the capture are part of the sequence on both sides)."""
+    from difffacto_b200.train_graph import GraphedTrainStep
+    B, N, steps, warm = 2, 256, 4, 3
+    batches = [_graph_inputs(40 + i, B, N) for i in range(1 + steps)]
+    # eager reference
+    d0 = _build(dropout=0.0).train()
+    opt0 = torch.optim.Adam(d0.parameters(), lr=1e-3, capturable=True)
+    # the capture runs `warm` eager steps on the example batch (the capture itself only records, it does not execute)
+    losses0 = []
+    for i in range(warm):
+        opt0.zero_grad(set_to_none=True)
+        l = _loss_fn(d0)(**batches[0]); l.backward(); opt0.step()
+    for i in range(steps):
+        opt0.zero_grad(set_to_none=True)
+        l = _loss_fn(d0)(**batches[1 + i]); l.backward(); opt0.step()
+        losses0.append(l.item())
+    # graphed
+    d1 = _build(dropout=0.0).train()
+    opt1 = torch.optim.Adam(d1.parameters(), lr=1e-3, capturable=True)
+    step = GraphedTrainStep(_loss_fn(d1), list(d1.parameters()), opt1, batches[0], warmup=warm)
+    losses1 = [step(**batches[1 + i]).item() for i in range(steps)]
+    assert np.allclose(losses0, losses1, rtol=2e-4, atol=1e-6), (losses0, losses1)
+    for (k, p0), (_, p1) in zip(d0.model.named_parameters(), d1.model.named_parameters()):
+        assert _rel(p1.detach(), p0.detach()) < 2e-3, k  # split-K atomics: summation order differs run to run
+
+
+def test_cuda_graph_training_step_draws_a_fresh_dropout_mask_per_replay():
+    """With dropout on, the replayed graph reads the device step counter: the same batch gives a different loss on every replay
+    (same weights up to a tiny Adam step), and the counter advances by one per step."""
+    from difffacto_b200.train_graph import GraphedTrainStep
+    d = _build(dropout=0.2).train()
+    opt = torch.optim.Adam(d.parameters(), lr=1e-8, capturable=True)
+    b = _graph_inputs(77, 2, 256)
+    step = GraphedTrainStep(_loss_fn(d), list(d.parameters()), opt, b, warmup=3)
+    c0 = int(step.counter.item())
+    losses = [step(**b).item() for _ in range(4)]
+    assert int(step.counter.item()) == c0 + 4
+    assert all(np.isfinite(losses)) and len({round(l, 7) for l in losses}) == 4, losses

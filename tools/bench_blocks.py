@@ -276,18 +276,31 @@ def train_block(torch, dist, build_model, synthetic_batch, world, rank, local, f
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     x0 = torch.sqrt(b["variance"]) * torch.randn(B, 3, N, device=dev, generator=g) + b["anchors"]
     flags = torch.ones(B, 1, N, device=dev)
-    opt = torch.optim.Adam(d.parameters(), lr=1e-4, fused=True)
+    graphed = world == 1  # one CUDA graph per step (difffacto_b200/train_graph.py); under DDP the step is issued eagerly
+    opt = torch.optim.Adam(d.parameters(), lr=1e-4, fused=True, capturable=graphed)
     ts, loss = [], None
+
+    def loss_fn(x0, t, anchors, variance, code, params, assign, valid, flags):
+        kw = dict(anchors=anchors, variance=variance, ctx=[code, params], anchor_assignment=assign, valid_id=valid, flags=flags)
+        return (model(x0, t, **kw) if world > 1 else d.training_losses(x0, t, **kw))["mse_loss"]
+
+    inputs = dict(x0=x0, t=torch.randint(0, T, (B,), device=dev, generator=g), anchors=b["anchors"], variance=b["variance"], code=b["code"],
+                  params=b["params"], assign=b["assign"], valid=b["valid"], flags=flags)
+    step = None
+    if graphed:
+        from difffacto_b200.train_graph import GraphedTrainStep
+        step = GraphedTrainStep(loss_fn, list(d.parameters()), opt, inputs)
     for it in range(warm + iters):
-        t = torch.randint(0, T, (B,), device=dev, generator=g)
+        inputs["t"] = torch.randint(0, T, (B,), device=dev, generator=g)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        opt.zero_grad(set_to_none=True)
-        kw = dict(anchors=b["anchors"], variance=b["variance"], ctx=[b["code"], b["params"]], anchor_assignment=b["assign"],
-                  valid_id=b["valid"], flags=flags)
-        loss = (model(x0, t, **kw) if world > 1 else d.training_losses(x0, t, **kw))["mse_loss"]
-        loss.backward()
-        opt.step()
+        if step is not None:
+            loss = step(**inputs)  # copies the batch into the graph's static buffers, replays fwd + bwd + Adam
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(**inputs)
+            loss.backward()
+            opt.step()
         e1.record()
         torch.cuda.synchronize()
         if it >= warm:
@@ -300,5 +313,6 @@ def train_block(torch, dist, build_model, synthetic_batch, world, rank, local, f
     flop = 3 * B * N * flop_per_point_step
     return {"ms_per_step": round(ms, 3), "shapes_per_s": round(B * world / ms * 1e3, 1), "batch_per_gpu": B, "global_batch": B * world,
             "algorithmic_TFLOPs_per_gpu": round(flop / ms / 1e9, 1), "n_gpus": world, "loss": float(loss.detach()),
-            "what": "denoiser training step (fwd+bwd+fused Adam), bf16 tcgen05 GEMMs, DDP over NCCL when n_gpus > 1; "
-                    "algorithmic FLOP = 3 x forward"}
+            "cuda_graph": bool(graphed),
+            "what": "denoiser training step (fwd+bwd+fused Adam), bf16 tcgen05 GEMMs; one CUDA graph per step at 1 GPU, eager under "
+                    "DDP over NCCL when n_gpus > 1; algorithmic FLOP = 3 x forward"}
