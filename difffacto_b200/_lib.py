@@ -70,6 +70,8 @@ SIGNATURES = {
     "dfb200_part_attention_forward": (c_int, [c_int, c_int] + [P] * 7),
     "dfb200_part_attention_backward": (c_int, [c_int, c_int] + [P] * 10),
     "dfb200_timestep_embedding": (c_int, [c_int, P, P, P, P]),
+    "dfb200_geglu_dropout_forward": (c_int, [ctypes.c_longlong, c_int, c_float, c_u64, c_u64, P, P, P, P]),
+    "dfb200_geglu_dropout_backward": (c_int, [ctypes.c_longlong, c_int, c_float, c_u64, c_u64, P, P, P, P, P, P]),
     "dfb200_dropout": (c_int, [c_size_t, c_float, c_u64, c_u64, P, P, P, P]),
     "dfb200_dropout_stepped": (c_int, [c_size_t, c_float, c_u64, c_u64, P, P, P, P, P]),
     "dfb200_q_sample_backward": (c_int, [c_int] * 3 + [P] * 9),

@@ -39,8 +39,11 @@ __device__ __forceinline__ void gt_load(float (&v)[4][8], const float* __restric
       const int gr = r0 + rblk * 16 + rsub + 8 * j, gk = k0 + (kq + 4 * i) * 8;
       const float* p = P + (size_t)gr * ld + gk;
       if (vec_ok && gr < rows && gk + 7 < kend) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+        // one 256-bit load per chunk (LDG.E.256, sm_100): every 32-byte sector is requested once (two 128-bit loads touched
+        // each sector twice, and the L1 data pipe -- 73 % busy in the ncu capture of round 2 -- is what bounds this kernel)
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[c][0]), "=f"(v[c][1]), "=f"(v[c][2]), "=f"(v[c][3]), "=f"(v[c][4]), "=f"(v[c][5]), "=f"(v[c][6]), "=f"(v[c][7])
+                     : "l"(p));
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[c][e] = (gr < rows && gk + e < kend) ? __ldg(p + e) : 0.f;
@@ -90,9 +93,9 @@ gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const 
   const uint32_t idesc = make_idesc_bf16(GT_M, GT_N);
   uint32_t ph[2] = {0, 0};
   int it = 0;
-  // 16-byte loads need k-contiguous rows that start on 16-byte boundaries (uniform per launch)
-  const bool a_vec = A_KC && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (kbeg % 4 == 0);
-  const bool b_vec = B_KC && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (kbeg % 4 == 0);
+  // 32-byte loads need k-contiguous rows that start on 32-byte boundaries (uniform per launch)
+  const bool a_vec = A_KC && (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 31) == 0) && (kbeg % 8 == 0);
+  const bool b_vec = B_KC && (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(B) & 31) == 0) && (kbeg % 8 == 0);
   float va[4][8], vb[4][8];
   if (kbeg < kend) {
     gt_load<A_KC>(va, A, lda, i0, M, kbeg, kend, a_vec);

@@ -207,6 +207,81 @@ geglu_bwd_kernel(long long total, int H, const float* __restrict__ h, const floa
   dh[row * 2 * H + H + c] = d * a * (cdf + g * pdf);
 }
 
+// GEGLU fused with the Dropout that follows it in FeedForward (attention.py:77-94: Sequential(GEGLU, Dropout, Linear)) and, in the
+// backward pass, with the bias gradient of the Linear in front of it (column sums of dh).  Round 2: the unfused chain wrote and
+// re-read the (M, H) activation for the dropout and re-read the (M, 2H) gradient for the column sums.  A thread owns 4 consecutive
+// hidden units (float4); the dropout mask is the one dfb200_dropout would draw on u (Philox quad = element index / 4), so fused
+// and unfused paths are interchangeable.  p == 0: no mask.  Requires H % 4 == 0.
+__device__ __forceinline__ void dropout_keep4(float p, float scale, uint64_t seed, uint64_t offset, long long quad, float (&m)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint64_t)quad, offset, seed, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = ((float)(r[i] >> 8) * 5.9604644775390625e-8f >= p) ? scale : 0.f;
+}
+__global__ void __launch_bounds__(256)
+geglu_dropout_fwd_kernel(long long quads, int H4, float p, float scale, uint64_t seed, uint64_t offset,
+                         const unsigned long long* __restrict__ step, const float4* __restrict__ h, float4* __restrict__ u) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= quads) return;
+  const long long row = q / H4;
+  const int c = (int)(q - row * H4);
+  const float4 a = __ldg(h + row * 2 * H4 + c), g = __ldg(h + row * 2 * H4 + H4 + c);
+  float m[4] = {1.f, 1.f, 1.f, 1.f};
+  if (p > 0.f) {
+    if (step != nullptr) seed += (uint64_t)__ldg(step) * 0x9E3779B97F4A7C15ull;
+    dropout_keep4(p, scale, seed, offset, q, m);
+  }
+  constexpr float RS2 = 0.70710678118654752440f;
+  u[q] = make_float4(m[0] * a.x * (0.5f * g.x * (1.f + erff(g.x * RS2))), m[1] * a.y * (0.5f * g.y * (1.f + erff(g.y * RS2))),
+                     m[2] * a.z * (0.5f * g.z * (1.f + erff(g.z * RS2))), m[3] * a.w * (0.5f * g.w * (1.f + erff(g.w * RS2))));
+}
+// grid (ceil(M / GD_ROWS), H4 / 128); block 256 = 128 quads x 2 row phases.  db_accum (2H floats, may be NULL) += column sums of dh.
+constexpr int GD_ROWS = 128;
+__global__ void __launch_bounds__(256)
+geglu_dropout_bwd_kernel(long long M, int H4, float p, float scale, uint64_t seed, uint64_t offset,
+                         const unsigned long long* __restrict__ step, const float4* __restrict__ h, const float4* __restrict__ du,
+                         float4* __restrict__ dh, float* __restrict__ db_accum) {
+  const int c = blockIdx.y * 128 + (threadIdx.x & 127), rs = threadIdx.x >> 7;
+  const long long r0 = (long long)blockIdx.x * GD_ROWS, r1 = min(M, r0 + GD_ROWS);
+  if (p > 0.f && step != nullptr) seed += (uint64_t)__ldg(step) * 0x9E3779B97F4A7C15ull;
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr float RS2 = 0.70710678118654752440f, IS2P = 0.39894228040143267794f;
+  if (c < H4) {
+#pragma unroll 2
+    for (long long row = r0 + rs; row < r1; row += 2) {
+      const float4 a4 = __ldg(h + row * 2 * H4 + c), g4 = __ldg(h + row * 2 * H4 + H4 + c), d4 = __ldg(du + row * H4 + c);
+      float m[4] = {1.f, 1.f, 1.f, 1.f};
+      if (p > 0.f) dropout_keep4(p, scale, seed, offset, row * H4 + c, m);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w}, d[4] = {d4.x * m[0], d4.y * m[1], d4.z * m[2], d4.w * m[3]};
+      float da[4], dg[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float cdf = 0.5f * (1.f + erff(g[i] * RS2));
+        const float pdf = IS2P * expf(-0.5f * g[i] * g[i]);
+        da[i] = d[i] * g[i] * cdf;
+        dg[i] = d[i] * a[i] * (cdf + g[i] * pdf);
+        sa[i] += da[i]; sg[i] += dg[i];
+      }
+      dh[row * 2 * H4 + c] = make_float4(da[0], da[1], da[2], da[3]);
+      dh[row * 2 * H4 + H4 + c] = make_float4(dg[0], dg[1], dg[2], dg[3]);
+    }
+  }
+  if (db_accum == nullptr) return;
+  __shared__ float part[128][8];
+  if (rs == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { part[threadIdx.x & 127][i] = sa[i]; part[threadIdx.x & 127][4 + i] = sg[i]; }
+  }
+  __syncthreads();
+  if (rs == 0 && c < H4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(db_accum + 4 * c + i, sa[i] + part[threadIdx.x][i]);
+      atomicAdd(db_accum + 4 * H4 + 4 * c + i, sg[i] + part[threadIdx.x][4 + i]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cross-attention core over the 4 part tokens (attention.py:183-203): 8 heads x 16, masked softmax over 4 keys.
 // Warp per token, lane = 4 of the 128 dims (head = lane / 4).  q/o (B*N,128), k/v (B,4,128), probs (B*N,8,4).
@@ -424,6 +499,29 @@ extern "C" int dfb200_geglu_backward(long long M, int H, const float* h, const f
   const long long total = M * H;
   if (total <= 0) return DFB200_OK;
   geglu_bwd_kernel<<<(unsigned)cdiv(total, 256LL), 256, 0, as_stream(stream)>>>(total, H, h, du, dh);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_geglu_dropout_forward(long long M, int H, float p, uint64_t seed, uint64_t offset, const unsigned long long* step,
+                                           const float* h, float* u, dfb200_stream_t stream) {
+  DFB_REQUIRE(H % 4 == 0 && p >= 0.f && p < 1.f, DFB200_ERR_INVALID_ARG, "geglu_dropout_forward: H %% 4 != 0 or p outside [0, 1) (H=%d)", H);
+  const long long quads = M * (H / 4);
+  if (quads <= 0) return DFB200_OK;
+  geglu_dropout_fwd_kernel<<<(unsigned)cdiv(quads, 256LL), 256, 0, as_stream(stream)>>>(quads, H / 4, p, 1.f / (1.f - p), seed, offset, step,
+                                                                                      reinterpret_cast<const float4*>(h),
+                                                                                      reinterpret_cast<float4*>(u));
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_geglu_dropout_backward(long long M, int H, float p, uint64_t seed, uint64_t offset, const unsigned long long* step,
+                                            const float* h, const float* du, float* dh, float* db_accum, dfb200_stream_t stream) {
+  DFB_REQUIRE(H % 4 == 0 && p >= 0.f && p < 1.f, DFB200_ERR_INVALID_ARG, "geglu_dropout_backward: H %% 4 != 0 or p outside [0, 1) (H=%d)", H);
+  if (M <= 0 || H <= 0) return DFB200_OK;
+  geglu_dropout_bwd_kernel<<<dim3((unsigned)cdiv(M, (long long)GD_ROWS), cdiv(H / 4, 128)), 256, 0, as_stream(stream)>>>(
+      M, H / 4, p, 1.f / (1.f - p), seed, offset, step, reinterpret_cast<const float4*>(h), reinterpret_cast<const float4*>(du),
+      reinterpret_cast<float4*>(dh), db_accum);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

@@ -209,8 +209,7 @@ class TransformerNet(nn.Module):
     # ---- training forward (differentiable) ----------------------------------------------------
     def _ff(self, ff, x, residual=None):
         """FeedForward (glu=True): Linear -> GEGLU -> Dropout -> Linear (reference attention.py:77-94)."""
-        h = T.linear(x, ff.net[0].proj.weight, ff.net[0].proj.bias)
-        u = T.dropout(T.geglu(h), self.dropout, self.training)
+        u = T.ff_in(x, ff.net[0].proj.weight, ff.net[0].proj.bias, self.dropout, self.training)  # Linear + GEGLU + Dropout, one node
         return T.linear(u, ff.net[2].weight, ff.net[2].bias, residual)
 
     def _freqs_on(self, dev):
@@ -247,11 +246,17 @@ class TransformerNet(nn.Module):
             valid = valid_id.to(f32).contiguous()
         h = T.linear(feat.contiguous(), self.proj_in.weight, self.proj_in.bias)
         h = T.layernorm128(h, self.pre_norm.weight, self.pre_norm.bias)
-        for blk in self.transformer_blocks:
+        # K / V of the 4 part tokens for ALL blocks in one GEMM (the context does not change over the blocks, :179-182): the
+        # 2 x depth projections of a (4B, 522) matrix were 10 launches of a single-wave kernel, forward, dgrad and wgrad alike;
+        # autograd's cat / slicing hand the gradient of the stacked weight back to the per-block parameters.
+        wkv = torch.cat([w for blk in self.transformer_blocks for w in (blk.attn2.to_k.weight, blk.attn2.to_v.weight)], dim=0)
+        kv_all = T.linear(ctx2d, wkv).view(B * self.n_class, 2 * len(self.transformer_blocks), self.inner_dim)
+        kv_parts = kv_all.transpose(0, 1).contiguous().unbind(0)  # 2 * depth tensors (4B, 128); backward = one stack
+        for li, blk in enumerate(self.transformer_blocks):
             a = T.layernorm128(h, blk.norm2.weight, blk.norm2.bias)
             q = T.linear(a, blk.attn2.to_q.weight)
-            k = T.linear(ctx2d, blk.attn2.to_k.weight).view(B, self.n_class, self.inner_dim)
-            v = T.linear(ctx2d, blk.attn2.to_v.weight).view(B, self.n_class, self.inner_dim)
+            k = kv_parts[2 * li].view(B, self.n_class, self.inner_dim)
+            v = kv_parts[2 * li + 1].view(B, self.n_class, self.inner_dim)
             o = T.part_attention(q, k, v, valid, B, N)
             if self.training and self.dropout > 0:  # to_out = [Linear, Dropout], then the residual add (:203, :303)
                 h = T.dropout(T.linear(o, blk.attn2.to_out[0].weight, blk.attn2.to_out[0].bias), self.dropout, True, residual=h)

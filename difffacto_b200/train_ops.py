@@ -185,6 +185,66 @@ def geglu(h):
     return GegluFn.apply(h)
 
 
+class FFInFn(Function):
+    """FeedForward's first half as ONE autograd node: u = dropout(geglu(x W1^T + b1)) (attention.py:77-94).  The GEGLU kernel
+    applies the dropout mask (same Philox stream as DropoutFn) and, in the backward pass, also produces the bias gradient (column
+    sums of dh), so neither the (M, H) activation nor the (M, 2H) gradient is read a second time."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p, seed, offset, counter):
+        x, weight = _c(x), _c(weight)
+        M, K = x.shape
+        H2 = weight.shape[0]
+        h = torch.empty(M, H2, device=x.device, dtype=torch.float32)
+        ctx.bf16 = _GEMM_BF16
+        _sgemm(True, True, M, H2, K, x, K, weight, K, h, H2, bias=bias, bf16=ctx.bf16)
+        u = torch.empty(M, H2 // 2, device=x.device, dtype=torch.float32)
+        with _lib.on(x.device):
+            check(_lib.load().dfb200_geglu_dropout_forward(M, H2 // 2, float(p), int(seed), int(offset), ptr(counter), ptr(h), ptr(u), stream()))
+        ctx.save_for_backward(x, weight, h)
+        ctx.args = (float(p), int(seed), int(offset))
+        ctx.counter, ctx.has_bias = counter, bias is not None
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        x, weight, h = ctx.saved_tensors
+        p, seed, offset = ctx.args
+        M, K = x.shape
+        H2 = weight.shape[0]
+        dh = torch.empty_like(h)
+        db = zeros((H2,), x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        with _lib.on(x.device):
+            check(_lib.load().dfb200_geglu_dropout_backward(M, H2 // 2, p, seed, offset, ptr(ctx.counter), ptr(h), ptr(_c(du)), ptr(dh), ptr(db),
+                                                            stream()))
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
+            _sgemm(True, False, M, K, H2, dh, H2, weight, K, dx, K, bf16=ctx.bf16)
+        if ctx.needs_input_grad[1]:
+            dw = zeros((H2, K), x.device)
+            tc = ctx.bf16 and H2 >= 128 and K >= 64 and M >= 64
+            t = 128 if tc else 64
+            tiles = ((H2 + t - 1) // t) * ((K + t - 1) // t)
+            split = max(1, min((M + 255) // 256, (148 * (2 if tc else 4) + tiles - 1) // tiles))
+            _sgemm(False, False, H2, K, M, dh, H2, x, K, dw, K, split_k=split, bf16=ctx.bf16)
+        return dx, dw, db, None, None, None, None
+
+
+def ff_in(x, weight, bias, p, training):
+    """dropout(geglu(linear(x))) of FeedForward; the dropout key follows dropout()'s conventions (host generator, or the device
+    step counter of a CUDA-graph step)."""
+    global _dropout_calls, _step_calls
+    if not training or p == 0.0:
+        return FFInFn.apply(x, weight, bias, 0.0, 0, 0, None)
+    if _step_counter is not None:
+        _step_calls += 1
+        return FFInFn.apply(x, weight, bias, p, _step_seed, _step_calls, _step_counter)
+    _dropout_calls += 1
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return FFInFn.apply(x, weight, bias, p, seed, _dropout_calls, None)
+
+
 class PartAttentionFn(Function):
     """softmax(q k^T / 4, masked) v over the 4 part tokens; q (B*N,128), k/v (B,4,128), valid (B,4) float or None."""
 

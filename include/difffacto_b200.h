@@ -256,6 +256,13 @@ int dfb200_part_attention_backward(int B, int N, const float* q, const float* k,
                                    dfb200_stream_t stream);
 /* timestep_embedding (nets/utils.py:7-24): out (B,256) = [cos(t f) | sin(t f)], f = the 128 frequencies. */
 int dfb200_timestep_embedding(int B, const float* t, const float* freqs128, float* out, dfb200_stream_t stream);
+/* FeedForward's GEGLU fused with the Dropout behind it (attention.py:77-94): u = dropout(a * gelu(g)) for h = [a | g] (M, 2H), with
+ * the mask dfb200_dropout(_stepped) would draw on u (p = 0: none; step may be NULL).  The backward also accumulates the column
+ * sums of dh (M, 2H) into db_accum (2H floats, may be NULL): the bias gradient of the Linear that produced h. */
+int dfb200_geglu_dropout_forward(long long M, int H, float p, uint64_t seed, uint64_t offset, const unsigned long long* step,
+                                 const float* h, float* u, dfb200_stream_t stream);
+int dfb200_geglu_dropout_backward(long long M, int H, float p, uint64_t seed, uint64_t offset, const unsigned long long* step,
+                                  const float* h, const float* du, float* dh, float* db_accum, dfb200_stream_t stream);
 /* Inverted dropout with a Philox mask keyed by (seed, offset): y = (keep ? x/(1-p) : 0) + residual (residual may be
  * NULL).  The backward pass applies the same call (without residual) to the incoming gradient. */
 int dfb200_dropout(size_t count, float p, uint64_t seed, uint64_t offset, const float* x, const float* residual, float* y,

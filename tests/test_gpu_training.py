@@ -207,3 +207,30 @@ def test_cuda_graph_training_step_draws_a_fresh_dropout_mask_per_replay():
     losses = [step(**b).item() for _ in range(4)]
     assert int(step.counter.item()) == c0 + 4
     assert all(np.isfinite(losses)) and len({round(l, 7) for l in losses}) == 4, losses
+
+
+def test_fused_ff_in_equals_linear_geglu_dropout_chain():
+    """FFInFn (Linear + GEGLU + Dropout as one node, bias gradient from the GEGLU backward) against the unfused chain
+    linear -> geglu -> DropoutFn with the same Philox key: outputs and all gradients."""
+    from difffacto_b200 import train_ops as T
+    torch.manual_seed(5)
+    M, K, H = 1000, 128, 512
+    x = torch.randn(M, K, device="cuda")
+    w = (torch.randn(2 * H, K, device="cuda") * 0.1)
+    b = torch.randn(2 * H, device="cuda") * 0.1
+    dy = torch.randn(M, H, device="cuda")
+    for p, seed, off in ((0.0, 0, 0), (0.3, 1234, 7)):
+        a = [t.clone().requires_grad_(True) for t in (x, w, b)]
+        u0 = T.geglu(T.linear(a[0], a[1], a[2]))
+        if p > 0:
+            u0 = T.DropoutFn.apply(u0, p, seed, off, None, None)
+        u0.backward(dy)
+        c = [t.clone().requires_grad_(True) for t in (x, w, b)]
+        u1 = T.FFInFn.apply(c[0], c[1], c[2], p, seed, off, None)
+        u1.backward(dy)
+        assert torch.allclose(u1, u0, rtol=1e-5, atol=1e-6)
+        if p > 0:
+            kept = (u1 != 0).float().mean().item()
+            assert abs(kept - (1 - p)) < 0.01, kept
+        for g1, g0, name in zip(c, a, "xwb"):
+            assert _rel(g1.grad, g0.grad) < 2e-5, (p, name, _rel(g1.grad, g0.grad))
