@@ -188,6 +188,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the training block captures DDP's NCCL all-reduces in a CUDA graph: the NCCL watchdog's event polling is not allowed
+        # while a stream is capturing (PyTorch CUDA-graphs notes, "DDP + whole-network capture")
+        os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"  # torchrun exports 1
         dist.init_process_group("nccl", device_id=dev)
     B, N, T = B_PER_GPU, NPTS, T_STEPS
     diff = build_model(T, args.precision).to(dev).eval()

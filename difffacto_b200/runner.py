@@ -170,7 +170,11 @@ class Runner:
         self.diffusion.train()
         model = self.diffusion
         if self.world > 1:  # DDP all-reduces the gradients the autograd Functions hand to the parameters
-            model = torch.nn.parallel.DistributedDataParallel(self.diffusion, device_ids=[self.device.index])
+            side = torch.cuda.Stream(self.device)  # built on a side stream so that a later CUDA-graph capture may include it
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                model = torch.nn.parallel.DistributedDataParallel(self.diffusion, device_ids=[self.device.index])
+            torch.cuda.current_stream(self.device).wait_stream(side)
         # stage-1 configuration (train_chair_stage1.py): the PointNetV2 encoder + latent-flow prior are trained jointly with the
         # denoiser (AnchorDiffAE.forward, anchor_gen.py:995-1037); otherwise the conditioning comes from the dataset
         joint = self.encoder is not None and getattr(self.encoder, "encoder", None) is not None and self.encoder.part_aligner is None \
@@ -179,7 +183,16 @@ class Runner:
         if joint:
             self.encoder.train()
         ocfg = dict(cfg.optimizer.dump()) if cfg.optimizer else dict(type="Adam", lr=2e-3, weight_decay=0.)
+        # cfg.cuda_graph = True: the denoiser step (forward + backward + clip + optimizer, DDP all-reduces included) is captured once
+        # and replayed (difffacto_b200/train_graph.py); the joint stage-1 step (encoder + flows, data-dependent host logic) stays eager
+        use_graph = bool(cfg.cuda_graph) and not joint
+        if use_graph and self.world > 1 and os.environ.get("TORCH_NCCL_ASYNC_ERROR_HANDLING") != "0":
+            print("[Runner] cuda_graph with DDP needs TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group: running the step eagerly")
+            use_graph = False
+        if use_graph and ocfg.get("type") in ("Adam", "AdamW"):
+            ocfg["capturable"] = True
         opt = getattr(torch.optim, ocfg.pop("type"))(params, **ocfg)
+        graphed = None
         max_epoch = int(cfg.max_epoch or 1)
         max_norm, log_interval, ckpt_interval = cfg.max_norm, int(cfg.log_interval or 50), int(cfg.checkpoint_interval or 500)
         torch.manual_seed(self.seed + self.rank)  # reference: seed + local_rank (runner.py:39)
@@ -202,6 +215,21 @@ class Runner:
                     b = {k: v.to(self.device) for k, v in ds.batch(bi + epoch * len(ds), lo, hi).items()}
                     x0 = torch.sqrt(b["variance"]) * torch.randn_like(b["anchors"]) + b["anchors"]
                     flags = torch.ones(hi - lo, 1, x0.shape[2], device=self.device)
+                    if use_graph:
+                        inputs = dict(x0=x0, t=t, flags=flags, **{k: b[k] for k in ("anchors", "variance", "code", "params", "assign", "valid")})
+                        if graphed is None:
+                            from .train_graph import GraphedTrainStep
+                            graphed = GraphedTrainStep(
+                                lambda x0, t, flags, **bb: _LossModule.forward_through(model, self.diffusion, x0, t, bb, flags), params, opt,
+                                inputs, max_norm=max_norm, warmup=11 if self.world > 1 else 3, seed=self.seed)
+                        loss = graphed(**inputs).clone()
+                        it += 1
+                        losses.append(loss)
+                        if it % log_interval == 0 and self.rank == 0:
+                            print(f"[Runner] epoch {epoch} iter {it} loss {torch.stack(losses[-log_interval:]).mean().item():.5f}")
+                        if max_iters is not None and it >= max_iters:
+                            break
+                        continue
                     # DDP hooks fire on the wrapped module's forward: route the loss through it
                     loss = _LossModule.forward_through(model, self.diffusion, x0, t, b, flags)
                 loss.backward()

@@ -270,13 +270,22 @@ def train_block(torch, dist, build_model, synthetic_batch, world, rank, local, f
     d = build_model(T, "fp32").to(dev).train()
     d.model.train_precision = "bf16"
     model = d
+    # DDP's bucketed NCCL all-reduces are captured inside the step's CUDA graph (NCCL >= 2.9.6; needs TORCH_NCCL_ASYNC_ERROR_HANDLING=0
+    # before init_process_group -- bench.py sets it -- DDP built on a side stream and 11 eager warm-up steps, per the PyTorch
+    # CUDA-graphs notes); DFB200_TRAIN_GRAPH_DDP=0 issues the DDP step eagerly instead
+    import os
+    graph_ddp = os.environ.get("DFB200_TRAIN_GRAPH_DDP", "1") != "0" and os.environ.get("TORCH_NCCL_ASYNC_ERROR_HANDLING", "") == "0"
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(d, device_ids=[local], gradient_as_bucket_view=True)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            model = torch.nn.parallel.DistributedDataParallel(d, device_ids=[local], gradient_as_bucket_view=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
     b = {k: v.to(dev) for k, v in synthetic_batch(500 + rank, B, N).items()}
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     x0 = torch.sqrt(b["variance"]) * torch.randn(B, 3, N, device=dev, generator=g) + b["anchors"]
     flags = torch.ones(B, 1, N, device=dev)
-    graphed = world == 1  # one CUDA graph per step (difffacto_b200/train_graph.py); under DDP the step is issued eagerly
+    graphed = world == 1 or graph_ddp  # one CUDA graph per step (difffacto_b200/train_graph.py)
     opt = torch.optim.Adam(d.parameters(), lr=1e-4, fused=True, capturable=graphed)
     ts, loss = [], None
 
@@ -289,7 +298,7 @@ def train_block(torch, dist, build_model, synthetic_batch, world, rank, local, f
     step = None
     if graphed:
         from difffacto_b200.train_graph import GraphedTrainStep
-        step = GraphedTrainStep(loss_fn, list(d.parameters()), opt, inputs)
+        step = GraphedTrainStep(loss_fn, list(d.parameters()), opt, inputs, warmup=11 if world > 1 else 3)
     for it in range(warm + iters):
         inputs["t"] = torch.randint(0, T, (B,), device=dev, generator=g)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,12 +316,21 @@ def train_block(torch, dist, build_model, synthetic_batch, world, rank, local, f
             ts.append(e0.elapsed_time(e1))
     ts.sort()
     ms = torch.tensor([ts[len(ts) // 2]], device=dev, dtype=torch.float64)
+    in_sync = None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # the gradient all-reduce really ran in every (replayed) step: after warm + iters optimizer steps on DIFFERENT per-rank
+        # batches the weights of all ranks are still bit-identical
+        flat = torch.cat([p.detach().reshape(-1) for p in d.parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        diff = (flat - ref).abs().max().reshape(1)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        in_sync = bool(diff.item() == 0.0)
     ms = ms.item()
     flop = 3 * B * N * flop_per_point_step
     return {"ms_per_step": round(ms, 3), "shapes_per_s": round(B * world / ms * 1e3, 1), "batch_per_gpu": B, "global_batch": B * world,
             "algorithmic_TFLOPs_per_gpu": round(flop / ms / 1e9, 1), "n_gpus": world, "loss": float(loss.detach()),
-            "cuda_graph": bool(graphed),
-            "what": "denoiser training step (fwd+bwd+fused Adam), bf16 tcgen05 GEMMs; one CUDA graph per step at 1 GPU, eager under "
-                    "DDP over NCCL when n_gpus > 1; algorithmic FLOP = 3 x forward"}
+            "cuda_graph": bool(graphed), "ranks_in_sync": in_sync,
+            "what": "denoiser training step (fwd+bwd+fused Adam), bf16 tcgen05 GEMMs, DistributedDataParallel over NCCL when n_gpus > 1; "
+                    "the whole step (incl. DDP's bucketed all-reduces) is one CUDA graph when cuda_graph is true; algorithmic FLOP = 3 x forward"}
