@@ -12,8 +12,11 @@
 //     bias is added in fp32 by the softmax, bo / b2 are K = 8 MMAs against a ones tile with the bias split hi + lo in tf32;
 //   * GEGLU with the reference's exact-CDF GELU to 2.7e-5 (sigmoid of a fitted odd polynomial, ex2 / rcp MUFU forms), bias b1' in fp32;
 //   * the hidden chunk (64 value + 64 gate columns) is DOUBLE-BUFFERED in TMEM, so FF-in of chunk c+1 runs on the tensor pipe
-//     while all 8 epilogue warps apply GEGLU to chunk c; the gated activations go back through a shared-memory tile.
-// TMEM map (512 columns): X [0,128)  H0 [128,256)  H1 [256,384)  S [384,416).
+//     while all 8 epilogue warps apply GEGLU to chunk c; the gated activations go back to TMEM over the value columns just read;
+//   * both feed-forward GEMMs run in TS form (A operand in tensor memory): the LayerNorm-3 output is written to TMEM columns
+//     [384,512) and read by all 8 FF-in chunks, FF-out reads the gated activations from the hidden buffer -- 128 KB less
+//     shared-memory traffic per chunk than the SS forms of the first version (4-byte operands make this kernel shared-memory bound).
+// TMEM map (512 columns): X [0,128)  H0 [128,256)  H1 [256,384)  S [384,416) during attention / LN3 output A [384,512) during FF.
 // Weights stream L2 -> smem as pre-packed tf32 UMMA tiles (16 KB quarter / half chunks) through a 6-slot cp.async.bulk ring.
 #include <float.h>
 
@@ -219,8 +222,21 @@ __device__ __forceinline__ float2 geglu_erf2(float2 a_half, float2 g, float2 ba,
   float rx, ry;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(den.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(den.y));
+  // (one reciprocal of the product for both columns -- 3 MUFU per pair -- measured slower: 80.2 vs 82.7 shapes/s; the phase is
+  //  issue / latency bound, not MUFU bound)
   const float2 u = __fmul2_rn(__fmul2_rn(a_half, g), make_float2(rx, ry));
   return make_float2(to_tf32(u.x), to_tf32(u.y));
+}
+// D[tmem] += A[tmem] * B[smem]^T, kind::tf32, A operand in TENSOR MEMORY (lane = row, one 32-bit k-value per column, 8 columns per
+// K = 8 step).  Measured 96 cycles per M128 x N128 x K8 MMA against 105 in SS form (tools/micro/umma_tf32_ts.cu), and no
+// shared-memory read of A.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -263,6 +279,23 @@ __device__ __forceinline__ void row_layernorm_to_tile32(uint32_t taddr, uint8_t*
   }
 }
 
+// LayerNorm of the TMEM row -> tf32 A-operand row in TENSOR MEMORY (columns [dst, dst + 128)): the FF-in GEMM reads it in TS form
+__device__ __forceinline__ void row_layernorm_to_tmem32(uint32_t taddr, uint32_t dst) {
+  float mean, rstd;
+  row_stats32(taddr, mean, rstd);
+  const float nm = -mean * rstd;
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    float h[32];
+    tmem_ld32(taddr + cb * 32, h);
+    tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) h[k] = to_tf32(fmaf(h[k], rstd, nm));
+    tmem_st32(dst + cb * 32, h);
+  }
+  tmem_wait_st();
+}
+
 __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf32Params P) {
   using namespace t32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -275,7 +308,7 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
   if (warp == 8 && lane == 0) {
     mbar_init(&bars[BAR_A], 128); mbar_init(&bars[BAR_S], 1); mbar_init(&bars[BAR_X], 1);
     mbar_init(&bars[BAR_ACC], 1); mbar_init(&bars[BAR_ACC + 1], 1);
-    mbar_init(&bars[BAR_UREADY], 256); mbar_init(&bars[BAR_UFREE], 1);
+    mbar_init(&bars[BAR_UREADY], 256);
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&bars[BAR_WFULL + i], 1); mbar_init(&bars[BAR_WEMPTY + i], 1); }
     fence_barrier_init();
   }
@@ -299,7 +332,7 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
     const uint32_t X = lane_base, S = lane_base + 384;
     uint8_t* a_tile = smem + SM_A;
     uint8_t* u_tile = smem + SM_U;
-    uint32_t ph_s = 0, ph_x = 0, ph_acc0 = 0, ph_acc1 = 0, ph_ufree = 1;  // first UFREE wait passes: the barrier starts "free"
+    uint32_t ph_s = 0, ph_x = 0, ph_acc0 = 0, ph_acc1 = 0;
     int G = 0;  // packets consumed so far (this CTA), to find the fold packet of a layer
 #pragma unroll 1
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -395,8 +428,7 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
           mbar_wait(&bars[BAR_X], ph_x);
           ph_x ^= 1;
           tc_fence_after();
-          row_layernorm_to_tile32(X, a_tile, r);
-          fence_proxy_async();
+          row_layernorm_to_tmem32(X, lane_base + 384);  // LN3 output: the TS-form A operand of all 8 FF-in chunks (the logits are dead)
           tc_fence_before();
           mbar_arrive(&bars[BAR_A]);
         }
@@ -425,13 +457,11 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
                                         make_float2(ba[2 * k], ba[2 * k + 1]), make_float2(bg[2 * k], bg[2 * k + 1]));
             a[2 * k] = u.x; a[2 * k + 1] = u.y;
           }
+          // the gated activations go back to TENSOR MEMORY over the value columns this thread has just consumed; FF-out reads them
+          // in TS form (the first version wrote a 32 KB shared-memory tile per chunk and waited for the previous FF-out to free it)
+          tmem_st32(ACC, a);
+          tmem_wait_st();
           tc_fence_before();
-          mbar_wait(&bars[BAR_UFREE], ph_ufree);  // FF-out of the previous chunk has finished reading the U tile
-          ph_ufree ^= 1;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(u_tile + (H * 8 + j) * 2048 + r * 16) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
-          fence_proxy_async();
           mbar_arrive(&bars[BAR_UREADY]);
         }
         if (H == 0) {
@@ -486,8 +516,7 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(d, make_smem_desc(a_base + (4 * q + ks) * 4096, 2048, TILE_SBO), make_smem_desc(pw + ks * 4096, 2048, TILE_SBO), idesc128,
-                      (q | ks) ? 1u : 0u);
+            umma_tf32_ts(d, 384 + (4 * q + ks) * 8, make_smem_desc(pw + ks * 4096, 2048, TILE_SBO), idesc128, (q | ks) ? 1u : 0u);
           umma_commit(&bars[BAR_WEMPTY + (g_first + q) % NSLOT]);
           if (q == 3) umma_commit(&bars[BAR_ACC + (c & 1)]);
         }
@@ -537,13 +566,10 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_tf32(0, make_smem_desc(u_base + (4 * h + ks) * 4096, 2048, TILE_SBO), make_smem_desc(pw + ks * 4096, 2048, TILE_SBO), idesc128, 1u);
+                umma_tf32_ts(0, 128 + (c & 1) * 128 + (4 * h + ks) * 8, make_smem_desc(pw + ks * 4096, 2048, TILE_SBO), idesc128, 1u);
               if (c == FF_CHUNKS - 1 && h == 1) umma_tf32(0, ones_desc, make_smem_desc(pw + SLAB_OFF, 0, TILE_SBO), idesc128, 1u);
               umma_commit(&bars[BAR_WEMPTY + g % NSLOT]);
-              if (h == 1) {
-                umma_commit(&bars[BAR_UFREE]);
-                if (c == FF_CHUNKS - 1) umma_commit(&bars[BAR_X]);
-              }
+              if (h == 1 && c == FF_CHUNKS - 1) umma_commit(&bars[BAR_X]);
             }
             __syncwarp();
           }
