@@ -686,6 +686,117 @@ ball_query_scan4_kernel(int n, int m, float radius2, int nsample, int centres_pe
 }
 
 // --------------------------------------------------------------------------------------------
+// Thread-per-centre scan (round 2).  The warp-per-centre scans above spend most of their issue slots on the ORDERED
+// compaction (4 ballots + prefix popcounts per 128 candidates) and on per-centre set-up; here a THREAD owns a centre and walks
+// the whole cloud in index order, so "the first nsample hits in ascending k" needs no cross-lane work at all:
+//   * the cloud is staged once per CTA, negated (c - p == c + (-p) exactly), as three arrays padded to a multiple of 32 points
+//     with a never-hit value; every lane of a warp reads the SAME four points per step (one broadcast LDS.128 per coordinate);
+//   * 4 candidates cost 6 packed fp32x2 instructions (same rounding as the reference's fma chain, sq3x2) + 4 compares that
+//     set bits of a per-thread 32-candidate hit mask;
+//   * after 32 candidates the (few) set bits are appended, in ascending order, to the thread's slot list in shared memory
+//     ([slot][33] halfwords per warp: conflict-free for the thread-private writes and for the transposed read-back);
+//   * a warp leaves the loop as soon as all its 32 centres hold nsample hits (dense balls stop early, sparse ones read the
+//     cloud once: 6.4 issue slots per candidate and centre, no grid, no sort, no bitmap);
+//   * the warp then writes the 32 rows of idx with coalesced stores, padding with the first hit (0 for an empty ball).
+// Needs n <= 65535 (halfword slots) and the cloud + slot lists in shared memory.
+// --------------------------------------------------------------------------------------------
+// A thread owns BQT_C centres (register tile): the broadcast loads return 512 bytes per LDS.128 to the register file, and with
+// one centre per thread that return path (128 B/clk per SM) bound the kernel at 3 loads per 4 candidates; the loaded points
+// are reused for BQT_C centres.
+constexpr int BQT_THREADS = 256;
+__host__ __device__ inline size_t bqt_smem_bytes(int n, int nsample, int C) {
+  const size_t npad = ((size_t)n + 31) & ~(size_t)31;
+  return npad * 12 + (size_t)(BQT_THREADS / 32) * C * nsample * 33 * 2;
+}
+template <int BQT_C>
+__global__ void __launch_bounds__(BQT_THREADS)
+ball_query_tpc_kernel(int n, int m, float radius2, int nsample, const float* __restrict__ new_xyz, const float* __restrict__ xyz,
+                      int* __restrict__ idx) {
+  extern __shared__ __align__(16) float bqt_smem[];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npad = (n + 31) & ~31;
+  float* xs = bqt_smem;
+  float* ys = xs + npad;
+  float* zs = ys + npad;
+  unsigned short* slots = reinterpret_cast<unsigned short*>(zs + npad) + (size_t)warp * BQT_C * nsample * 33;  // [c][slot][33]
+  const float* pts = xyz + (size_t)b * n * 3;
+  for (int i = threadIdx.x; i < npad * 3; i += BQT_THREADS) {
+    const int k = i / 3, ch = i - k * 3;
+    (ch == 0 ? xs : ch == 1 ? ys : zs)[k] = k < n ? -__ldg(pts + i) : -3.0e38f;  // padding: (c + 3e38)^2 overflows to +inf, never < r^2
+  }
+  __syncthreads();
+  // centre c of this thread: j0 + c * BQT_THREADS + tid  (a warp's 32 lanes hold 32 consecutive centres for every c)
+  const int j0 = blockIdx.x * (BQT_THREADS * BQT_C);
+  float2 cx2[BQT_C], cy2[BQT_C], cz2[BQT_C];
+  int cnt[BQT_C];
+#pragma unroll
+  for (int c = 0; c < BQT_C; ++c) {
+    const int j = j0 + c * BQT_THREADS + threadIdx.x;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (j < m) {
+      const float* cq = new_xyz + ((size_t)b * m + j) * 3;
+      cx = __ldg(cq); cy = __ldg(cq + 1); cz = __ldg(cq + 2);
+    }
+    cx2[c] = make_float2(cx, cx); cy2[c] = make_float2(cy, cy); cz2[c] = make_float2(cz, cz);
+    cnt[c] = j < m ? 0 : nsample;  // lanes without a centre count as full
+  }
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+  const float4* ys4 = reinterpret_cast<const float4*>(ys);
+  const float4* zs4 = reinterpret_cast<const float4*>(zs);
+  const int r2bits = __float_as_int(radius2);
+#pragma unroll 1
+  for (int k0 = 0; k0 < npad; k0 += 32) {
+    // candidate i of the block ends up at bit 31 - i of mask[c]: d2 >= 0 (or NaN / +inf, which never hit), so its bit pattern
+    // compares like an integer and (d2bits - r2bits) has its sign bit set exactly when d2 < r2 (reference: `if (d2 < radius2)`);
+    // a funnel shift moves that bit into the mask
+    unsigned mask[BQT_C];
+#pragma unroll
+    for (int c = 0; c < BQT_C; ++c) mask[c] = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 X = xs4[(k0 >> 2) + q], Y = ys4[(k0 >> 2) + q], Z = zs4[(k0 >> 2) + q];  // warp-uniform addresses: broadcast
+#pragma unroll
+      for (int c = 0; c < BQT_C; ++c) {
+        const float2 da = sq3x2(__fadd2_rn(cx2[c], make_float2(X.x, X.y)), __fadd2_rn(cy2[c], make_float2(Y.x, Y.y)),
+                                __fadd2_rn(cz2[c], make_float2(Z.x, Z.y)));
+        const float2 db = sq3x2(__fadd2_rn(cx2[c], make_float2(X.z, X.w)), __fadd2_rn(cy2[c], make_float2(Y.z, Y.w)),
+                                __fadd2_rn(cz2[c], make_float2(Z.z, Z.w)));
+        mask[c] = __funnelshift_l((unsigned)(__float_as_int(da.x) - r2bits), mask[c], 1);
+        mask[c] = __funnelshift_l((unsigned)(__float_as_int(da.y) - r2bits), mask[c], 1);
+        mask[c] = __funnelshift_l((unsigned)(__float_as_int(db.x) - r2bits), mask[c], 1);
+        mask[c] = __funnelshift_l((unsigned)(__float_as_int(db.y) - r2bits), mask[c], 1);
+      }
+    }
+    bool full = true;
+#pragma unroll
+    for (int c = 0; c < BQT_C; ++c) {
+      unsigned mk = mask[c];
+      unsigned short* sl = slots + (size_t)c * nsample * 33;
+      while (mk != 0u && cnt[c] < nsample) {  // ascending k within the block; blocks are visited in ascending order
+        const int bpos = __clz(mk);
+        sl[cnt[c] * 33 + lane] = (unsigned short)(k0 + bpos);
+        ++cnt[c];
+        mk &= ~(0x80000000u >> bpos);
+      }
+      full = full && cnt[c] >= nsample;
+    }
+    if (__all_sync(0xFFFFFFFFu, full)) break;
+  }
+  // write-out: the warp emits its 32 rows per centre set one after the other (coalesced), padding with the first hit / 0
+#pragma unroll
+  for (int c = 0; c < BQT_C; ++c) {
+    const unsigned short* sl = slots + (size_t)c * nsample * 33;
+    const int jw = j0 + c * BQT_THREADS + warp * 32;
+    const int first = (jw + lane < m && cnt[c] > 0) ? (int)sl[lane] : 0;
+    for (int r = 0; r < 32 && jw + r < m; ++r) {
+      const int c_r = __shfl_sync(0xFFFFFFFFu, cnt[c], r), f_r = __shfl_sync(0xFFFFFFFFu, first, r);
+      int* o = idx + ((size_t)b * m + jw + r) * nsample;
+      for (int l = lane; l < nsample; l += 32) o[l] = l < c_r ? (int)sl[l * 33 + r] : f_r;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // Grid path (1024 <= n <= 8192): sparse balls (r = 0.1 / 0.2 on a unit-scale cloud hold 6 / 43 of
 // 2048 points on average, so 77-92 % of the centres scan ALL n points in the brute-force kernel).
 // Each CTA bins the cloud into a uniform grid of cell size >= 1.001 r (at most 16 cells per axis)
@@ -1459,6 +1570,35 @@ extern "C" int dfb200_query_ball_point(int b, int n, int m, float radius, int ns
   // sparse-ball path: uniform grid + 8 lanes per centre (see ball_query_grid_kernel), then the ordered scan for handed-over clouds;
   // DFB200_BALL_QUERY=scan forces the ordered brute-force scan (A/B measurements)
   static const bool force_scan = [] { const char* e = getenv("DFB200_BALL_QUERY"); return e != nullptr && e[0] == 's'; }();
+  // thread-per-centre scan (ball_query_tpc_kernel): DFB200_BALL_QUERY=tpc forces it, =grid forces the grid path (A/B measurements)
+  static const int tpc_mode = [] { const char* e = getenv("DFB200_BALL_QUERY"); return e == nullptr ? 0 : e[0] == 't' ? 1 : e[0] == 'g' ? -1 : 0; }();
+  {
+    // centres per thread (DFB200_BQT_C, A/B): 1 is the measured optimum at batch 256 (104 / 118 / 138 us for r = 0.1 / 0.2 / 0.4; 2:
+    // 117 / 127 / -, 4 with 128 threads: 145 / 174 / -: the register tile halves the broadcast-load traffic that bounds the
+    // kernel, but one cloud per CTA leaves 1.7 CTAs per SM)
+    static const int tpc_c = [] { const char* e = getenv("DFB200_BQT_C"); return e != nullptr ? atoi(e) : 1; }();
+    const int C = tpc_c == 4 ? 4 : tpc_c == 2 ? 2 : 1;
+    const size_t tsm = bqt_smem_bytes(n, nsample, C);
+    const bool fits = n >= 1 && n <= 65535 && tsm <= 110 * 1024;
+    // default policy: nsample is the caller's estimate of the ball population.  Balls expected to hold >= 48 points go to the
+    // thread-per-centre scan (radius-independent: 118 vs 159 us at r = 0.2, 138 vs 190 us at r = 0.4 against the grid path, same
+    // inputs); sparser queries keep the grid path, whose pruning wins there (97 vs 104 us at r = 0.1, nsample 16).
+    const bool want = tpc_mode == 1 || (tpc_mode == 0 && !force_scan && nsample >= 48 && n >= 256 && m >= 64 && (long long)b * m >= 148LL * BQT_THREADS);  // at least one CTA per SM
+    if (fits && want) {
+      static DeviceOnce once;
+      if (once.first_time()) {
+        DFB_CUDA(cudaFuncSetAttribute(ball_query_tpc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        DFB_CUDA(cudaFuncSetAttribute(ball_query_tpc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        DFB_CUDA(cudaFuncSetAttribute(ball_query_tpc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      }
+      const dim3 grid(cdiv(m, BQT_THREADS * C), b);
+      if (C == 1) ball_query_tpc_kernel<1><<<grid, BQT_THREADS, tsm, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
+      else if (C == 2) ball_query_tpc_kernel<2><<<grid, BQT_THREADS, tsm, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
+      else ball_query_tpc_kernel<4><<<grid, BQT_THREADS, tsm, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
+      DFB_LAUNCH_CHECK();
+      return DFB200_OK;
+    }
+  }
   if (!force_scan && n >= 1024 && n <= 8192 && m >= 32) {
     const size_t gsm = bqg_smem_bytes(n);
     // persistent CTAs (as many as fit: shared memory or 8 x 256 threads per SM), balanced static partition

@@ -130,6 +130,28 @@ def test_ball_query_grid_path_large_batch_sorted_centres(pu, ref_ext):
             assert np.array_equal(got, ref_ext["ref_pointnet2_ext"].ball_query(cu(new_xyz), cu(xyz), r, ns).cpu().numpy())
 
 
+def test_ball_query_thread_per_centre_path(pu, ref_ext):
+    """Shapes the default policy sends to ball_query_tpc_kernel (nsample >= 48, batch x centres >= one CTA per SM): ragged n
+    (not a multiple of 32) and m (partial warps / CTAs), dense balls that stop early, empty balls (centres far from the cloud),
+    non-finite points, r = 0 - bit-exact against the C oracle and the reference kernel."""
+    rng = np.random.default_rng(33)
+    cases = []
+    xyz = part_cloud(rng, 90, 777)
+    sel = np.stack([rng.permutation(777)[:433] for _ in range(90)])
+    ctr = np.take_along_axis(xyz, sel[..., None].repeat(3, -1), 1).copy()
+    ctr[:, :7] += np.float32(5.0)          # empty balls
+    cases += [(xyz, ctr, 0.2, 64), (xyz, ctr, 0.45, 48), (xyz, ctr, 0.0, 50), (xyz, ctr, 0.05, 129)]
+    big = part_cloud(rng, 150, 2048)
+    big[3, 11] = np.nan
+    big[4, 12, 0] = np.inf
+    cases.append((big, big[:, 1000:1300].copy(), 0.3, 100))
+    for (p, c, r, ns) in cases:
+        got = pu.ball_query(r, ns, cu(p), cu(c)).cpu().numpy()
+        assert np.array_equal(got, O.ball_query(c, p, r, ns)), (p.shape, c.shape, r, ns)
+        if "ref_pointnet2_ext" in ref_ext:
+            assert np.array_equal(got, ref_ext["ref_pointnet2_ext"].ball_query(cu(c), cu(p), r, ns).cpu().numpy())
+
+
 @pytest.mark.parametrize("B,C,N,NP,NS", [(4, 7, 2048, 512, 64), (2, 131, 512, 128, 64), (2, 320, 512, 128, 32), (1, 3, 50, 7, 5), (2, 4, 100, 9, 1)])
 def test_group_and_gather_bit_exact(pu, ref_ext, B, C, N, NP, NS):
     rng = np.random.default_rng(C + NP)
