@@ -10,6 +10,7 @@
 // of a slice and commits to the slice's mbarrier.  Round 2: the operands of slice i+1 are requested into registers (64 per thread)
 // before slice i's barrier, so their global-memory latency overlaps the MMAs and the other resident CTAs.  gridDim.z > 1
 // splits K (wgrad reduces over the B*N token rows) with an atomicAdd epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -175,6 +176,211 @@ gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Round 2: ASYNCHRONOUS-COPY form for k-contiguous operands (forward GEMMs; dgrad with a pre-transposed weight).  The kernel above
+// stages fp32 operands through REGISTERS (convert to bf16, store): one 64-deep k-slice = 64 KB of loads per CTA is all that can be
+// in flight, and the training GEMMs ran 2.5-4x off their memory floor for it.  Here nothing passes through registers:
+//   * the tensor cores take the fp32 containers as they are (tcgen05.mma kind::tf32: the top 19 bits of each value, fp32
+//     accumulation -- 10 mantissa bits instead of the 8 of the bf16 staging; the MMA runs at a third of the bf16 rate, which does not
+//     matter for GEMMs that are memory bound by a wide margin),
+//   * 4 producer warps copy 128 x 32 fp32 slices global -> shared with 16-byte cp.async (LDGSTS) straight into the SWIZZLE_128B
+//     K-major UMMA layout (a row of a slice = 128 contiguous bytes, the 16-byte chunk index XORed with row % 8: coalesced global
+//     reads, conflict-free shared-memory writes), 3 slices in flight per thread in a 5-stage ring,
+//   * one warp issues the MMAs (4 x K=8 per slice), 4 epilogue warps drain two double-buffered TMEM accumulators through a
+//     shared-memory transpose into 128-bit global stores while the next tile's MMAs run; CTAs are persistent over (tile, k-split)
+//     work items, n fastest, so A row blocks are shared through L2.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int GA_STAGES = 5, GA_K = 32, GA_PROD = 128, GA_THREADS = GA_PROD + 5 * 32, GA_INFLIGHT = 3;
+constexpr uint32_t GA_TILE = 128 * GA_K * 4;                 // 16 KB per operand and slice
+constexpr uint32_t GA_STAGE = 2 * GA_TILE;
+constexpr uint32_t GA_TW_STRIDE = 36;
+constexpr uint32_t GA_SM_TW = GA_STAGES * GA_STAGE;
+constexpr uint32_t GA_SM_BAR = GA_SM_TW + 4 * 32 * GA_TW_STRIDE * 4;
+constexpr uint32_t GA_SMEM = GA_SM_BAR + 256;
+enum GaBar { GA_FULL = 0, GA_EMPTY = GA_STAGES, GA_ACC_FULL = 2 * GA_STAGES, GA_ACC_EMPTY = 2 * GA_STAGES + 2 };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copy rows [r0, r0+128) x k [k0, k0+32) of a k-contiguous fp32 operand into a SWIZZLE_128B tile (zero fill outside rows / kend)
+__device__ __forceinline__ void ga_copy(uint32_t tile, const float* __restrict__ P, int ld, int r0, int rows, int k0, int kend) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 16 + (t >> 3), c = t & 7;
+    const int gr = r0 + row, gk = k0 + c * 4;
+    int bytes = 0;
+    if (gr < rows && gk < kend) bytes = min(4, kend - gk) * 4;
+    const float* src = P + (size_t)(gr < rows ? gr : 0) * ld + (gk < kend ? gk : 0);
+    cp_async16(tile + row * 128 + ((c ^ (row & 7)) << 4), src, (uint32_t)bytes);
+  }
+}
+
+__global__ void __launch_bounds__(GA_THREADS, 1)
+gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
+                       int ldc, const float* __restrict__ bias, int beta, int k_per_split, int tiles_n, int tiles_mn, int items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GA_SM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GA_SM_BAR + 192);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  constexpr int W_MMA = GA_PROD / 32;
+  if (tid == 0) {
+    for (int i = 0; i < GA_STAGES; ++i) { mbar_init(&bars[GA_FULL + i], GA_PROD); mbar_init(&bars[GA_EMPTY + i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[GA_ACC_FULL + i], 1); mbar_init(&bars[GA_ACC_EMPTY + i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool split = items > tiles_mn;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp < W_MMA) {
+    // =========================== producers ===========================
+    int it = 0;       // slices issued
+    int done = 0;     // slices published
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int z = item / tiles_mn, mn = item - z * tiles_mn;
+      const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
+      const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+#pragma unroll 1
+      for (int k0 = kb; k0 < ke; k0 += GA_K, ++it) {
+        const int s = it % GA_STAGES;
+        mbar_wait(&bars[GA_EMPTY + s], (((uint32_t)(it / GA_STAGES)) & 1u) ^ 1u);
+        const uint32_t st = sbase + s * GA_STAGE;
+        ga_copy(st, A, lda, i0, M, k0, ke);
+        ga_copy(st + GA_TILE, B, ldb, j0, N, k0, ke);
+        cp_async_commit();
+        if (it - done >= GA_INFLIGHT - 1) {  // the slice issued GA_INFLIGHT - 1 iterations ago has landed: publish it
+          cp_async_wait<GA_INFLIGHT - 1>();
+          fence_proxy_async();
+          mbar_arrive(&bars[GA_FULL + done % GA_STAGES]);
+          ++done;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; done < it; ++done) mbar_arrive(&bars[GA_FULL + done % GA_STAGES]);
+  } else if (warp == W_MMA) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_tf32(GT_M, GT_N);
+    int it = 0, t = 0;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
+      const int z = item / tiles_mn;
+      const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+      const int b = t & 1;
+      mbar_wait(&bars[GA_ACC_EMPTY + b], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+      tc_fence_after();
+      bool first = true;
+#pragma unroll 1
+      for (int k0 = kb; k0 < ke; k0 += GA_K, ++it) {
+        const int s = it % GA_STAGES;
+        mbar_wait(&bars[GA_FULL + s], ((uint32_t)(it / GA_STAGES)) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t aa = sbase + s * GA_STAGE, bb = aa + GA_TILE;
+#pragma unroll
+          for (int ks = 0; ks < GA_K / 8; ++ks)  // SWIZZLE_128B K-major: 8-row atoms of 1024 B; a K = 8 step (32 B) advances the start address
+            umma_tf32(tmem + b * 128, make_smem_desc(aa + ks * 32, 16, 1024) | ((uint64_t)2 << 61),
+                      make_smem_desc(bb + ks * 32, 16, 1024) | ((uint64_t)2 << 61), idesc, (!first || ks > 0) ? 1u : 0u);
+          umma_commit(&bars[GA_EMPTY + s]);
+        }
+        __syncwarp();
+        first = false;
+      }
+      if (elect_one()) umma_commit(&bars[GA_ACC_FULL + b]);
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    // =========================== epilogue (4 warps; TMEM lanes 32 * (warp % 4) ..) ===========================
+    const int q = warp & 3;
+    float* tw = reinterpret_cast<float*>(smem + GA_SM_TW) + (warp - W_MMA - 1) * (32 * GA_TW_STRIDE);
+    const bool vec_c = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    int t = 0;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
+      const int z = item / tiles_mn, mn = item - z * tiles_mn;
+      const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
+      const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+      const int b = t & 1;
+      mbar_wait(&bars[GA_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128;
+      const int rbase = i0 + q * 32;
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        float h[32];
+        if (kb < ke) {
+          tmem_ld32(taddr + cb * 32, h);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) h[e] = 0.f;
+        }
+        if (cb == 3) {  // the accumulator is in registers: hand the buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&bars[GA_ACC_EMPTY + b]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4)
+          *reinterpret_cast<float4*>(tw + lane * GA_TW_STRIDE + 4 * e4) = make_float4(h[4 * e4], h[4 * e4 + 1], h[4 * e4 + 2], h[4 * e4 + 3]);
+        __syncwarp();
+        const int jb = j0 + cb * 32;
+        if (vec_c) {
+          const int j = jb + 4 * (lane & 7);
+          float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias != nullptr && z == 0 && j < N) bj = __ldg(reinterpret_cast<const float4*>(bias + j));
+#pragma unroll 2
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int rr = r4 * 4 + (lane >> 3), i = rbase + rr;
+            if (i < M && j < N) {
+              float4 v = *reinterpret_cast<const float4*>(tw + rr * GA_TW_STRIDE + 4 * (lane & 7));
+              v.x += bj.x; v.y += bj.y; v.z += bj.z; v.w += bj.w;
+              float* o = C + (size_t)i * ldc + j;
+              if (split) { atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w); }
+              else {
+                if (beta) { const float4 c0 = *reinterpret_cast<const float4*>(o); v.x += c0.x; v.y += c0.y; v.z += c0.z; v.w += c0.w; }
+                *reinterpret_cast<float4*>(o) = v;
+              }
+            }
+          }
+        } else {
+          const int j = jb + lane;
+          const float bj = (bias != nullptr && z == 0 && j < N) ? __ldg(bias + j) : 0.f;
+          if (j < N) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int i = rbase + rr;
+              if (i >= M) break;
+              const float v = tw[rr * GA_TW_STRIDE + lane] + bj;
+              float* o = C + (size_t)i * ldc + j;
+              if (split) atomicAdd(o, v);
+              else *o = beta ? *o + v : v;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 }  // namespace dfb200
 
 using namespace dfb200;
@@ -186,6 +392,25 @@ extern "C" int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, i
   int kps = cdiv(cdiv(K, split_k), GT_K) * GT_K;
   if (kps == 0) kps = GT_K;
   const int splits = K == 0 ? 1 : cdiv(K, kps);
+  // asynchronous-copy tf32 kernel for k-contiguous, 16-byte aligned operands (DFB200_GEMM_ASYNC=0 keeps the register-staged
+  // bf16 kernel for A/B measurements)
+  static const bool use_async = [] { const char* e = getenv("DFB200_GEMM_ASYNC"); return e == nullptr || e[0] != '0'; }();
+  if (use_async && a_k_contiguous && b_k_contiguous && K > 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0) {
+    const int kps_a = cdiv(cdiv(K, split_k), GA_K) * GA_K;
+    const int splits_a = cdiv(K, kps_a);
+    const int tiles_n = cdiv(N, GT_N), tiles_m = cdiv(M, GT_M);
+    const long long items = (long long)tiles_n * tiles_m * splits_a;
+    DFB_REQUIRE(items <= 0x7fffffffLL, DFB200_ERR_INVALID_ARG, "gemm_bf16: too many tiles");
+    const int n_sm = current_device_sm_count();
+    DFB_REQUIRE(n_sm > 0, DFB200_ERR_CUDA, "gemm_bf16: cannot query the SM count of the current device");
+    static DeviceOnce once;
+    if (once.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
+    gemm_tf32_async_kernel<<<(int)(items < n_sm ? items : n_sm), GA_THREADS, GA_SMEM, as_stream(stream)>>>(
+        M, N, K, A, lda, B, ldb, C, ldc, bias, beta, kps_a, tiles_n, tiles_n * tiles_m, (int)items);
+    DFB_LAUNCH_CHECK();
+    return DFB200_OK;
+  }
   dim3 grid(cdiv(N, GT_N), cdiv(M, GT_M), splits);
   DFB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DFB200_ERR_INVALID_ARG, "gemm_bf16: grid too large");
   const int smem = 4 * GT_TILE_BYTES + 128;

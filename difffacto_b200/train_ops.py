@@ -63,6 +63,16 @@ def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split
                                        int(split_k), stream()))
 
 
+def _dgrad(M, K, N, dy, weight, dx, bf16):
+    """dx (M,K) = dy (M,N) . W (N,K).  On the tensor cores the weight is transposed first (a few hundred KB): with both operands
+    k-contiguous the GEMM takes the asynchronous-copy kernel (csrc/gemm_tc.cu) instead of the register-staged one."""
+    if bf16 and M >= 128 and K >= 64 and N >= 64:
+        wt = weight.t().contiguous()  # (K, N): B(n, k) = wt[k * N + n]
+        _sgemm(True, True, M, K, N, dy, N, wt, N, dx, K, bf16=True)
+    else:
+        _sgemm(True, False, M, K, N, dy, N, weight, K, dx, K, bf16=bf16)
+
+
 _GEMM_BF16 = False  # set by gemm_precision(): Linear layers built inside use the tensor cores (forward AND backward)
 
 
@@ -111,7 +121,7 @@ class LinearFn(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
-            _sgemm(True, False, M, K, N, dy, N, weight, K, dx, K, bf16=ctx.bf16)  # dx(i,k) = sum_n dy(i,n) W(n,k)
+            _dgrad(M, K, N, dy, weight, dx, ctx.bf16)  # dx(i,k) = sum_n dy(i,n) W(n,k)
         if ctx.needs_input_grad[1]:
             dw = zeros((N, K), x.device)
             tc = ctx.bf16 and N >= 128 and K >= 64 and M >= 64
@@ -220,7 +230,7 @@ class FFInFn(Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
-            _sgemm(True, False, M, K, H2, dh, H2, weight, K, dx, K, bf16=ctx.bf16)
+            _dgrad(M, K, H2, dh, weight, dx, ctx.bf16)
         if ctx.needs_input_grad[1]:
             dw = zeros((H2, K), x.device)
             tc = ctx.bf16 and H2 >= 128 and K >= 64 and M >= 64

@@ -109,29 +109,37 @@ def test_dropout_mask_statistics_and_backward():
 
 
 def test_tensor_core_gemm_layouts_match_bf16_reference():
-    """dfb200_gemm_bf16 (tcgen05) in the four operand layouts, edge tiles, bias, accumulate and split-K against a bf16-operand,
-    fp64-accumulate reference."""
+    """dfb200_gemm_bf16 (tcgen05) in the four operand layouts, edge tiles, bias, accumulate and split-K.  k-contiguous operands take
+    the asynchronous-copy kernel (fp32 containers read as tf32: 10 mantissa bits, truncated), the other layouts the register-staged
+    kernel (operands rounded to bf16: 8 bits): both are checked against the exact fp64 product with the bf16 operand-rounding bound
+    (measured: 1.2e-2 sqrt(K) for bf16, 4e-3 sqrt(K) for tf32 on N(0,1) operands; a layout bug gives O(sqrt(K)))."""
     from difffacto_b200 import train_ops as T
     torch.manual_seed(1)
-    bf = lambda t: t.bfloat16().double()  # noqa: E731
-    for (M, N, K) in [(128, 128, 64), (300, 200, 136), (1000, 128, 512), (257, 1024, 128)]:
+    d64 = lambda t: t.double()  # noqa: E731
+    for (M, N, K) in [(128, 128, 64), (300, 200, 136), (1000, 128, 512), (257, 1024, 128), (4100, 260, 100)]:
         x, w, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda"), torch.randn(N, device="cuda")
         c0 = torch.randn(M, N, device="cuda")
         y = c0.clone()
         T._sgemm(True, True, M, N, K, x, K, w, K, y, N, bias=b, beta=1, bf16=True)
-        ref = c0.double() + bf(x) @ bf(w).t() + b.double()
-        assert (y.double() - ref).abs().max().item() < 2e-3 * K ** 0.5, (M, N, K)
+        ref = d64(c0) + d64(x) @ d64(w).t() + d64(b)
+        assert (d64(y) - ref).abs().max().item() < 6e-3 * K ** 0.5, (M, N, K)   # tf32 path (or bf16 if K is not 16-byte aligned)
+        y3 = torch.zeros(M, N, device="cuda")
+        T._sgemm(True, True, M, N, K, x, K, w, K, y3, N, split_k=3, bf16=True)  # split-K on the same path
+        assert (d64(y3) - d64(x) @ d64(w).t()).abs().max().item() < 6e-3 * K ** 0.5, (M, N, K)
         dy = torch.randn(M, N, device="cuda")
         dx = torch.empty(M, K, device="cuda")
         T._sgemm(True, False, M, K, N, dy, N, w, K, dx, K, bf16=True)                 # dgrad layout
-        assert (dx.double() - bf(dy) @ bf(w)).abs().max().item() < 2e-3 * N ** 0.5
+        assert (d64(dx) - d64(dy) @ d64(w)).abs().max().item() < 1.8e-2 * N ** 0.5
+        dx2 = torch.empty(M, K, device="cuda")
+        T._dgrad(M, K, N, dy, w, dx2, True)                                            # dgrad through the transposed weight
+        assert (d64(dx2) - d64(dy) @ d64(w)).abs().max().item() < 1.8e-2 * N ** 0.5
         dw = torch.zeros(N, K, device="cuda")
         T._sgemm(False, False, N, K, M, dy, N, x, K, dw, K, split_k=3, bf16=True)     # wgrad layout, split-K with atomics
-        assert (dw.double() - bf(dy).t() @ bf(x)).abs().max().item() < 2e-3 * M ** 0.5
+        assert (d64(dw) - d64(dy).t() @ d64(x)).abs().max().item() < 1.8e-2 * M ** 0.5
         xt = x.t().contiguous()
         y2 = torch.empty(M, N, device="cuda")
         T._sgemm(False, True, M, N, K, xt, M, w, K, y2, N, bf16=True)                 # A row-contiguous, B k-contiguous
-        assert (y2.double() - bf(x) @ bf(w).t()).abs().max().item() < 2e-3 * K ** 0.5
+        assert (d64(y2) - d64(x) @ d64(w).t()).abs().max().item() < 1.8e-2 * K ** 0.5
 
 
 def test_bf16_training_gradients_close_to_fp32():
@@ -175,7 +183,9 @@ def test_cuda_graph_training_step_equals_the_eager_step():
     batches = [_graph_inputs(40 + i, B, N) for i in range(1 + steps)]
     # eager reference
     d0 = _build(dropout=0.0).train()
-    opt0 = torch.optim.Adam(d0.parameters(), lr=1e-3, capturable=True)
+    # SGD with momentum: Adam normalises noise-level gradients to +-lr, so the summation order of the split-K atomics would show up
+    # as O(lr) weight differences that have nothing to do with the capture
+    opt0 = torch.optim.SGD(d0.parameters(), lr=0.05, momentum=0.9)
     # the capture runs `warm` eager steps on the example batch (the capture itself only records, it does not execute)
     losses0 = []
     for i in range(warm):
@@ -187,7 +197,7 @@ def test_cuda_graph_training_step_equals_the_eager_step():
         losses0.append(l.item())
     # graphed
     d1 = _build(dropout=0.0).train()
-    opt1 = torch.optim.Adam(d1.parameters(), lr=1e-3, capturable=True)
+    opt1 = torch.optim.SGD(d1.parameters(), lr=0.05, momentum=0.9)
     step = GraphedTrainStep(_loss_fn(d1), list(d1.parameters()), opt1, batches[0], warmup=warm)
     losses1 = [step(**batches[1 + i]).item() for i in range(steps)]
     assert np.allclose(losses0, losses1, rtol=2e-4, atol=1e-6), (losses0, losses1)
