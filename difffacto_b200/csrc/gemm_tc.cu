@@ -190,7 +190,7 @@ gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const 
 //     shared-memory transpose into 128-bit global stores while the next tile's MMAs run; CTAs are persistent over (tile, k-split)
 //     work items, n fastest, so A row blocks are shared through L2.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int GA_STAGES = 5, GA_K = 32, GA_PROD = 128, GA_THREADS = GA_PROD + 5 * 32, GA_INFLIGHT = 3;
+constexpr int GA_STAGES = 6, GA_K = 32, GA_PROD = 128, GA_THREADS = GA_PROD + 5 * 32, GA_INFLIGHT = 5;
 constexpr uint32_t GA_TILE = 128 * GA_K * 4;                 // 16 KB per operand and slice
 constexpr uint32_t GA_STAGE = 2 * GA_TILE;
 constexpr uint32_t GA_TW_STRIDE = 36;

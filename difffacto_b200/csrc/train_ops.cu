@@ -286,7 +286,7 @@ geglu_dropout_bwd_kernel(long long M, int H4, float p, float scale, uint64_t see
 // Cross-attention core over the 4 part tokens (attention.py:183-203): 8 heads x 16, masked softmax over 4 keys.
 // Warp per token, lane = 4 of the 128 dims (head = lane / 4).  q/o (B*N,128), k/v (B,4,128), probs (B*N,8,4).
 // ---------------------------------------------------------------------------------------------
-constexpr int PA_TOK = 256;  // tokens per CTA (all of one sample: N % PA_TOK is handled by clamping)
+constexpr int PA_TOK = 64;   // tokens per CTA (of one sample: N % PA_TOK is handled by clamping), 8 per warp
 __global__ void __launch_bounds__(256)
 part_attn_fwd_kernel(int N, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                      const float* __restrict__ valid, float* __restrict__ o, float* __restrict__ probs) {

@@ -66,7 +66,7 @@ def _sgemm(a_kc, b_kc, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0, split
 def _dgrad(M, K, N, dy, weight, dx, bf16):
     """dx (M,K) = dy (M,N) . W (N,K).  On the tensor cores the weight is transposed first (a few hundred KB): with both operands
     k-contiguous the GEMM takes the asynchronous-copy kernel (csrc/gemm_tc.cu) instead of the register-staged one."""
-    if bf16 and M >= 128 and K >= 64 and N >= 64:
+    if bf16 and M >= 128 and K >= 64 and N >= 64 and N * K >= 65536:  # 128 x 128 weights: the transpose costs what the faster kernel saves
         wt = weight.t().contiguous()  # (K, N): B(n, k) = wt[k * N + n]
         _sgemm(True, True, M, K, N, dy, N, wt, N, dx, K, bf16=True)
     else:
