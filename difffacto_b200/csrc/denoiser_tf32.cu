@@ -55,7 +55,7 @@ constexpr uint32_t SM_BAR = SM_EX + ((EX_FLOATS * 4 + 127) / 128) * 128;
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
 constexpr uint32_t SMEM_BYTES = SM_BAR + 512;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-enum Bar { BAR_A = 0, BAR_S = 1, BAR_X = 2, BAR_ACC = 3 /*[2]*/, BAR_UREADY = 5, BAR_UFREE = 6, BAR_WFULL = 7 /*[NSLOT]*/,
+enum Bar { BAR_A = 0, BAR_S = 1, BAR_X = 2, BAR_ACC = 3 /*[2]*/, BAR_UREADY = 5 /*[2], one per accumulator buffer*/, BAR_WFULL = 7 /*[NSLOT]*/,
            BAR_WEMPTY = 7 + NSLOT, BAR_COUNT = 7 + 2 * NSLOT };
 static_assert(BAR_COUNT * 8 <= 256, "barrier block");
 }  // namespace t32
@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
     mbar_init(&bars[BAR_A], 128); mbar_init(&bars[BAR_S], 1); mbar_init(&bars[BAR_X], 1);
     mbar_init(&bars[BAR_ACC], 1); mbar_init(&bars[BAR_ACC + 1], 1);
     mbar_init(&bars[BAR_UREADY], 256);
+    mbar_init(&bars[BAR_UREADY + 1], 256);
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&bars[BAR_WFULL + i], 1); mbar_init(&bars[BAR_WEMPTY + i], 1); }
     fence_barrier_init();
   }
@@ -462,7 +463,9 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
           tmem_st32(ACC, a);
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&bars[BAR_UREADY]);
+          // one barrier PER BUFFER: the two column halves (warps 0-3 / 4-7) may be a chunk apart, and on a single barrier 128
+          // arrivals for chunk c plus 128 for chunk c+1 from the same half would complete the phase without the other half
+          mbar_arrive(&bars[BAR_UREADY + (c & 1)]);
         }
         if (H == 0) {
           mbar_wait(&bars[BAR_X], ph_x);
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
     const uint32_t sbase = smem_u32(smem);
     const uint32_t ring = sbase + SM_RING, a_base = sbase + SM_A, u_base = sbase + SM_U;
     const uint64_t ones_desc = make_smem_desc(sbase + SM_ONES, 2048, TILE_SBO);
-    uint32_t ph_a = 0, ph_u = 0;
+    uint32_t ph_a = 0, ph_u = 0;  // ph_u: bit b = parity of BAR_UREADY[b]
     int G = 0;
     auto pkt = [&](int g) -> uint32_t {
       mbar_wait(&bars[BAR_WFULL + g % NSLOT], (uint32_t)(g / NSLOT) & 1u);
@@ -557,8 +560,8 @@ __global__ void __launch_bounds__(t32::THREADS, 1) denoiser_tf32_kernel(const Tf
 #pragma unroll 1
         for (int c = 0; c < FF_CHUNKS; ++c) {
           if (c + 1 < FF_CHUNKS) ff_in(c + 1, G0 + 2 + w1q(c + 1, 0));
-          mbar_wait(&bars[BAR_UREADY], ph_u);
-          ph_u ^= 1;
+          mbar_wait(&bars[BAR_UREADY + (c & 1)], (ph_u >> (c & 1)) & 1u);
+          ph_u ^= 1u << (c & 1);
           tc_fence_after();
           for (int h = 0; h < 2; ++h) {
             const int g = G0 + 2 + w2h(c, h);

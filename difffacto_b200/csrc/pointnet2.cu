@@ -783,6 +783,7 @@ ball_query_tpc_kernel(int n, int m, float radius2, int nsample, const float* __r
     if (__all_sync(0xFFFFFFFFu, full)) break;
   }
   // write-out: the warp emits its 32 rows per centre set one after the other (coalesced), padding with the first hit / 0
+  __syncwarp();  // the slot lists are read across lanes below (the vote above does not order shared-memory accesses)
 #pragma unroll
   for (int c = 0; c < BQT_C; ++c) {
     const unsigned short* sl = slots + (size_t)c * nsample * 33;
