@@ -219,6 +219,16 @@ __device__ __forceinline__ void ga_copy(uint32_t tile, const float* __restrict__
   }
 }
 
+// interior form of ga_copy (all 128 rows and all 32 k inside the operand): the per-thread source pointer and the swizzled destination
+// are loop invariants of the caller, a copy is one LDGSTS plus one 64-bit add.  The general form recomputes row / k bounds, the
+// zero-fill size and the address for each of its 8 copies (~230 dependent integer instructions per slice and warp), which made the
+// 4 producer warps -- not the memory system -- the second bottleneck of the memory-bound shapes.
+__device__ __forceinline__ void ga_copy_interior(uint32_t dst, const float* __restrict__ src, size_t row_step) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 2048), "l"(src + i * row_step) : "memory");
+}
+
 __global__ void __launch_bounds__(GA_THREADS, 1)
 gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
                        int ldc, const float* __restrict__ bias, int beta, int k_per_split, int tiles_n, int tiles_mn, int items) {
@@ -250,13 +260,23 @@ gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda
       const int z = item / tiles_mn, mn = item - z * tiles_mn;
       const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
       const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+      const bool interior = i0 + GT_M <= M && j0 + GT_N <= N && (ke - kb) % GA_K == 0;
+      // thread t copies 16-byte chunk t % 8 of rows t / 8 + 16 i; (row & 7) does not depend on i, so the swizzle is a thread constant
+      const uint32_t dst0 = (uint32_t)(tid >> 3) * 128u + (uint32_t)(((tid & 7) ^ ((tid >> 3) & 7)) << 4);
+      const float* pa = A + (size_t)(i0 + (tid >> 3)) * lda + (tid & 7) * 4 + kb;
+      const float* pb = B + (size_t)(j0 + (tid >> 3)) * ldb + (tid & 7) * 4 + kb;
 #pragma unroll 1
-      for (int k0 = kb; k0 < ke; k0 += GA_K, ++it) {
+      for (int k0 = kb; k0 < ke; k0 += GA_K, ++it, pa += GA_K, pb += GA_K) {
         const int s = it % GA_STAGES;
         mbar_wait(&bars[GA_EMPTY + s], (((uint32_t)(it / GA_STAGES)) & 1u) ^ 1u);
         const uint32_t st = sbase + s * GA_STAGE;
-        ga_copy(st, A, lda, i0, M, k0, ke);
-        ga_copy(st + GA_TILE, B, ldb, j0, N, k0, ke);
+        if (interior) {
+          ga_copy_interior(st + dst0, pa, (size_t)16 * lda);
+          ga_copy_interior(st + GA_TILE + dst0, pb, (size_t)16 * ldb);
+        } else {
+          ga_copy(st, A, lda, i0, M, k0, ke);
+          ga_copy(st + GA_TILE, B, ldb, j0, N, k0, ke);
+        }
         cp_async_commit();
         if (it - done >= GA_INFLIGHT - 1) {  // the slice issued GA_INFLIGHT - 1 iterations ago has landed: publish it
           cp_async_wait<GA_INFLIGHT - 1>();
@@ -313,11 +333,20 @@ gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda
       const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
       const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
       const int b = t & 1;
+      const bool interior = vec_c && !split && i0 + GT_M <= M && j0 + GT_N <= N;
+      // bias of the 4 column blocks, requested BEFORE the wait for the accumulator (a global load per column block on the critical
+      // path of each block cost ~4 x 700 cycles per tile)
+      float4 bj4[4];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        bj4[cb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (interior && bias != nullptr) bj4[cb] = __ldg(reinterpret_cast<const float4*>(bias + j0 + cb * 32 + 4 * (lane & 7)));
+      }
       mbar_wait(&bars[GA_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128;
       const int rbase = i0 + q * 32;
-#pragma unroll 1
+#pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
         float h[32];
         if (kb < ke) {
@@ -337,7 +366,31 @@ gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda
           *reinterpret_cast<float4*>(tw + lane * GA_TW_STRIDE + 4 * e4) = make_float4(h[4 * e4], h[4 * e4 + 1], h[4 * e4 + 2], h[4 * e4 + 3]);
         __syncwarp();
         const int jb = j0 + cb * 32;
-        if (vec_c) {
+        if (interior) {
+          // interior tile: branch-free, all 8 shared-memory reads (and the 8 loads of C for beta) in flight before the first
+          // store.  The general path below runs one LDS -> FADD -> STG chain at a time behind its bounds checks; with 4 epilogue
+          // warps that chain, not the copies or the MMAs, set the pace of the memory-bound shapes (ncu: MMA warp waiting on
+          // ACC_EMPTY, producers on EMPTY, epilogue warps never idle)
+          const int j = jb + 4 * (lane & 7);
+          const float4 bj = bj4[cb];
+          float* o = C + (size_t)(rbase + (lane >> 3)) * ldc + j;
+          const float* ts = tw + (lane >> 3) * GA_TW_STRIDE + 4 * (lane & 7);
+          float4 v[8];
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) {
+            v[r4] = *reinterpret_cast<const float4*>(ts + r4 * 4 * GA_TW_STRIDE);
+            v[r4].x += bj.x; v[r4].y += bj.y; v[r4].z += bj.z; v[r4].w += bj.w;  // same order as the general path: (acc + bias) + C
+          }
+          if (beta) {
+            float4 c0[8];
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) c0[r4] = *reinterpret_cast<const float4*>(o + (size_t)r4 * 4 * ldc);
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) { v[r4].x += c0[r4].x; v[r4].y += c0[r4].y; v[r4].z += c0[r4].z; v[r4].w += c0[r4].w; }
+          }
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) *reinterpret_cast<float4*>(o + (size_t)r4 * 4 * ldc) = v[r4];
+        } else if (vec_c) {
           const int j = jb + 4 * (lane & 7);
           float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias != nullptr && z == 0 && j < N) bj = __ldg(reinterpret_cast<const float4*>(bias + j));

@@ -10,7 +10,8 @@ def tm(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-for (M, N, K) in [(128, 128, 64), (300, 200, 136), (1000, 128, 512), (257, 1024, 128), (32768, 1024, 128), (32768, 128, 512), (32768, 128, 128), (32768, 128, 1024), (32768, 512, 128)]:
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]]  # e.g. 32768x1024x128
+for (M, N, K) in SHAPES or [(128, 128, 64), (300, 200, 136), (1000, 128, 512), (257, 1024, 128), (32768, 1024, 128), (32768, 128, 512), (32768, 128, 128), (32768, 128, 1024), (32768, 512, 128)]:
     x, w, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda"), torch.randn(N, device="cuda")
     c0 = torch.randn(M, N, device="cuda")
     y = c0.clone()
