@@ -12,6 +12,7 @@
 // splits K (wgrad reduces over the B*N token rows) with an atomicAdd epilogue.
 #include <stdlib.h>
 #include "common.cuh"
+#include <cuda.h>
 #include "tc_common.cuh"
 
 namespace dfb200 {
@@ -434,6 +435,211 @@ gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// TMA form of the kernel above (the default for k-contiguous operands).  ncu of the cp.async form on the memory-bound training
+// shapes (32 768 x 1 024 x 128: 42 us against a 21 us HBM floor) showed producers and epilogue warps both > 80 % busy while DRAM,
+// L2 and the tensor pipe idled: every operand byte went through the LSU as a 16-byte LDGSTS, and every result byte through it
+// three times (STS, LDS, STG).  Here
+//   * ONE thread issues two cp.async.bulk.tensor.2d loads per k-slice (box 32 k x 128 rows, SWIZZLE_128B tensor maps built on the
+//     host per call; rows / k outside the operand are zero-filled by the TMA unit, so there is no edge form), completion by
+//     mbarrier complete_tx: all GA2_STAGES slices can be in flight and the LSU sees none of it;
+//   * 8 epilogue warps (two per TMEM lane quadrant, two 32-column blocks each) add the bias in registers, stage their 32 x 32
+//     block row-wise in shared memory and every lane sends ITS row to global memory with one 128-byte cp.async.bulk -- or
+//     cp.reduce.async.bulk .add.f32 for beta = 1 (C is never read into the SM) and for split-K partial sums (no scalar atomics).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int GA2_STAGES = 5, GA2_EPI = 8, GA2_THREADS = (2 + GA2_EPI) * 32;
+constexpr uint32_t GA2_SM_TW = GA2_STAGES * GA_STAGE;
+constexpr uint32_t GA2_TW_BYTES = 32 * 128;  // one 32 x 32 fp32 block, SWIZZLE_128B rows
+constexpr uint32_t GA2_SM_BAR = GA2_SM_TW + GA2_EPI * 2 * GA2_TW_BYTES;
+constexpr uint32_t GA2_SMEM = GA2_SM_BAR + 256;
+enum Ga2Bar { GA2_FULL = 0, GA2_EMPTY = GA2_STAGES, GA2_ACC_FULL = 2 * GA2_STAGES, GA2_ACC_EMPTY = 2 * GA2_STAGES + 2 };
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+               "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(GA2_THREADS, 1)
+gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_c, int M, int N, int K, const float* __restrict__ bias, int beta, int k_per_split, int tiles_n, int tiles_mn,
+                     int items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GA2_SM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GA2_SM_BAR + 192);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  if (tid == 0) {
+    for (int i = 0; i < GA2_STAGES; ++i) { mbar_init(&bars[GA2_FULL + i], 1); mbar_init(&bars[GA2_EMPTY + i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[GA2_ACC_FULL + i], 1); mbar_init(&bars[GA2_ACC_EMPTY + i], GA2_EPI * 32); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool split = items > tiles_mn;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 0) {
+    // =========================== TMA producer (one lane) ===========================
+    if (lane == 0) {
+      int it = 0;
+#pragma unroll 1
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int z = item / tiles_mn, mn = item - z * tiles_mn;
+        const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
+        const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+#pragma unroll 1
+        for (int k0 = kb; k0 < ke; k0 += GA_K, ++it) {
+          const int s = it % GA2_STAGES;
+          mbar_wait(&bars[GA2_EMPTY + s], (((uint32_t)(it / GA2_STAGES)) & 1u) ^ 1u);
+          const uint32_t st = sbase + s * GA_STAGE;
+          mbar_arrive_expect_tx(&bars[GA2_FULL + s], GA_STAGE);
+          tma_load_2d(st, &map_a, k0, i0, &bars[GA2_FULL + s]);
+          tma_load_2d(st + GA_TILE, &map_b, k0, j0, &bars[GA2_FULL + s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_tf32(GT_M, GT_N);
+    int it = 0, t = 0;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
+      const int z = item / tiles_mn;
+      const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+      const int b = t & 1;
+      mbar_wait(&bars[GA2_ACC_EMPTY + b], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+      tc_fence_after();
+      bool first = true;
+#pragma unroll 1
+      for (int k0 = kb; k0 < ke; k0 += GA_K, ++it) {
+        const int s = it % GA2_STAGES;
+        mbar_wait(&bars[GA2_FULL + s], ((uint32_t)(it / GA2_STAGES)) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t aa = sbase + s * GA_STAGE, bb = aa + GA_TILE;
+#pragma unroll
+          for (int ks = 0; ks < GA_K / 8; ++ks)
+            umma_tf32(tmem + b * 128, make_smem_desc(aa + ks * 32, 16, 1024) | ((uint64_t)2 << 61),
+                      make_smem_desc(bb + ks * 32, 16, 1024) | ((uint64_t)2 << 61), idesc, (!first || ks > 0) ? 1u : 0u);
+          umma_commit(&bars[GA2_EMPTY + s]);
+        }
+        __syncwarp();
+        first = false;
+      }
+      if (elect_one()) umma_commit(&bars[GA2_ACC_FULL + b]);
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    // =========================== epilogue: 8 warps, TMEM lanes 32 (warp % 4).., column blocks 2 half, 2 half + 1 ===========================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* tw = smem + GA2_SM_TW + (warp - 2) * (2 * GA2_TW_BYTES);  // two 4 KB staging blocks (1 024-byte aligned: SWIZZLE_128B)
+    int t = 0, nst = 0;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
+      const int z = item / tiles_mn, mn = item - z * tiles_mn;
+      const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
+      const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
+      const int b = t & 1;
+      // bias of this warp's two column blocks: lane l holds column l; requested before the wait for the accumulator
+      float bl[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = j0 + (2 * half + c) * 32 + lane;
+        bl[c] = (bias != nullptr && z == 0 && j < N) ? __ldg(bias + j) : 0.f;
+      }
+      mbar_wait(&bars[GA2_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128;
+      const int rbase = i0 + q * 32;
+#pragma unroll
+      for (int c = 0; c < 2; ++c, ++nst) {
+        const int cb = 2 * half + c;
+        float h[32];
+        if (kb < ke) {
+          tmem_ld32(taddr + cb * 32, h);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) h[e] = 0.f;
+        }
+        if (c == 1) {  // this warp's part of the accumulator is in registers
+          tc_fence_before();
+          mbar_arrive(&bars[GA2_ACC_EMPTY + b]);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) h[e] += __shfl_sync(0xFFFFFFFFu, bl[c], e);
+        uint8_t* buf = tw + (nst & 1) * GA2_TW_BYTES;
+        if (lane == 0) bulk_wait_read<1>();  // the store issued two blocks ago has read this buffer
+        __syncwarp();
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4)  // row = lane, 16-byte chunk e4 at position e4 ^ (row % 8): conflict-free, and what the tensor map expects
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((e4 ^ (lane & 7)) << 4)) = make_float4(h[4 * e4], h[4 * e4 + 1], h[4 * e4 + 2], h[4 * e4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {  // rows >= M / columns >= N of the box are clipped by the TMA unit
+          const int jb = j0 + cb * 32;
+          if (rbase < M && jb < N) {
+            if (split || beta) tma_reduce_add_2d(&map_c, jb, rbase, smem_u32(buf));
+            else tma_store_2d(&map_c, jb, rbase, smem_u32(buf));
+          }
+          bulk_commit();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on a driver symbol)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// k-contiguous fp32 operand (rows x K, leading dimension ld) as a 2-D tensor map with a 32 k x 128 row box, SWIZZLE_128B
+static bool make_operand_map(CUtensorMap* map, const float* P, int rows, int K, int ld, int box_rows = 128) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)GA_K, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace dfb200
 
 using namespace dfb200;
@@ -457,6 +663,20 @@ extern "C" int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, i
     DFB_REQUIRE(items <= 0x7fffffffLL, DFB200_ERR_INVALID_ARG, "gemm_bf16: too many tiles");
     const int n_sm = current_device_sm_count();
     DFB_REQUIRE(n_sm > 0, DFB200_ERR_CUDA, "gemm_bf16: cannot query the SM count of the current device");
+    // DFB200_GEMM_ASYNC=cp keeps the cp.async form (A/B measurements)
+    static const bool use_tma = [] { const char* e = getenv("DFB200_GEMM_ASYNC"); return e == nullptr || e[0] != 'c'; }();
+    if (use_tma && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+      CUtensorMap map_a, map_b, map_c;  // C: 32 x 32 boxes (the epilogue's staging blocks)
+      DFB_REQUIRE(make_operand_map(&map_a, A, M, K, lda) && make_operand_map(&map_b, B, N, K, ldb) && make_operand_map(&map_c, C, M, N, ldc, 32),
+                  DFB200_ERR_CUDA,
+                  "gemm_bf16: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldb=%d)", M, N, K, lda, ldb);
+      static DeviceOnce once2;
+      if (once2.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA2_SMEM));
+      gemm_tf32_tma_kernel<<<(int)(items < n_sm ? items : n_sm), GA2_THREADS, GA2_SMEM, as_stream(stream)>>>(
+          map_a, map_b, map_c, M, N, K, bias, beta, kps_a, tiles_n, tiles_n * tiles_m, (int)items);
+      DFB_LAUNCH_CHECK();
+      return DFB200_OK;
+    }
     static DeviceOnce once;
     if (once.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
     gemm_tf32_async_kernel<<<(int)(items < n_sm ? items : n_sm), GA_THREADS, GA_SMEM, as_stream(stream)>>>(

@@ -1,3 +1,4 @@
+#include <mutex>
 // Training-side primitives of the cross-diffusion denoiser (fp32, CUDA cores): the differentiable building blocks that
 // difffacto_b200/train_ops.py composes - through torch.autograd.Function wrappers - into the training forward/backward of
 // TransformerNet (reference: python/difffacto/models/diffusions/nets/attention.py:50-57 GEGLU, :77-94 FeedForward,
@@ -846,5 +847,96 @@ extern "C" int dfb200_coupling_backward(int B, int d, const float* s_t, const fl
   if (B <= 0 || d <= 0) return DFB200_OK;
   coupling_bwd_kernel<<<cdiv(B * d, 256), 256, 0, as_stream(stream)>>>(B, d, s_t, x2, ldx, dy1, ldy, dlogdet, ds_t, dx2, lddx);
   DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Adam for ALL parameter tensors of a group in one launch (torch.optim.Adam semantics, no amsgrad; the reference builds
+// torch.optim.Adam from the config, runner.py:60-66).  torch's fused multi-tensor Adam needs 8 launches of ~22 us for the ~130
+// small tensors of the denoiser plus 3 for the per-tensor step counters (0.25 ms of a 3 ms step); here the tensor table travels as a
+// kernel parameter (up to ADAM_MAX_TENSORS entries per launch), one CTA per 2 048-element chunk finds its tensor by binary search,
+// and the step count is ONE device scalar (so the launch is capturable in a CUDA graph).
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace dfb200 {
+constexpr int ADAM_MAX_TENSORS = 320, ADAM_CHUNK = 2048, ADAM_THREADS = 256;
+struct AdamBatch {
+  dfb200_adam_tensor_t t[ADAM_MAX_TENSORS];
+  int first_chunk[ADAM_MAX_TENSORS + 1];
+  int n;
+};
+__global__ void __launch_bounds__(ADAM_THREADS)
+adam_kernel(const __grid_constant__ AdamBatch B, const long long* __restrict__ step, float lr, float beta1, float beta2, float eps,
+            float weight_decay, const float* __restrict__ grad_scale) {
+  __shared__ float s_c[2];
+  if (threadIdx.x == 0) {  // bias corrections in double, as torch does on the host for the non-capturable form
+    const double t = (double)*step;
+    s_c[0] = (float)(1.0 / (1.0 - pow((double)beta1, t)));        // 1 / bias_correction1
+    s_c[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, t)));    // 1 / sqrt(bias_correction2)
+  }
+  int lo = 0, hi = B.n;  // last tensor with first_chunk <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (B.first_chunk[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const dfb200_adam_tensor_t T = B.t[lo];
+  const long long base = (long long)((int)blockIdx.x - B.first_chunk[lo]) * ADAM_CHUNK;
+  const int cnt = (int)min((long long)ADAM_CHUNK, T.count - base);
+  float* p = T.param + base;
+  const float* g = T.grad + base;
+  float* m = T.exp_avg + base;
+  float* v = T.exp_avg_sq + base;
+  __syncthreads();
+  const float step_size = lr * s_c[0], rsb2 = s_c[1];
+  const float gs = grad_scale != nullptr ? __ldg(grad_scale) : 1.f;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg = gg * gs + weight_decay * pp;
+    mm = mm + (gg - mm) * (1.f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+    vv = vv * beta2 + (1.f - beta2) * gg * gg;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    pp -= step_size * mm / (sqrtf(vv) * rsb2 + eps);
+  };
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  if (vec) {
+    for (int i = threadIdx.x * 4; i + 3 < cnt; i += ADAM_THREADS * 4) {
+      float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+      *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+    }
+    for (int i = (cnt & ~3) + threadIdx.x; i < cnt; i += ADAM_THREADS) upd(p[i], g[i], m[i], v[i]);
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += ADAM_THREADS) upd(p[i], g[i], m[i], v[i]);
+  }
+}
+}  // namespace dfb200
+
+extern "C" int dfb200_adam_step(int n_tensors, const dfb200_adam_tensor_t* tensors, const long long* step, float lr, float beta1, float beta2,
+                                float eps, float weight_decay, const float* grad_scale, dfb200_stream_t stream) {
+  DFB_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || tensors != nullptr) && step != nullptr, DFB200_ERR_INVALID_ARG, "adam_step: bad arguments");
+  DFB_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, DFB200_ERR_INVALID_ARG,
+              "adam_step: betas must be in [0, 1) and eps >= 0 (got %g, %g, %g)", (double)beta1, (double)beta2, (double)eps);
+  static dfb200::AdamBatch batch;  // 14 KB: built on the host, passed by value
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int done = 0;
+  while (done < n_tensors) {
+    int n = 0, chunks = 0;
+    while (done < n_tensors && n < dfb200::ADAM_MAX_TENSORS) {
+      const dfb200_adam_tensor_t& t = tensors[done++];
+      DFB_REQUIRE(t.count >= 0 && (t.count == 0 || (t.param && t.grad && t.exp_avg && t.exp_avg_sq)), DFB200_ERR_INVALID_ARG,
+                  "adam_step: tensor %d has a null pointer or a negative count", done - 1);
+      if (t.count == 0) continue;
+      const long long c = (t.count + dfb200::ADAM_CHUNK - 1) / dfb200::ADAM_CHUNK;
+      DFB_REQUIRE(chunks + c < 0x7fffffffLL, DFB200_ERR_INVALID_ARG, "adam_step: too many elements in one launch");
+      batch.t[n] = t;
+      batch.first_chunk[n] = chunks;
+      chunks += (int)c;
+      ++n;
+    }
+    if (n == 0) continue;
+    batch.first_chunk[n] = chunks;
+    batch.n = n;
+    dfb200::adam_kernel<<<chunks, dfb200::ADAM_THREADS, 0, as_stream(stream)>>>(batch, step, lr, beta1, beta2, eps, weight_decay, grad_scale);
+    DFB_LAUNCH_CHECK();
+  }
   return DFB200_OK;
 }

@@ -191,7 +191,13 @@ class Runner:
             use_graph = False
         if use_graph and ocfg.get("type") in ("Adam", "AdamW"):
             ocfg["capturable"] = True
-        opt = getattr(torch.optim, ocfg.pop("type"))(params, **ocfg)
+        if (ocfg.get("type") == "Adam" and not ocfg.get("amsgrad") and cfg.fused_adam is not False
+                and set(ocfg) <= {"type", "lr", "betas", "eps", "weight_decay", "amsgrad", "capturable"}):
+            # same update rule and state_dict layout as torch.optim.Adam, one launch for all tensors (difffacto_b200/optim.py)
+            from .optim import FusedAdam
+            opt = FusedAdam(params, **{k: v for k, v in ocfg.items() if k not in ("type", "amsgrad", "capturable")})
+        else:
+            opt = getattr(torch.optim, ocfg.pop("type"))(params, **ocfg)
         graphed = None
         max_epoch = int(cfg.max_epoch or 1)
         max_norm, log_interval, ckpt_interval = cfg.max_norm, int(cfg.log_interval or 50), int(cfg.checkpoint_interval or 500)

@@ -271,6 +271,20 @@ int dfb200_dropout(size_t count, float p, uint64_t seed, uint64_t offset, const 
  * captured in a CUDA graph draws a fresh mask on every replay when the graph increments the counter (train_graph.py). */
 int dfb200_dropout_stepped(size_t count, float p, uint64_t seed, uint64_t offset, const unsigned long long* step, const float* x,
                            const float* residual, float* y, dfb200_stream_t stream);
+/* torch.optim.Adam (no amsgrad; L2 weight decay) for a whole parameter group in ONE launch per 320 tensors.  `tensors` is a HOST array;
+ * every pointer in it is a device pointer to `count` fp32 elements.  *step (device) is the 1-based step count of THIS update (the
+ * caller increments it before the call - it lives on the device so that the update can be captured in a CUDA graph); the gradients
+ * are multiplied by *grad_scale when it is non-NULL (gradient clipping coefficient).  Replaces the optimizer the reference builds
+ * from cfg.optimizer (python/difffacto/runner/runner.py:60-66, torch.optim.Adam) on the training hot path. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long count;
+} dfb200_adam_tensor_t;
+int dfb200_adam_step(int n_tensors, const dfb200_adam_tensor_t* tensors, const long long* step, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, const float* grad_scale, dfb200_stream_t stream);
 /* Backward of dfb200_q_sample: any of the three outputs may be NULL. */
 int dfb200_q_sample_backward(int B, int N, int T, const float* sched, const int* t, const float* variance,
                              const float* noise, const float* grad_x_t, float* grad_x_start, float* grad_anchors,

@@ -290,7 +290,11 @@ def train_block(torch, dist, build_model, synthetic_batch, world, rank, local, f
     x0 = torch.sqrt(b["variance"]) * torch.randn(B, 3, N, device=dev, generator=g) + b["anchors"]
     flags = torch.ones(B, 1, N, device=dev)
     graphed = world == 1 or graph_ddp  # one CUDA graph per step (difffacto_b200/train_graph.py)
-    opt = torch.optim.Adam(d.parameters(), lr=1e-4, fused=True, capturable=graphed)
+    if os.environ.get("DFB200_TORCH_ADAM") == "1":  # A/B: torch's fused multi-tensor Adam (8 + 3 launches)
+        opt = torch.optim.Adam(d.parameters(), lr=1e-4, fused=True, capturable=graphed)
+    else:
+        from difffacto_b200.optim import FusedAdam
+        opt = FusedAdam(d.parameters(), lr=1e-4)  # torch.optim.Adam's update, one launch for all tensors
     ts, loss = [], None
 
     def loss_fn(x0, t, anchors, variance, code, params, assign, valid, flags):
