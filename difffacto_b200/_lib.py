@@ -74,6 +74,7 @@ SIGNATURES = {
     "dfb200_geglu_dropout_backward": (c_int, [ctypes.c_longlong, c_int, c_float, c_u64, c_u64, P, P, P, P, P, P]),
     "dfb200_dropout": (c_int, [c_size_t, c_float, c_u64, c_u64, P, P, P, P]),
     "dfb200_dropout_stepped": (c_int, [c_size_t, c_float, c_u64, c_u64, P, P, P, P, P]),
+    "dfb200_ff_in_forward": (c_int, [ctypes.c_longlong, c_int, c_int, P, c_int, P, c_int, P, c_float, c_u64, c_u64, P, P, P, P]),
     "dfb200_adam_step": (c_int, [c_int, P, P] + [c_float] * 5 + [P, P]),
     "dfb200_q_sample_backward": (c_int, [c_int] * 3 + [P] * 9),
     "dfb200_layernorm_forward": (c_int, [ctypes.c_longlong, c_int, P, P, P, P, P]),

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include "tc_common.cuh"
+#include "geglu_math.cuh"
 
 namespace dfb200 {
 using namespace tc;
@@ -474,9 +475,21 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+// GEGLU = true: FeedForward's first half in one kernel (attention.py:77-94: Linear(128, 2H) -> GEGLU -> Dropout).  A tile covers 64
+// hidden units: the B operand is TWO 64-row boxes of W1 (value rows n0.., gate rows H + n0..), so the accumulator holds the value
+// columns in [0, 64) and their gates in [64, 128); an epilogue warp reads a 32-column value block and its gate block, stores both
+// to h (kept for the backward) and u = dropout(value * gelu(gate)) to a second output -- the (M, 2H) pre-activation is not read again.
+struct GegluArgs {
+  int H;
+  float p, scale;
+  unsigned long long seed, offset;
+  const unsigned long long* step;
+};
+template <bool GEGLU>
 __global__ void __launch_bounds__(GA2_THREADS, 1)
 gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const __grid_constant__ CUtensorMap map_c, int M, int N, int K, const float* __restrict__ bias, int beta, int k_per_split, int tiles_n, int tiles_mn,
+                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_u, const GegluArgs G, int M, int N,
+                     int K, const float* __restrict__ bias, int beta, int k_per_split, int tiles_n, int tiles_mn,
                      int items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GA2_SM_BAR);
@@ -512,7 +525,13 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const uint32_t st = sbase + s * GA_STAGE;
           mbar_arrive_expect_tx(&bars[GA2_FULL + s], GA_STAGE);
           tma_load_2d(st, &map_a, k0, i0, &bars[GA2_FULL + s]);
-          tma_load_2d(st + GA_TILE, &map_b, k0, j0, &bars[GA2_FULL + s]);
+          if constexpr (GEGLU) {
+            const int n0 = (mn % tiles_n) * 64;
+            tma_load_2d(st + GA_TILE, &map_b, k0, n0, &bars[GA2_FULL + s]);
+            tma_load_2d(st + GA_TILE + 64 * 128, &map_b, k0, G.H + n0, &bars[GA2_FULL + s]);
+          } else {
+            tma_load_2d(st + GA_TILE, &map_b, k0, j0, &bars[GA2_FULL + s]);
+          }
         }
       }
     }
@@ -553,55 +572,97 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int q = warp & 3, half = (warp - 2) >> 2;
     uint8_t* tw = smem + GA2_SM_TW + (warp - 2) * (2 * GA2_TW_BYTES);  // two 4 KB staging blocks (1 024-byte aligned: SWIZZLE_128B)
     int t = 0, nst = 0;
+    // one 32 x 32 block (row = lane) -> staging -> global: rows >= M / columns outside the tensor are clipped by the TMA unit
+    auto stage_store = [&](const float (&h)[32], const CUtensorMap* map, int col, int row, bool issue, bool reduce) {
+      uint8_t* buf = tw + (nst & 1) * GA2_TW_BYTES;
+      ++nst;
+      if (lane == 0) bulk_wait_read<1>();  // the store issued two blocks ago has read this buffer
+      __syncwarp();
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4)  // 16-byte chunk e4 of row `lane` at position e4 ^ (row % 8): conflict-free, and what the tensor map expects
+        *reinterpret_cast<float4*>(buf + lane * 128 + ((e4 ^ (lane & 7)) << 4)) = make_float4(h[4 * e4], h[4 * e4 + 1], h[4 * e4 + 2], h[4 * e4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (issue) {
+          if (reduce) tma_reduce_add_2d(map, col, row, smem_u32(buf));
+          else tma_store_2d(map, col, row, smem_u32(buf));
+        }
+        bulk_commit();
+      }
+    };
 #pragma unroll 1
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
       const int z = item / tiles_mn, mn = item - z * tiles_mn;
-      const int i0 = (mn / tiles_n) * GT_M, j0 = (mn % tiles_n) * GT_N;
+      const int i0 = (mn / tiles_n) * GT_M;
       const int kb = z * k_per_split, ke = min(K, kb + k_per_split);
       const int b = t & 1;
-      // bias of this warp's two column blocks: lane l holds column l; requested before the wait for the accumulator
-      float bl[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int j = j0 + (2 * half + c) * 32 + lane;
-        bl[c] = (bias != nullptr && z == 0 && j < N) ? __ldg(bias + j) : 0.f;
-      }
-      mbar_wait(&bars[GA2_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
-      tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128;
       const int rbase = i0 + q * 32;
+      if constexpr (GEGLU) {
+        const int hcol = (mn % tiles_n) * 64 + 32 * half;  // first hidden unit of this warp's block
+        const float bv = bias != nullptr ? __ldg(bias + hcol + lane) : 0.f, bg = bias != nullptr ? __ldg(bias + G.H + hcol + lane) : 0.f;
+        mbar_wait(&bars[GA2_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
+        tc_fence_after();
+        float v[32], g[32];
+        tmem_ld32(taddr + 32 * half, v);
+        tmem_ld32(taddr + 64 + 32 * half, g);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&bars[GA2_ACC_EMPTY + b]);
 #pragma unroll
-      for (int c = 0; c < 2; ++c, ++nst) {
-        const int cb = 2 * half + c;
-        float h[32];
-        if (kb < ke) {
-          tmem_ld32(taddr + cb * 32, h);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) h[e] = 0.f;
+        for (int e = 0; e < 32; ++e) {
+          v[e] += __shfl_sync(0xFFFFFFFFu, bv, e);
+          g[e] += __shfl_sync(0xFFFFFFFFu, bg, e);
         }
-        if (c == 1) {  // this warp's part of the accumulator is in registers
-          tc_fence_before();
-          mbar_arrive(&bars[GA2_ACC_EMPTY + b]);
-        }
+        const bool in = rbase < M;
+        stage_store(v, &map_c, hcol, rbase, in, false);
+        stage_store(g, &map_c, G.H + hcol, rbase, in, false);
+        unsigned long long seed = G.seed;
+        if (G.p > 0.f && G.step != nullptr) seed += __ldg(G.step) * 0x9E3779B97F4A7C15ull;
+        const long long quad0 = (long long)(rbase + lane) * (G.H >> 2) + (hcol >> 2);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) h[e] += __shfl_sync(0xFFFFFFFFu, bl[c], e);
-        uint8_t* buf = tw + (nst & 1) * GA2_TW_BYTES;
-        if (lane == 0) bulk_wait_read<1>();  // the store issued two blocks ago has read this buffer
-        __syncwarp();
+        for (int e4 = 0; e4 < 8; ++e4) {
+          float m[4] = {1.f, 1.f, 1.f, 1.f};
+          if (G.p > 0.f) dropout_keep4(G.p, G.scale, seed, G.offset, quad0 + e4, m);
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4)  // row = lane, 16-byte chunk e4 at position e4 ^ (row % 8): conflict-free, and what the tensor map expects
-          *reinterpret_cast<float4*>(buf + lane * 128 + ((e4 ^ (lane & 7)) << 4)) = make_float4(h[4 * e4], h[4 * e4 + 1], h[4 * e4 + 2], h[4 * e4 + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {  // rows >= M / columns >= N of the box are clipped by the TMA unit
-          const int jb = j0 + cb * 32;
-          if (rbase < M && jb < N) {
-            if (split || beta) tma_reduce_add_2d(&map_c, jb, rbase, smem_u32(buf));
-            else tma_store_2d(&map_c, jb, rbase, smem_u32(buf));
+          for (int i = 0; i < 4; ++i) {
+            float cdf, pdf;
+            normal_cdf_pdf(g[4 * e4 + i], cdf, pdf);
+            v[4 * e4 + i] = m[i] * v[4 * e4 + i] * (g[4 * e4 + i] * cdf);  // same expression as geglu_dropout_fwd_kernel
           }
-          bulk_commit();
+        }
+        stage_store(v, &map_u, hcol, rbase, in, false);
+      } else {
+        const int j0 = (mn % tiles_n) * GT_N;
+        // bias of this warp's two column blocks: lane l holds column l; requested before the wait for the accumulator
+        float bl[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = j0 + (2 * half + c) * 32 + lane;
+          bl[c] = (bias != nullptr && z == 0 && j < N) ? __ldg(bias + j) : 0.f;
+        }
+        mbar_wait(&bars[GA2_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int cb = 2 * half + c;
+          float h[32];
+          if (kb < ke) {
+            tmem_ld32(taddr + cb * 32, h);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) h[e] = 0.f;
+          }
+          if (c == 1) {  // this warp's part of the accumulator is in registers
+            tc_fence_before();
+            mbar_arrive(&bars[GA2_ACC_EMPTY + b]);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) h[e] += __shfl_sync(0xFFFFFFFFu, bl[c], e);
+          const int jb = j0 + cb * 32;
+          stage_store(h, &map_c, jb, rbase, rbase < M && jb < N, split || beta);
         }
       }
     }
@@ -671,9 +732,10 @@ extern "C" int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, i
                   DFB200_ERR_CUDA,
                   "gemm_bf16: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldb=%d)", M, N, K, lda, ldb);
       static DeviceOnce once2;
-      if (once2.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA2_SMEM));
-      gemm_tf32_tma_kernel<<<(int)(items < n_sm ? items : n_sm), GA2_THREADS, GA2_SMEM, as_stream(stream)>>>(
-          map_a, map_b, map_c, M, N, K, bias, beta, kps_a, tiles_n, tiles_n * tiles_m, (int)items);
+      if (once2.first_time())
+        DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA2_SMEM));
+      gemm_tf32_tma_kernel<false><<<(int)(items < n_sm ? items : n_sm), GA2_THREADS, GA2_SMEM, as_stream(stream)>>>(
+          map_a, map_b, map_c, map_c, GegluArgs{}, M, N, K, bias, beta, kps_a, tiles_n, tiles_n * tiles_m, (int)items);
       DFB_LAUNCH_CHECK();
       return DFB200_OK;
     }
@@ -699,6 +761,33 @@ extern "C" int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, i
   else if (b_k_contiguous) GT_LAUNCH(false, true);
   else GT_LAUNCH(false, false);
 #undef GT_LAUNCH
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_ff_in_forward(long long M, int H, int K, const float* x, int ldx, const float* w1, int ldw, const float* b1, float p,
+                                    uint64_t seed, uint64_t offset, const unsigned long long* step, float* h, float* u,
+                                    dfb200_stream_t stream) {
+  DFB_REQUIRE(M >= 0 && M <= 0x7fffff00LL && H > 0 && K > 0, DFB200_ERR_INVALID_ARG, "ff_in_forward: bad sizes M=%lld H=%d K=%d", M, H, K);
+  DFB_REQUIRE(p >= 0.f && p < 1.f, DFB200_ERR_INVALID_ARG, "ff_in_forward: dropout p must be in [0, 1) (got %g)", (double)p);
+  if (M == 0) return DFB200_OK;
+  DFB_REQUIRE(H % 64 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && ldx >= K && ldw >= K &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(u)) & 15) == 0,
+              DFB200_ERR_UNSUPPORTED, "ff_in_forward: needs H %% 64 == 0, leading dimensions that are multiples of 4 and 16-byte aligned pointers (H=%d)", H);
+  CUtensorMap map_a, map_b, map_c, map_u;
+  DFB_REQUIRE(make_operand_map(&map_a, x, (int)M, K, ldx) && make_operand_map(&map_b, w1, 2 * H, K, ldw, 64) &&
+                  make_operand_map(&map_c, h, (int)M, 2 * H, 2 * H, 32) && make_operand_map(&map_u, u, (int)M, H, H, 32),
+              DFB200_ERR_CUDA, "ff_in_forward: cuTensorMapEncodeTiled failed (M=%lld H=%d K=%d)", M, H, K);
+  const int tiles_n = H / 64, tiles_m = cdiv((int)M, GT_M);
+  const long long items = (long long)tiles_n * tiles_m;
+  DFB_REQUIRE(items <= 0x7fffffffLL, DFB200_ERR_INVALID_ARG, "ff_in_forward: too many tiles");
+  const int n_sm = current_device_sm_count();
+  DFB_REQUIRE(n_sm > 0, DFB200_ERR_CUDA, "ff_in_forward: cannot query the SM count of the current device");
+  static DeviceOnce once;
+  if (once.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA2_SMEM));
+  const GegluArgs G{H, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed, offset, step};
+  gemm_tf32_tma_kernel<true><<<(int)(items < n_sm ? items : n_sm), GA2_THREADS, GA2_SMEM, as_stream(stream)>>>(
+      map_a, map_b, map_c, map_u, G, (int)M, 2 * H, K, b1, 0, cdiv(K, GA_K) * GA_K, tiles_n, tiles_n * tiles_m, (int)items);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
 }

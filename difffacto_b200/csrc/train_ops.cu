@@ -10,6 +10,7 @@
 
 #include "denoiser.cuh"
 #include "philox.cuh"
+#include "geglu_math.cuh"
 
 namespace dfb200 {
 
@@ -123,6 +124,40 @@ colsum_kernel(long long M, int N, const float* __restrict__ X, int ld, float* __
   }
 }
 
+// The same for 16-byte aligned rows (N % 4 == 0): a lane owns 4 columns, a warp reads 512 contiguous bytes per row with 4
+// independent 128-bit loads in flight (the scalar form keeps one 128-byte load per warp in flight: 14 us for 32 768 x 128, 2.5 us
+// of HBM time).
+constexpr int CS_ROWS = 128;
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(long long M, int N, const float* __restrict__ X, int ld, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 128 + lane * 4;
+  const long long r0 = (long long)blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < N) {
+    const float* col = X + j;
+    long long r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(col + r * ld)), b = __ldg(reinterpret_cast<const float4*>(col + (r + 8) * ld));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(col + (r + 16) * ld)), d = __ldg(reinterpret_cast<const float4*>(col + (r + 24) * ld));
+      s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y); s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(col + r * ld));
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  __shared__ float4 part[8][32];
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && j < N) {
+    float4 t = part[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 q = part[k][lane]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+    atomicAdd(out + j, t.x); atomicAdd(out + j + 1, t.y); atomicAdd(out + j + 2, t.z); atomicAdd(out + j + 3, t.w);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over 128 features (nn.LayerNorm(128), eps 1e-5): warp per row, lane = 4 features
 // ---------------------------------------------------------------------------------------------
@@ -186,21 +221,6 @@ ln_bwd_kernel(long long M, const float* __restrict__ x, const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 // GEGLU (attention.py:50-57): h = [a | g] (2*H wide), u = a * gelu(g) with the exact-CDF GELU (F.gelu default) to fp32 accuracy
 // ---------------------------------------------------------------------------------------------
-// Phi(g) and phi(g) of the standard normal with ONE exponential: erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z),
-// z = |g| / sqrt 2 (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7 -- the accuracy of erff's fp32 result), and phi(g) is that same
-// exp(-g^2 / 2) / sqrt(2 pi).  erff + expf cost ~40 instructions per element and bound the fused GEGLU kernels; this costs ~18.
-__device__ __forceinline__ void normal_cdf_pdf(float g, float& cdf, float& pdf) {
-  const float z = fabsf(g) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  const float e = __expf(-z * z);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float erf_abs = fmaf(-p * t, e, 1.f);
-  cdf = 0.5f * (1.f + copysignf(erf_abs, g));
-  pdf = 0.39894228040143267794f * e;
-}
 __global__ void __launch_bounds__(256)
 geglu_fwd_kernel(long long total, int H, const float* __restrict__ h, float* __restrict__ u) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,12 +250,6 @@ geglu_bwd_kernel(long long total, int H, const float* __restrict__ h, const floa
 // re-read the (M, H) activation for the dropout and re-read the (M, 2H) gradient for the column sums.  A thread owns 4 consecutive
 // hidden units (float4); the dropout mask is the one dfb200_dropout would draw on u (Philox quad = element index / 4), so fused
 // and unfused paths are interchangeable.  p == 0: no mask.  Requires H % 4 == 0.
-__device__ __forceinline__ void dropout_keep4(float p, float scale, uint64_t seed, uint64_t offset, long long quad, float (&m)[4]) {
-  uint32_t r[4];
-  philox4x32_10((uint64_t)quad, offset, seed, r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) m[i] = ((float)(r[i] >> 8) * 5.9604644775390625e-8f >= p) ? scale : 0.f;
-}
 __global__ void __launch_bounds__(256)
 geglu_dropout_fwd_kernel(long long quads, int H4, float p, float scale, uint64_t seed, uint64_t offset,
                          const unsigned long long* __restrict__ step, const float4* __restrict__ h, float4* __restrict__ u) {
@@ -479,6 +493,11 @@ extern "C" int dfb200_sgemm(int a_k_contiguous, int b_k_contiguous, int M, int N
 
 extern "C" int dfb200_colsum_accumulate(long long M, int N, const float* X, int ld, float* out, dfb200_stream_t stream) {
   if (M <= 0 || N <= 0) return DFB200_OK;
+  if (N % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && M >= 1024) {
+    colsum_vec_kernel<<<dim3(cdiv(N, 128), (unsigned)cdiv(M, (long long)CS_ROWS)), 256, 0, as_stream(stream)>>>(M, N, X, ld, out);
+    DFB_LAUNCH_CHECK();
+    return DFB200_OK;
+  }
   const int rpb = 512;
   colsum_kernel<<<dim3(cdiv(N, 32), (unsigned)cdiv(M, (long long)rpb)), 256, 0, as_stream(stream)>>>(M, N, X, ld, out, rpb);
   DFB_LAUNCH_CHECK();

@@ -7,6 +7,8 @@ forward AND backward pass runs in this repo's kernels.  Composed by TransformerN
 (models/diffusions/nets/attention.py), which follows the reference's module structure op for op
 (python/difffacto/models/diffusions/nets/attention.py:50-57, 77-94, 161-204, 259-306, 385-440).
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -195,6 +197,9 @@ def geglu(h):
     return GegluFn.apply(h)
 
 
+_FUSED_FF_IN = os.environ.get("DFB200_FUSED_FF_IN", "1") != "0"  # A/B switch: 0 = GEMM, then the GEGLU + dropout kernel
+
+
 class FFInFn(Function):
     """FeedForward's first half as ONE autograd node: u = dropout(geglu(x W1^T + b1)) (attention.py:77-94).  The GEGLU kernel
     applies the dropout mask (same Philox stream as DropoutFn) and, in the backward pass, also produces the bias gradient (column
@@ -206,11 +211,17 @@ class FFInFn(Function):
         M, K = x.shape
         H2 = weight.shape[0]
         h = torch.empty(M, H2, device=x.device, dtype=torch.float32)
-        ctx.bf16 = _GEMM_BF16
-        _sgemm(True, True, M, H2, K, x, K, weight, K, h, H2, bias=bias, bf16=ctx.bf16)
         u = torch.empty(M, H2 // 2, device=x.device, dtype=torch.float32)
-        with _lib.on(x.device):
-            check(_lib.load().dfb200_geglu_dropout_forward(M, H2 // 2, float(p), int(seed), int(offset), ptr(counter), ptr(h), ptr(u), stream()))
+        ctx.bf16 = _GEMM_BF16
+        if ctx.bf16 and _FUSED_FF_IN and (H2 // 2) % 64 == 0 and K % 4 == 0 and M >= 128:
+            # GEMM + GEGLU + dropout in one kernel (csrc/gemm_tc.cu, GEGLU epilogue): h is written once and not read back
+            with _lib.on(x.device):
+                check(_lib.load().dfb200_ff_in_forward(M, H2 // 2, K, ptr(x), K, ptr(weight), K, ptr(bias), float(p), int(seed), int(offset),
+                                                       ptr(counter), ptr(h), ptr(u), stream()))
+        else:
+            _sgemm(True, True, M, H2, K, x, K, weight, K, h, H2, bias=bias, bf16=ctx.bf16)
+            with _lib.on(x.device):
+                check(_lib.load().dfb200_geglu_dropout_forward(M, H2 // 2, float(p), int(seed), int(offset), ptr(counter), ptr(h), ptr(u), stream()))
         ctx.save_for_backward(x, weight, h)
         ctx.args = (float(p), int(seed), int(offset))
         ctx.counter, ctx.has_bias = counter, bias is not None

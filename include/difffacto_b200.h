@@ -256,6 +256,13 @@ int dfb200_part_attention_backward(int B, int N, const float* q, const float* k,
                                    dfb200_stream_t stream);
 /* timestep_embedding (nets/utils.py:7-24): out (B,256) = [cos(t f) | sin(t f)], f = the 128 frequencies. */
 int dfb200_timestep_embedding(int B, const float* t, const float* freqs128, float* out, dfb200_stream_t stream);
+/* FeedForward's first half in ONE kernel (attention.py:77-94: Linear(dim, 2H) -> GEGLU -> Dropout): h = x W1^T + b1 (M x 2H, kept for
+ * the backward) and u = dropout(h[:, :H] * gelu(h[:, H:])) (M x H) from a tcgen05 kind::tf32 GEMM whose epilogue applies the GEGLU and
+ * the dropout mask of dfb200_geglu_dropout_forward (same Philox key: seed / offset / *step), so the pre-activation is never read
+ * back.  x: M x K (leading dimension ldx), w1: 2H x K (ldw), both k-contiguous; needs H % 64 == 0, ldx % 4 == ldw % 4 == 0 and
+ * 16-byte aligned pointers, otherwise DFB200_ERR_UNSUPPORTED (callers then use dfb200_gemm_bf16 + dfb200_geglu_dropout_forward). */
+int dfb200_ff_in_forward(long long M, int H, int K, const float* x, int ldx, const float* w1, int ldw, const float* b1, float p,
+                         uint64_t seed, uint64_t offset, const unsigned long long* step, float* h, float* u, dfb200_stream_t stream);
 /* FeedForward's GEGLU fused with the Dropout behind it (attention.py:77-94): u = dropout(a * gelu(g)) for h = [a | g] (M, 2H), with
  * the mask dfb200_dropout(_stepped) would draw on u (p = 0: none; step may be NULL).  The backward also accumulates the column
  * sums of dh (M, 2H) into db_accum (2H floats, may be NULL): the bias gradient of the Linear that produced h. */

@@ -310,3 +310,16 @@ def test_fused_adam_matches_torch_adam_and_is_graph_capturable():
         assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
     with pytest.raises(NotImplementedError):
         FusedAdam(q1, amsgrad=True)
+
+
+@pytest.mark.parametrize("M,N,ld", [(5000, 128, 128), (4097, 132, 136), (1024, 4, 4), (100, 7, 7), (3000, 130, 131)])
+def test_colsum_accumulate_vector_and_scalar_forms(M, N, ld):
+    """dfb200_colsum_accumulate (bias gradients): out[j] += sum_i X[i, j] - the 128-bit form (N, ld multiples of 4, M >= 1024) and the
+    scalar form, on a strided matrix, accumulating into a non-zero output."""
+    from difffacto_b200 import _lib
+    torch.manual_seed(M + N)
+    X = torch.randn(M, ld, device="cuda")
+    out = torch.randn(N, device="cuda")
+    want = out.double() + X[:, :N].double().sum(0)
+    _lib.check(_lib.load().dfb200_colsum_accumulate(M, N, _lib.ptr(X), ld, _lib.ptr(out), _lib.stream()))
+    assert torch.allclose(out.double(), want, rtol=1e-5, atol=2e-4 * M ** 0.5)
