@@ -450,6 +450,7 @@ gemm_tf32_async_kernel(int M, int N, int K, const float* __restrict__ A, int lda
 //     cp.reduce.async.bulk .add.f32 for beta = 1 (C is never read into the SM) and for split-K partial sums (no scalar atomics).
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int GA2_STAGES = 5, GA2_EPI = 8, GA2_THREADS = (2 + GA2_EPI) * 32;
+constexpr int GA2_EPI_GEGLU = 16, GA2_THREADS_GEGLU = (2 + GA2_EPI_GEGLU) * 32;  // GEGLU epilogue: 16 warps x 16 hidden units (latency-bound math)
 constexpr uint32_t GA2_SM_TW = GA2_STAGES * GA_STAGE;
 constexpr uint32_t GA2_TW_BYTES = 32 * 128;  // one 32 x 32 fp32 block, SWIZZLE_128B rows
 constexpr uint32_t GA2_SM_BAR = GA2_SM_TW + GA2_EPI * 2 * GA2_TW_BYTES;
@@ -486,7 +487,7 @@ struct GegluArgs {
   const unsigned long long* step;
 };
 template <bool GEGLU>
-__global__ void __launch_bounds__(GA2_THREADS, 1)
+__global__ void __launch_bounds__(GEGLU ? GA2_THREADS_GEGLU : GA2_THREADS, 1)
 gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_u, const GegluArgs G, int M, int N,
                      int K, const float* __restrict__ bias, int beta, int k_per_split, int tiles_n, int tiles_mn,
@@ -498,7 +499,7 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
   if (tid == 0) {
     for (int i = 0; i < GA2_STAGES; ++i) { mbar_init(&bars[GA2_FULL + i], 1); mbar_init(&bars[GA2_EMPTY + i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars[GA2_ACC_FULL + i], 1); mbar_init(&bars[GA2_ACC_EMPTY + i], GA2_EPI * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[GA2_ACC_FULL + i], 1); mbar_init(&bars[GA2_ACC_EMPTY + i], (GEGLU ? GA2_EPI_GEGLU : GA2_EPI) * 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
@@ -570,8 +571,24 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else {
     // =========================== epilogue: 8 warps, TMEM lanes 32 (warp % 4).., column blocks 2 half, 2 half + 1 ===========================
     const int q = warp & 3, half = (warp - 2) >> 2;
-    uint8_t* tw = smem + GA2_SM_TW + (warp - 2) * (2 * GA2_TW_BYTES);  // two 4 KB staging blocks (1 024-byte aligned: SWIZZLE_128B)
+    // two staging blocks per warp: 32 x 32 fp32 (4 KB, SWIZZLE_128B) or, GEGLU form, 32 x 16 (2 KB, SWIZZLE_64B); 64 KB in all either way
+    uint8_t* tw = smem + GA2_SM_TW + (warp - 2) * (GEGLU ? GA2_TW_BYTES : 2 * GA2_TW_BYTES);
     int t = 0, nst = 0;
+    auto stage_store16 = [&](const float (&h)[16], const CUtensorMap* map, int col, int row, bool issue) {
+      uint8_t* buf = tw + (nst & 1) * (GA2_TW_BYTES / 2);
+      ++nst;
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4)  // SWIZZLE_64B: chunk e4 of row `lane` at position e4 ^ ((row / 2) % 4)
+        *reinterpret_cast<float4*>(buf + lane * 64 + ((e4 ^ ((lane >> 1) & 3)) << 4)) = make_float4(h[4 * e4], h[4 * e4 + 1], h[4 * e4 + 2], h[4 * e4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (issue) tma_store_2d(map, col, row, smem_u32(buf));
+        bulk_commit();
+      }
+    };
     // one 32 x 32 block (row = lane) -> staging -> global: rows >= M / columns outside the tensor are clipped by the TMA unit
     auto stage_store = [&](const float (&h)[32], const CUtensorMap* map, int col, int row, bool issue, bool reduce) {
       uint8_t* buf = tw + (nst & 1) * GA2_TW_BYTES;
@@ -600,29 +617,34 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128;
       const int rbase = i0 + q * 32;
       if constexpr (GEGLU) {
-        const int hcol = (mn % tiles_n) * 64 + 32 * half;  // first hidden unit of this warp's block
-        const float bv = bias != nullptr ? __ldg(bias + hcol + lane) : 0.f, bg = bias != nullptr ? __ldg(bias + G.H + hcol + lane) : 0.f;
+        // warp = (quadrant q, slice): 16 hidden units; the Philox + normal-CDF math of the GEGLU is a long dependent chain per element,
+        // so the block is kept small and 16 warps (4 per scheduler) hide each other's latencies (8 warps x 32 units: 67 us per
+        // 32 768 x 1 024 x 128 launch against 38 us for the plain GEMM)
+        const int slice = (warp - 2) >> 2;
+        const int hcol = (mn % tiles_n) * 64 + 16 * slice;  // first hidden unit of this warp's block
+        float bb = 0.f;  // lanes 0-15: value bias of unit hcol + lane, lanes 16-31: gate bias of unit hcol + lane - 16
+        if (bias != nullptr) bb = __ldg(bias + (lane < 16 ? hcol + lane : G.H + hcol + lane - 16));
         mbar_wait(&bars[GA2_ACC_FULL + b], ((uint32_t)(t >> 1)) & 1u);
         tc_fence_after();
-        float v[32], g[32];
-        tmem_ld32(taddr + 32 * half, v);
-        tmem_ld32(taddr + 64 + 32 * half, g);
+        float v[16], g[16];
+        tmem_ld16(taddr + 16 * slice, v);
+        tmem_ld16(taddr + 64 + 16 * slice, g);
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&bars[GA2_ACC_EMPTY + b]);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          v[e] += __shfl_sync(0xFFFFFFFFu, bv, e);
-          g[e] += __shfl_sync(0xFFFFFFFFu, bg, e);
+        for (int e = 0; e < 16; ++e) {
+          v[e] += __shfl_sync(0xFFFFFFFFu, bb, e);
+          g[e] += __shfl_sync(0xFFFFFFFFu, bb, 16 + e);
         }
         const bool in = rbase < M;
-        stage_store(v, &map_c, hcol, rbase, in, false);
-        stage_store(g, &map_c, G.H + hcol, rbase, in, false);
+        stage_store16(v, &map_c, hcol, rbase, in);
+        stage_store16(g, &map_c, G.H + hcol, rbase, in);
         unsigned long long seed = G.seed;
         if (G.p > 0.f && G.step != nullptr) seed += __ldg(G.step) * 0x9E3779B97F4A7C15ull;
         const long long quad0 = (long long)(rbase + lane) * (G.H >> 2) + (hcol >> 2);
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
+        for (int e4 = 0; e4 < 4; ++e4) {
           float m[4] = {1.f, 1.f, 1.f, 1.f};
           if (G.p > 0.f) dropout_keep4(G.p, G.scale, seed, G.offset, quad0 + e4, m);
 #pragma unroll
@@ -632,7 +654,7 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             v[4 * e4 + i] = m[i] * v[4 * e4 + i] * (g[4 * e4 + i] * cdf);  // same expression as geglu_dropout_fwd_kernel
           }
         }
-        stage_store(v, &map_u, hcol, rbase, in, false);
+        stage_store16(v, &map_u, hcol, rbase, in);
       } else {
         const int j0 = (mn % tiles_n) * GT_N;
         // bias of this warp's two column blocks: lane l holds column l; requested before the wait for the accumulator
@@ -690,15 +712,15 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 // k-contiguous fp32 operand (rows x K, leading dimension ld) as a 2-D tensor map with a 32 k x 128 row box, SWIZZLE_128B
-static bool make_operand_map(CUtensorMap* map, const float* P, int rows, int K, int ld, int box_rows = 128) {
+static bool make_operand_map(CUtensorMap* map, const float* P, int rows, int K, int ld, int box_rows = 128, int box_cols = GA_K) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)GA_K, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};  // inner extent 128 bytes -> SWIZZLE_128B, 64 bytes -> SWIZZLE_64B
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace dfb200
@@ -776,7 +798,7 @@ extern "C" int dfb200_ff_in_forward(long long M, int H, int K, const float* x, i
               DFB200_ERR_UNSUPPORTED, "ff_in_forward: needs H %% 64 == 0, leading dimensions that are multiples of 4 and 16-byte aligned pointers (H=%d)", H);
   CUtensorMap map_a, map_b, map_c, map_u;
   DFB_REQUIRE(make_operand_map(&map_a, x, (int)M, K, ldx) && make_operand_map(&map_b, w1, 2 * H, K, ldw, 64) &&
-                  make_operand_map(&map_c, h, (int)M, 2 * H, 2 * H, 32) && make_operand_map(&map_u, u, (int)M, H, H, 32),
+                  make_operand_map(&map_c, h, (int)M, 2 * H, 2 * H, 32, 16) && make_operand_map(&map_u, u, (int)M, H, H, 32, 16),
               DFB200_ERR_CUDA, "ff_in_forward: cuTensorMapEncodeTiled failed (M=%lld H=%d K=%d)", M, H, K);
   const int tiles_n = H / 64, tiles_m = cdiv((int)M, GT_M);
   const long long items = (long long)tiles_n * tiles_m;
@@ -786,7 +808,7 @@ extern "C" int dfb200_ff_in_forward(long long M, int H, int K, const float* x, i
   static DeviceOnce once;
   if (once.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA2_SMEM));
   const GegluArgs G{H, p, p > 0.f ? 1.f / (1.f - p) : 1.f, seed, offset, step};
-  gemm_tf32_tma_kernel<true><<<(int)(items < n_sm ? items : n_sm), GA2_THREADS, GA2_SMEM, as_stream(stream)>>>(
+  gemm_tf32_tma_kernel<true><<<(int)(items < n_sm ? items : n_sm), GA2_THREADS_GEGLU, GA2_SMEM, as_stream(stream)>>>(
       map_a, map_b, map_c, map_u, G, (int)M, 2 * H, K, b1, 0, cdiv(K, GA_K) * GA_K, tiles_n, tiles_n * tiles_m, (int)items);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
