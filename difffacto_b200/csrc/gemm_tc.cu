@@ -31,10 +31,12 @@ constexpr uint32_t GT_TILE_BYTES = GT_M * GT_K * 2;  // 16 KB per operand per st
 //     touches 8 rows x 128 contiguous bytes (8 cache lines; the row-per-lane mapping of round 1 touched 32), and a quarter warp
 //     stores 8 consecutive rows of one chunk (conflict-free STS.128).
 //   row-contiguous mapping: thread -> row tid % 128, chunks (tid / 128) * 4 + ch; lanes read consecutive rows of one k (coalesced).
-template <bool KC>
+// operand layouts of the register-staged kernel (template parameters: each mapping keeps its own register budget)
+constexpr int GT_ROWS = 0, GT_KC = 1, GT_ROWS4 = 2;  // row-contiguous 32-bit loads, k-contiguous, row-contiguous 128-bit loads
+template <int L>
 __device__ __forceinline__ void gt_load(float (&v)[4][8], const float* __restrict__ P, int ld, int r0, int rows, int k0, int kend, bool vec_ok) {
   const int t = threadIdx.x;
-  if (KC) {
+  if (L == GT_KC) {
     const int rsub = t & 7, kq = (t >> 3) & 3, rblk = t >> 5;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -53,29 +55,60 @@ __device__ __forceinline__ void gt_load(float (&v)[4][8], const float* __restric
       }
     }
   } else {
+    if (L == GT_ROWS4) {
+      // 128-bit form (ld % 4 == 0, 16-byte aligned base): thread -> rows 4 (t % 32) .. + 3, k-chunk t / 32; a warp reads 512 contiguous
+      // bytes of ONE k per instruction, 8 LDG.128 per operand and slice instead of 32 LDG.32.  v[i][e] = (row 4 (t % 32) + i, k 8 (t / 32) + e)
+      const int rq = t & 31, kc = t >> 5, gr = r0 + 4 * rq, gk = k0 + kc * 8;
+      if (r0 + GT_M <= rows && k0 + GT_K <= kend) {
+        const float* p = P + (size_t)gk * ld + gr;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(p + (size_t)e * ld));
+          v[0][e] = f.x; v[1][e] = f.y; v[2][e] = f.z; v[3][e] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[i][e] = (gr + i < rows && gk + e < kend) ? __ldg(P + (size_t)(gk + e) * ld + gr + i) : 0.f;
+      }
+      return;
+    }
     const int r = t & 127, kh = t >> 7, gr = r0 + r;
+    if (r0 + GT_M <= rows && k0 + GT_K <= kend) {
+      // interior slice (uniform per CTA): one pointer, 32 loads at constant multiples of ld.  The guarded form below spends ~5
+      // instructions per element on bounds and addresses; ncu of the wgrad shapes showed the kernel issue-bound (52 % of the issue
+      // slots busy at 3.1 TB/s) on exactly that
+      const float* p = P + (size_t)(k0 + kh * 32) * ld + gr;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int gk = k0 + (kh * 4 + c) * 8;
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[c][e] = (gr < rows && gk + e < kend) ? __ldg(P + (size_t)(gk + e) * ld + gr) : 0.f;
+        for (int e = 0; e < 8; ++e) v[c][e] = __ldg(p + (size_t)(c * 8 + e) * ld);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int gk = k0 + (kh * 4 + c) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[c][e] = (gr < rows && gk + e < kend) ? __ldg(P + (size_t)(gk + e) * ld + gr) : 0.f;
+      }
     }
   }
 }
-template <bool KC>
+template <int L>
 __device__ __forceinline__ void gt_store(uint8_t* tile, const float (&v)[4][8]) {
   const int t = threadIdx.x;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     int r, kc;
-    if (KC) { r = (t >> 5) * 16 + (t & 7) + 8 * (c >> 1); kc = ((t >> 3) & 3) + 4 * (c & 1); }
+    if (L == GT_KC) { r = (t >> 5) * 16 + (t & 7) + 8 * (c >> 1); kc = ((t >> 3) & 3) + 4 * (c & 1); }
+    else if (L == GT_ROWS4) { r = 4 * (t & 31) + c; kc = t >> 5; }  // 128-bit load mapping (4-way bank conflict on this store, measured cheaper than the loads it saves)
     else { r = t & 127; kc = (t >> 7) * 4 + c; }
     *reinterpret_cast<uint4*>(tile + kc * (GT_M * 16) + r * 16) =
         make_uint4(pack_bf16(v[c][0], v[c][1]), pack_bf16(v[c][2], v[c][3]), pack_bf16(v[c][4], v[c][5]), pack_bf16(v[c][6], v[c][7]));
   }
 }
 
-template <bool A_KC, bool B_KC>
+template <int A_L, int B_L>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                float* __restrict__ C, int ldc, const float* __restrict__ bias, int beta, int k_per_split) {
@@ -97,12 +130,12 @@ gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const 
   uint32_t ph[2] = {0, 0};
   int it = 0;
   // 32-byte loads need k-contiguous rows that start on 32-byte boundaries (uniform per launch)
-  const bool a_vec = A_KC && (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 31) == 0) && (kbeg % 8 == 0);
-  const bool b_vec = B_KC && (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(B) & 31) == 0) && (kbeg % 8 == 0);
+  const bool a_vec = (A_L == GT_KC) && (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 31) == 0) && (kbeg % 8 == 0);
+  const bool b_vec = (B_L == GT_KC) && (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(B) & 31) == 0) && (kbeg % 8 == 0);
   float va[4][8], vb[4][8];
   if (kbeg < kend) {
-    gt_load<A_KC>(va, A, lda, i0, M, kbeg, kend, a_vec);
-    gt_load<B_KC>(vb, B, ldb, j0, N, kbeg, kend, b_vec);
+    gt_load<A_L>(va, A, lda, i0, M, kbeg, kend, a_vec);
+    gt_load<B_L>(vb, B, ldb, j0, N, kbeg, kend, b_vec);
   }
   for (int k0 = kbeg; k0 < kend; k0 += GT_K, ++it) {
     const int s = it & 1;
@@ -110,11 +143,11 @@ gemm_tc_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const 
       mbar_wait(&bars[s], ph[s]);
       ph[s] ^= 1;
     }
-    gt_store<A_KC>(a_tiles + s * GT_TILE_BYTES, va);
-    gt_store<B_KC>(b_tiles + s * GT_TILE_BYTES, vb);
+    gt_store<A_L>(a_tiles + s * GT_TILE_BYTES, va);
+    gt_store<B_L>(b_tiles + s * GT_TILE_BYTES, vb);
     if (k0 + GT_K < kend) {  // the next slice's operands fly while this slice's MMAs run
-      gt_load<A_KC>(va, A, lda, i0, M, k0 + GT_K, kend, a_vec);
-      gt_load<B_KC>(vb, B, ldb, j0, N, k0 + GT_K, kend, b_vec);
+      gt_load<A_L>(va, A, lda, i0, M, k0 + GT_K, kend, a_vec);
+      gt_load<B_L>(vb, B, ldb, j0, N, k0 + GT_K, kend, b_vec);
     }
     fence_proxy_async();
     __syncthreads();
@@ -778,10 +811,17 @@ extern "C" int dfb200_gemm_bf16(int a_k_contiguous, int b_k_contiguous, int M, i
     if (once.first_time()) DFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     gemm_tc_kernel<AK, BK><<<grid, GT_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta, kps);                  \
   } while (0)
-  if (a_k_contiguous && b_k_contiguous) GT_LAUNCH(true, true);
-  else if (a_k_contiguous) GT_LAUNCH(true, false);
-  else if (b_k_contiguous) GT_LAUNCH(false, true);
-  else GT_LAUNCH(false, false);
+  // row-contiguous operands take 128-bit loads when their rows start on 16-byte boundaries
+  const int la = a_k_contiguous ? GT_KC : (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) ? GT_ROWS4 : GT_ROWS;
+  const int lb = b_k_contiguous ? GT_KC : (ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0) ? GT_ROWS4 : GT_ROWS;
+#define GT_ROW(LA)                                  \
+  if (lb == GT_KC) GT_LAUNCH(LA, GT_KC);            \
+  else if (lb == GT_ROWS4) GT_LAUNCH(LA, GT_ROWS4); \
+  else GT_LAUNCH(LA, GT_ROWS)
+  if (la == GT_KC) { GT_ROW(GT_KC); }
+  else if (la == GT_ROWS4) { GT_ROW(GT_ROWS4); }
+  else { GT_ROW(GT_ROWS); }
+#undef GT_ROW
 #undef GT_LAUNCH
   DFB_LAUNCH_CHECK();
   return DFB200_OK;
