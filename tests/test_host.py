@@ -178,3 +178,23 @@ def test_gather_shapes_world_size_2_gloo(total):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_fused_adam_host_contract():
+    """difffacto_b200/optim.py FusedAdam on the host side: torch.optim.Adam's constructor contract (defaults, param groups, state_dict
+    keys), loud failures for what it does not implement, and no CPU fallback (a CPU parameter is an error, not a slow path)."""
+    from difffacto_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(5))
+    opt = FusedAdam([p], lr=2e-3, betas=(0.8, 0.9), eps=1e-6, weight_decay=0.1)
+    g = opt.param_groups[0]
+    assert (g["lr"], g["betas"], g["eps"], g["weight_decay"], g["capturable"]) == (2e-3, (0.8, 0.9), 1e-6, 0.1, True)
+    assert set(opt.state_dict()) == {"state", "param_groups"}
+    with pytest.raises(NotImplementedError):
+        FusedAdam([p], amsgrad=True)
+    for bad in (dict(lr=-1.0), dict(betas=(1.0, 0.9)), dict(betas=(0.9, -0.1)), dict(eps=-1e-8), dict(weight_decay=-0.1)):
+        with pytest.raises(ValueError):
+            FusedAdam([p], **bad)
+    opt.step()                       # no gradient yet: nothing to do
+    p.grad = torch.ones(5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
