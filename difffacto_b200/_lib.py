@@ -65,6 +65,7 @@ SIGNATURES = {
     "dfb200_colsum_accumulate": (c_int, [ctypes.c_longlong, c_int, P, c_int, P, P]),
     "dfb200_layernorm128_forward": (c_int, [ctypes.c_longlong] + [P] * 7),
     "dfb200_layernorm128_backward": (c_int, [ctypes.c_longlong] + [P] * 9),
+    "dfb200_layernorm128_backward_residual": (c_int, [ctypes.c_longlong] + [P] * 10),
     "dfb200_geglu_forward": (c_int, [ctypes.c_longlong, c_int, P, P, P]),
     "dfb200_geglu_backward": (c_int, [ctypes.c_longlong, c_int, P, P, P, P]),
     "dfb200_part_attention_forward": (c_int, [c_int, c_int] + [P] * 7),

@@ -186,7 +186,7 @@ ln_fwd_kernel(long long M, const float* __restrict__ x, const float* __restrict_
 // dx = rstd * (g.dy - mean(g.dy) - xhat * mean(g.dy.xhat));  dgamma += dy.xhat;  dbeta += dy   (atomics per CTA)
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(long long M, const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean_in,
-              const float* __restrict__ rstd_in, const float* __restrict__ dy, float* __restrict__ dx,
+              const float* __restrict__ rstd_in, const float* __restrict__ dy, const float* __restrict__ dres, float* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp) {
   __shared__ float red[2][D_MODEL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -199,6 +199,9 @@ ln_bwd_kernel(long long M, const float* __restrict__ x, const float* __restrict_
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * D_MODEL) + lane);
     const float4 d = __ldg(reinterpret_cast<const float4*>(dy + row * D_MODEL) + lane);
     const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    // gradient of the residual connection that bypasses this LayerNorm (x also feeds `x + branch(LN(x))`): added here instead of by a
+    // separate accumulation pass over the (M, 128) tensor
+    const float4 dr = dres != nullptr ? __ldg(reinterpret_cast<const float4*>(dres + row * D_MODEL) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
     const float4 gd = make_float4(gg.x * d.x, gg.y * d.y, gg.z * d.z, gg.w * d.w);
     float m1 = gd.x + gd.y + gd.z + gd.w;
@@ -207,8 +210,8 @@ ln_bwd_kernel(long long M, const float* __restrict__ x, const float* __restrict_
     for (int s = 16; s >= 1; s >>= 1) { m1 += __shfl_xor_sync(0xFFFFFFFFu, m1, s); m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, s); }
     m1 *= (1.f / D_MODEL); m2 *= (1.f / D_MODEL);
     reinterpret_cast<float4*>(dx + row * D_MODEL)[lane] =
-        make_float4(rstd * (gd.x - m1 - xh.x * m2), rstd * (gd.y - m1 - xh.y * m2), rstd * (gd.z - m1 - xh.z * m2),
-                    rstd * (gd.w - m1 - xh.w * m2));
+        make_float4(rstd * (gd.x - m1 - xh.x * m2) + dr.x, rstd * (gd.y - m1 - xh.y * m2) + dr.y, rstd * (gd.z - m1 - xh.z * m2) + dr.z,
+                    rstd * (gd.w - m1 - xh.w * m2) + dr.w);
     ag.x += d.x * xh.x; ag.y += d.y * xh.y; ag.z += d.z * xh.z; ag.w += d.w * xh.w;
     ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
   }
@@ -517,7 +520,18 @@ extern "C" int dfb200_layernorm128_backward(long long M, const float* x, const f
                                             dfb200_stream_t stream) {
   if (M <= 0) return DFB200_OK;
   const int rpw = 16;
-  ln_bwd_kernel<<<(unsigned)cdiv(M, (long long)(8 * rpw)), 256, 0, as_stream(stream)>>>(M, x, gamma, mean, rstd, dy, dx, dgamma_accum,
+  ln_bwd_kernel<<<(unsigned)cdiv(M, (long long)(8 * rpw)), 256, 0, as_stream(stream)>>>(M, x, gamma, mean, rstd, dy, nullptr, dx, dgamma_accum,
+                                                                                        dbeta_accum, rpw);
+  DFB_LAUNCH_CHECK();
+  return DFB200_OK;
+}
+
+extern "C" int dfb200_layernorm128_backward_residual(long long M, const float* x, const float* gamma, const float* mean, const float* rstd,
+                                                      const float* dy, const float* dres, float* dx, float* dgamma_accum, float* dbeta_accum,
+                                                      dfb200_stream_t stream) {
+  if (M <= 0) return DFB200_OK;
+  const int rpw = 16;
+  ln_bwd_kernel<<<(unsigned)cdiv(M, (long long)(8 * rpw)), 256, 0, as_stream(stream)>>>(M, x, gamma, mean, rstd, dy, dres, dx, dgamma_accum,
                                                                                         dbeta_accum, rpw);
   DFB_LAUNCH_CHECK();
   return DFB200_OK;

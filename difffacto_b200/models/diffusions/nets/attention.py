@@ -253,7 +253,7 @@ class TransformerNet(nn.Module):
         kv_all = T.linear(ctx2d, wkv).view(B * self.n_class, 2 * len(self.transformer_blocks), self.inner_dim)
         kv_parts = kv_all.transpose(0, 1).contiguous().unbind(0)  # 2 * depth tensors (4B, 128); backward = one stack
         for li, blk in enumerate(self.transformer_blocks):
-            a = T.layernorm128(h, blk.norm2.weight, blk.norm2.bias)
+            a, h = T.layernorm128_res(h, blk.norm2.weight, blk.norm2.bias)  # h: the same values, as the residual of this sub-block
             q = T.linear(a, blk.attn2.to_q.weight)
             k = kv_parts[2 * li].view(B, self.n_class, self.inner_dim)
             v = kv_parts[2 * li + 1].view(B, self.n_class, self.inner_dim)
@@ -262,7 +262,7 @@ class TransformerNet(nn.Module):
                 h = T.dropout(T.linear(o, blk.attn2.to_out[0].weight, blk.attn2.to_out[0].bias), self.dropout, True, residual=h)
             else:
                 h = T.linear(o, blk.attn2.to_out[0].weight, blk.attn2.to_out[0].bias, h)
-            f = T.layernorm128(h, blk.norm3.weight, blk.norm3.bias)
+            f, h = T.layernorm128_res(h, blk.norm3.weight, blk.norm3.bias)
             h = self._ff(blk.ff, f, residual=h)
         h = T.layernorm128(h, self.post_norm.weight, self.post_norm.bias)
         out = T.linear(h, self.proj_out.weight, self.proj_out.bias)

@@ -173,6 +173,51 @@ def layernorm128(x, gamma, beta):
     return LayerNorm128Fn.apply(x, gamma, beta)
 
 
+_LN_RES = os.environ.get("DFB200_LN_RES", "1") != "0"
+
+
+class LayerNorm128ResFn(Function):
+    """(LayerNorm(x), x): the second output is x itself, to be used as the residual of the block the LayerNorm opens
+    (x + branch(LayerNorm(x)), attention.py:296-306).  With x consumed by this ONE node, its two gradients (through the LayerNorm and
+    through the residual) arrive together and are summed inside the LayerNorm backward kernel; through `layernorm128` autograd
+    accumulates them with a separate add over the (M, 128) tensor (12 such passes per training step)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        x = _c(x)
+        M = x.shape[0]
+        assert x.shape[1] == 128
+        y = torch.empty_like(x)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        with _lib.on(x.device):
+            check(_lib.load().dfb200_layernorm128_forward(M, ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), ptr(mean), ptr(rstd), stream()))
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        if dy is None:  # the normalised branch is unused: only the residual gradient flows
+            return dres, None, None
+        dx = torch.empty_like(x)
+        dg = zeros((128,), x.device)
+        db = zeros((128,), x.device)
+        with _lib.on(x.device):
+            check(_lib.load().dfb200_layernorm128_backward_residual(x.shape[0], ptr(x), ptr(_c(gamma)), ptr(mean), ptr(rstd), ptr(_c(dy)),
+                                                                    ptr(_c(dres) if dres is not None else None), ptr(dx), ptr(dg), ptr(db),
+                                                                    stream()))
+        return dx, dg, db
+
+
+def layernorm128_res(x, gamma, beta):
+    """-> (LayerNorm(x), x) with the residual's gradient folded into the LayerNorm backward (LayerNorm128ResFn).
+    DFB200_LN_RES=0 (A/B switch): plain LayerNorm128Fn, autograd accumulates the two gradients of x."""
+    if not _LN_RES:
+        return LayerNorm128Fn.apply(x, gamma, beta), x
+    return LayerNorm128ResFn.apply(x, gamma, beta)
+
+
 class GegluFn(Function):
     @staticmethod
     def forward(ctx, h):

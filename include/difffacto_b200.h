@@ -244,6 +244,11 @@ int dfb200_layernorm128_forward(long long M, const float* x, const float* gamma,
 int dfb200_layernorm128_backward(long long M, const float* x, const float* gamma, const float* mean, const float* rstd,
                                  const float* dy, float* dx, float* dgamma_accum, float* dbeta_accum,
                                  dfb200_stream_t stream);
+/* The same with dx += dres (M x 128, may be NULL): the gradient of the residual connection around the LayerNorm'd branch
+ * (attention.py:296-306: x = attn(norm(x)) + x) joins the LayerNorm backward instead of a separate accumulation pass. */
+int dfb200_layernorm128_backward_residual(long long M, const float* x, const float* gamma, const float* mean, const float* rstd,
+                                          const float* dy, const float* dres, float* dx, float* dgamma_accum, float* dbeta_accum,
+                                          dfb200_stream_t stream);
 /* GEGLU (attention.py:50-57): h (M, 2H) = [a | g] -> u (M, H) = a * gelu_erf(g); backward dh (M, 2H). */
 int dfb200_geglu_forward(long long M, int H, const float* h, float* u, dfb200_stream_t stream);
 int dfb200_geglu_backward(long long M, int H, const float* h, const float* du, float* dh, dfb200_stream_t stream);

@@ -323,3 +323,36 @@ def test_colsum_accumulate_vector_and_scalar_forms(M, N, ld):
     want = out.double() + X[:, :N].double().sum(0)
     _lib.check(_lib.load().dfb200_colsum_accumulate(M, N, _lib.ptr(X), ld, _lib.ptr(out), _lib.stream()))
     assert torch.allclose(out.double(), want, rtol=1e-5, atol=2e-4 * M ** 0.5)
+
+
+def test_layernorm_residual_node_equals_layernorm_plus_autograd_accumulation():
+    """T.layernorm128_res returns (LayerNorm(x), x): used as `x + f(LN(x))` it must give the values and gradients of the two-consumer
+    form (LayerNorm128Fn + autograd's accumulation), with either output unused as well."""
+    from difffacto_b200 import train_ops as T
+    torch.manual_seed(21)
+    M = 777
+    x0 = torch.randn(M, 128, device="cuda")
+    g0, b0 = torch.randn(128, device="cuda"), torch.randn(128, device="cuda")
+    w = torch.randn(128, 128, device="cuda") * 0.1
+    go = torch.randn(M, 128, device="cuda")
+    def run(fused):
+        x, g, b = (t.clone().requires_grad_(True) for t in (x0, g0, b0))
+        if fused:
+            a, r = T.layernorm128_res(x, g, b)
+        else:
+            a, r = T.layernorm128(x, g, b), x
+        y = T.linear(a, w, None, r)
+        y.backward(go)
+        return y.detach(), x.grad, g.grad, b.grad
+    for u, v in zip(run(True), run(False)):
+        assert torch.allclose(u, v, rtol=1e-5, atol=1e-5)
+    x = x0.clone().requires_grad_(True)
+    a, r = T.layernorm128_res(x, g0, b0)
+    (r * go).sum().backward()                      # only the pass-through output is used
+    assert torch.equal(x.grad, go)
+    x = x0.clone().requires_grad_(True)
+    a, r = T.layernorm128_res(x, g0, b0)
+    (a * go).sum().backward()                      # only the normalised output is used
+    x2 = x0.clone().requires_grad_(True)
+    (T.layernorm128(x2, g0, b0) * go).sum().backward()
+    assert torch.allclose(x.grad, x2.grad, rtol=1e-6, atol=1e-6)
